@@ -1,0 +1,318 @@
+"""ctypes binding of libgaunegf_b200.so (C ABI: include/gaunegf_b200.h).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is present, creating a
+context raises.  numpy in, numpy out; torch is only used (elsewhere) for device buffers and NCCL.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libgaunegf_b200.so")
+
+HOST, DEVICE = 0, 1
+ERR_SINGULAR = 3
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+SIGNATURES = {
+    "gnb_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "gnb_destroy": (C.c_int, [_vp]),
+    "gnb_last_error": (C.c_char_p, [_vp]),
+    "gnb_version": (C.c_char_p, []),
+    "gnb_set_stream": (C.c_int, [_vp, _vp]),
+    "gnb_set_workspace_limit": (C.c_int, [_vp, C.c_size_t]),
+    "gnb_launch_count": (C.c_int64, [_vp]),
+    "gnb_last_elim_ms": (C.c_double, [_vp]),
+    "gnb_set_timing": (C.c_int, [_vp, C.c_int]),
+    "gnb_set_system": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "gnb_sigma_clear": (C.c_int, [_vp]),
+    "gnb_sigma_set_dense0": (C.c_int, [_vp, _vp, C.c_int]),
+    "gnb_sigma_add_const_block": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "gnb_sigma_add_chain1d": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double,
+                                        C.c_double, C.c_int]),
+    "gnb_sigma_add_bethe": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double,
+                                      C.c_double, C.c_int]),
+    "gnb_sigma_eval": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "gnb_green": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "gnb_transmission": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "gnb_dos": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "gnb_gr_int": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "gnb_gless_int": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int]),
+    "gnb_green_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_int]),
+    "gnb_transmission_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
+    "gnb_dos_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, _vp]),
+    "gnb_gr_int_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp, C.c_int]),
+    "gnb_gless_int_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_int]),
+    "gnb_inverse_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int]),
+}
+
+
+def load_library(path=None):
+    """dlopen the in-tree library and bind every symbol the header declares."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: build it with `python -m gaunegf_b200.build` (nvcc, sm_100a). "
+            "gaunegf_b200 has no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def c128(a):
+    """contiguous complex128 view/copy (row-major) of an array-like"""
+    return np.ascontiguousarray(np.asarray(a), dtype=np.complex128)
+
+
+def ptr(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+class GnbError(RuntimeError):
+    pass
+
+
+class Context:
+    """One context per GPU / host thread; owns the device workspace."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.gnb_create(C.byref(h), int(device))
+        if rc != 0 or not h:
+            raise RuntimeError(
+                "gaunegf_b200: could not create a CUDA context on device %d (rc=%d). A B200 (sm_100a) "
+                "GPU is required; there is no CPU fallback." % (device, rc))
+        self.h = h
+        self.device = device
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc == 0:
+            return
+        msg = self.lib.gnb_last_error(self.h).decode()
+        if rc == ERR_SINGULAR:
+            raise np.linalg.LinAlgError(msg or "Singular matrix")
+        if rc == 2:
+            raise ValueError(msg)
+        raise GnbError(f"libgaunegf_b200 rc={rc}: {msg}")
+
+    # -- plumbing -------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self.check(self.lib.gnb_set_stream(self.h, _vp(cuda_stream)))
+
+    def set_workspace_limit(self, nbytes):
+        self.check(self.lib.gnb_set_workspace_limit(self.h, int(nbytes)))
+
+    def set_timing(self, on):
+        self.check(self.lib.gnb_set_timing(self.h, int(bool(on))))
+
+    @property
+    def launches(self):
+        return int(self.lib.gnb_launch_count(self.h))
+
+    @property
+    def last_elim_ms(self):
+        return float(self.lib.gnb_last_elim_ms(self.h))
+
+    # -- system / sigma -------------------------------------------------------------------
+    def set_system(self, F, S):
+        F, S = c128(F), c128(S)
+        assert F.shape == S.shape, "F and S must have the same shape"
+        assert F.ndim == 2 and F.shape[0] == F.shape[1], "F and S must be square matrices"
+        self.N = F.shape[0]
+        self.check(self.lib.gnb_set_system(self.h, self.N, ptr(F), ptr(S), HOST))
+
+    def set_system_device(self, N, F_ptr, S_ptr):
+        self.N = int(N)
+        self.check(self.lib.gnb_set_system(self.h, self.N, _vp(F_ptr), _vp(S_ptr), DEVICE))
+
+    def sigma_clear(self):
+        self.check(self.lib.gnb_sigma_clear(self.h))
+
+    def sigma_set_dense0(self, sig0):
+        sig0 = c128(sig0)
+        assert sig0.shape == (self.N, self.N)
+        self.check(self.lib.gnb_sigma_set_dense0(self.h, ptr(sig0), HOST))
+
+    def sigma_add_const_block(self, inds, blk):
+        inds = np.ascontiguousarray(inds, dtype=np.int32)
+        blk = c128(blk)
+        assert blk.shape == (len(inds), len(inds))
+        self.check(self.lib.gnb_sigma_add_const_block(self.h, len(inds), ptr(inds), ptr(blk)))
+
+    def sigma_add_chain1d(self, inds, alpha, Salpha, beta, Sbeta, tau, stau, eta, conv, relax, max_iter=2000):
+        inds = np.ascontiguousarray(inds, dtype=np.int32)
+        mats = [c128(m) for m in (alpha, Salpha, beta, Sbeta, tau, stau)]
+        n = len(inds)
+        for m in mats:
+            if m.shape != (n, n):
+                raise ValueError("chain1d: every contact matrix must be (len(inds), len(inds)); got %s" % (m.shape,))
+        self.check(self.lib.gnb_sigma_add_chain1d(self.h, n, ptr(inds), *[ptr(m) for m in mats],
+                                                  float(eta), float(conv), float(relax), int(max_iter)))
+
+    def sigma_add_bethe(self, atom_inds, nb_lists, H, Slist, Vlist, eta, conv, mix=0.5, max_iter=1000):
+        inds = np.ascontiguousarray(np.asarray(atom_inds).reshape(-1), dtype=np.int32)
+        natoms = len(nb_lists)
+        assert inds.size == natoms * 9
+        off = np.zeros(natoms + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(x) for x in nb_lists])
+        dirs = np.ascontiguousarray([d for x in nb_lists for d in x] or [0], dtype=np.int32)
+        H, Sl, Vl = c128(H), c128(Slist), c128(Vlist)
+        assert H.shape == (9, 9) and Sl.shape == (12, 9, 9) and Vl.shape == (12, 9, 9)
+        self.check(self.lib.gnb_sigma_add_bethe(self.h, natoms, ptr(inds), ptr(off), ptr(dirs), ptr(H), ptr(Sl),
+                                                ptr(Vl), float(eta), float(conv), float(mix), int(max_iter)))
+
+    def sigma_eval(self, contact, which, E, shape):
+        E = c128(np.atleast_1d(E))
+        M = E.size
+        out = np.empty((M,) + tuple(shape), dtype=np.complex128)
+        iters = np.zeros(M, dtype=np.int32)
+        diffs = np.zeros(M, dtype=np.float64)
+        self.check(self.lib.gnb_sigma_eval(self.h, int(contact), int(which), M, ptr(E), ptr(out), ptr(iters), ptr(diffs)))
+        return out, iters, diffs
+
+    # -- reductions ------------------------------------------------------------------------
+    def green(self, E):
+        E = c128(np.atleast_1d(E))
+        G = np.empty((E.size, self.N, self.N), dtype=np.complex128)
+        self.check(self.lib.gnb_green(self.h, E.size, ptr(E), ptr(G), HOST))
+        return G
+
+    def transmission(self, E, ca=0, cb=-1):
+        E = c128(np.atleast_1d(E))
+        T = np.empty(E.size, dtype=np.float64)
+        self.check(self.lib.gnb_transmission(self.h, E.size, ptr(E), int(ca), int(cb), ptr(T)))
+        return T
+
+    def dos(self, E, per_site=True):
+        E = c128(np.atleast_1d(E))
+        tot = np.empty(E.size, dtype=np.float64)
+        per = np.empty((E.size, self.N), dtype=np.float64) if per_site else None
+        self.check(self.lib.gnb_dos(self.h, E.size, ptr(E), ptr(tot), ptr(per)))
+        return tot, per
+
+    def gr_int(self, E, w, out_device_ptr=None):
+        E, w = c128(np.atleast_1d(E)), c128(np.atleast_1d(w))
+        assert E.size == w.size, "Elist and weights must have the same length"
+        if out_device_ptr is not None:
+            self.check(self.lib.gnb_gr_int(self.h, E.size, ptr(E), ptr(w), _vp(out_device_ptr), DEVICE))
+            return None
+        out = np.empty((self.N, self.N), dtype=np.complex128)
+        self.check(self.lib.gnb_gr_int(self.h, E.size, ptr(E), ptr(w), ptr(out), HOST))
+        return out
+
+    def gless_int(self, E, w, contact=-1, out_device_ptr=None):
+        E, w = c128(np.atleast_1d(E)), c128(np.atleast_1d(w))
+        assert E.size == w.size, "Elist and weights must have the same length"
+        if out_device_ptr is not None:
+            self.check(self.lib.gnb_gless_int(self.h, E.size, ptr(E), ptr(w), int(contact), _vp(out_device_ptr), DEVICE))
+            return None
+        out = np.empty((self.N, self.N), dtype=np.complex128)
+        self.check(self.lib.gnb_gless_int(self.h, E.size, ptr(E), ptr(w), int(contact), ptr(out), HOST))
+        return out
+
+    # -- dense (caller-evaluated sigma) variants -----------------------------------------------
+    def _dense(self, a, M):
+        if a is None:
+            return None, 0
+        a = c128(a)
+        if a.ndim == 2:
+            assert a.shape == (self.N, self.N)
+            return a, 0
+        assert a.shape == (M, self.N, self.N)
+        return a, self.N * self.N
+
+    def green_dense(self, E, sig):
+        E = c128(np.atleast_1d(E))
+        s, ss = self._dense(sig, E.size)
+        G = np.empty((E.size, self.N, self.N), dtype=np.complex128)
+        self.check(self.lib.gnb_green_dense(self.h, E.size, ptr(E), ptr(s), ss, ptr(G), HOST))
+        return G
+
+    def transmission_dense(self, E, sig, gam1, gam2):
+        E = c128(np.atleast_1d(E))
+        s, ss = self._dense(sig, E.size)
+        g1, s1 = self._dense(gam1, E.size)
+        g2, s2 = self._dense(gam2, E.size)
+        T = np.empty(E.size, dtype=np.float64)
+        self.check(self.lib.gnb_transmission_dense(self.h, E.size, ptr(E), ptr(s), ss, ptr(g1), s1, ptr(g2), s2, ptr(T)))
+        return T
+
+    def dos_dense(self, E, sig, per_site=True):
+        E = c128(np.atleast_1d(E))
+        s, ss = self._dense(sig, E.size)
+        tot = np.empty(E.size, dtype=np.float64)
+        per = np.empty((E.size, self.N), dtype=np.float64) if per_site else None
+        self.check(self.lib.gnb_dos_dense(self.h, E.size, ptr(E), ptr(s), ss, ptr(tot), ptr(per)))
+        return tot, per
+
+    def gr_int_dense(self, E, w, sig, out_device_ptr=None):
+        E, w = c128(np.atleast_1d(E)), c128(np.atleast_1d(w))
+        assert E.size == w.size, "Elist and weights must have the same length"
+        s, ss = self._dense(sig, E.size)
+        if out_device_ptr is not None:
+            self.check(self.lib.gnb_gr_int_dense(self.h, E.size, ptr(E), ptr(w), ptr(s), ss, _vp(out_device_ptr), DEVICE))
+            return None
+        out = np.empty((self.N, self.N), dtype=np.complex128)
+        self.check(self.lib.gnb_gr_int_dense(self.h, E.size, ptr(E), ptr(w), ptr(s), ss, ptr(out), HOST))
+        return out
+
+    def gless_int_dense(self, E, w, sig, gam, out_device_ptr=None):
+        E, w = c128(np.atleast_1d(E)), c128(np.atleast_1d(w))
+        assert E.size == w.size, "Elist and weights must have the same length"
+        s, ss = self._dense(sig, E.size)
+        g, gs = self._dense(gam, E.size)
+        if out_device_ptr is not None:
+            self.check(self.lib.gnb_gless_int_dense(self.h, E.size, ptr(E), ptr(w), ptr(s), ss, ptr(g), gs,
+                                                    _vp(out_device_ptr), DEVICE))
+            return None
+        out = np.empty((self.N, self.N), dtype=np.complex128)
+        self.check(self.lib.gnb_gless_int_dense(self.h, E.size, ptr(E), ptr(w), ptr(s), ss, ptr(g), gs, ptr(out), HOST))
+        return out
+
+    def inverse_batch(self, A):
+        A = c128(A)
+        single = A.ndim == 2
+        if single:
+            A = A[None]
+        assert A.ndim == 3 and A.shape[1] == A.shape[2]
+        out = np.empty_like(A)
+        self.check(self.lib.gnb_inverse_batch(self.h, A.shape[1], A.shape[0], ptr(A), ptr(out), HOST))
+        return out[0] if single else out
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context for the current GPU (LOCAL_RANK-aware under torchrun)."""
+    if device is None:
+        device = int(os.environ.get("GAUNEGF_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,642 @@
+// C ABI of libgaunegf_b200 (include/gaunegf_b200.h): context, chunked energy-grid drivers.
+// Host orchestration only — every floating-point operation of the path runs in the kernels of
+// gnb_elim.cu / gnb_reduce.cu / gnb_sigma.cu / gnb_small.cu.  There is no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gaunegf_b200.h"
+#include "gnb_ctx.h"
+
+int gnb_fail(gnb_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where) {
+    if (c) c->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + where;
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? GNB_ERR_NOMEM : GNB_ERR_CUDA;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+extern "C" const char* gnb_version(void) { return "gaunegf_b200 0.1 (sm_100a)"; }
+
+extern "C" int gnb_create(gnb_ctx** out, int device) {
+    if (!out) return GNB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return GNB_ERR_CUDA; }   // no CPU fallback
+    if (device < 0 || device >= ndev) return GNB_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GNB_ERR_CUDA; }
+    gnb_ctx* c = new gnb_ctx();
+    c->device = device;
+    if (gnb_kernels_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+        cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return GNB_ERR_CUDA;
+    }
+    *out = c;
+    return GNB_OK;
+}
+
+static void release_contact(Contact& ct) {
+    DevBuf* bufs[] = {&ct.d_inds, &ct.d_const, &ct.alpha, &ct.Salpha, &ct.beta, &ct.Sbeta, &ct.tau, &ct.stau,
+                      &ct.d_nb_off, &ct.d_nb_dirs, &ct.H, &ct.Slist, &ct.Vlist, &ct.blk, &ct.gam, &ct.iters,
+                      &ct.diffs, &ct.surf};
+    for (DevBuf* b : bufs) b->release();
+}
+
+extern "C" int gnb_destroy(gnb_ctx* c) {
+    if (!c) return GNB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& ct : c->contacts) release_contact(ct);
+    DevBuf* bufs[] = {&c->dF, &c->dS, &c->dSig0, &c->A, &c->Pws, &c->LU, &c->moves, &c->cand0, &c->cand1,
+                      &c->perm, &c->invperm, &c->info, &c->dE, &c->dW, &c->G, &c->Y, &c->Z, &c->Xr, &c->out,
+                      &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
+                      &c->in_stage, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
+    for (DevBuf* b : bufs) b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return GNB_OK;
+}
+
+extern "C" const char* gnb_last_error(const gnb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int gnb_set_stream(gnb_ctx* c, void* s) { if (!c) return GNB_ERR_ARG; c->stream = (cudaStream_t)s; return GNB_OK; }
+extern "C" int gnb_set_workspace_limit(gnb_ctx* c, size_t bytes) {
+    if (!c || bytes < ((size_t)64 << 20)) return gnb_fail(c, GNB_ERR_ARG, "workspace limit must be >= 64 MiB");
+    c->ws_limit = bytes;
+    return GNB_OK;
+}
+extern "C" int64_t gnb_launch_count(const gnb_ctx* c) { return c ? c->launches : 0; }
+extern "C" double gnb_last_elim_ms(const gnb_ctx* c) { return c ? c->elim_ms : 0.0; }
+extern "C" int gnb_set_timing(gnb_ctx* c, int on) { if (!c) return GNB_ERR_ARG; c->timing = on != 0; return GNB_OK; }
+
+static int put(gnb_ctx* c, DevBuf& buf, const void* src, size_t bytes, int loc) {
+    GNB_CK(buf.ensure(bytes));
+    GNB_CK(cudaMemcpyAsync(buf.p, src, bytes, loc == GNB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           c->stream));
+    return GNB_OK;
+}
+
+extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* S, int loc) {
+    if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
+    cudaSetDevice(c->device);
+    if (N != c->N) {                      // a new size invalidates the self-energy description
+        for (auto& ct : c->contacts) release_contact(ct);
+        c->contacts.clear();
+        c->has_sig0 = false;
+    }
+    c->N = N;
+    const size_t bytes = (size_t)N * N * sizeof(cplx);
+    int rc;
+    if ((rc = put(c, c->dF, F, bytes, loc))) return rc;
+    if ((rc = put(c, c->dS, S, bytes, loc))) return rc;
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    return GNB_OK;
+}
+
+extern "C" int gnb_sigma_clear(gnb_ctx* c) {
+    if (!c) return GNB_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& ct : c->contacts) release_contact(ct);
+    c->contacts.clear();
+    c->has_sig0 = false;
+    return GNB_OK;
+}
+
+extern "C" int gnb_sigma_set_dense0(gnb_ctx* c, const double* sig0, int loc) {
+    if (!c || c->N <= 0 || !sig0) return gnb_fail(c, GNB_ERR_ARG, "sigma_set_dense0: set_system first");
+    cudaSetDevice(c->device);
+    int rc = put(c, c->dSig0, sig0, (size_t)c->N * c->N * sizeof(cplx), loc);
+    if (rc) return rc;
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    c->has_sig0 = true;
+    return GNB_OK;
+}
+
+static int check_inds(gnb_ctx* c, int n, const int32_t* inds) {
+    if (n <= 0 || !inds) return gnb_fail(c, GNB_ERR_ARG, "contact: empty index list");
+    for (int i = 0; i < n; i++)
+        if (inds[i] < 0 || inds[i] >= c->N) return gnb_fail(c, GNB_ERR_ARG, "contact: orbital index out of range");
+    return GNB_OK;
+}
+
+extern "C" int gnb_sigma_add_const_block(gnb_ctx* c, int nc, const int32_t* inds, const double* blk) {
+    if (!c || c->N <= 0 || !blk) return gnb_fail(c, GNB_ERR_ARG, "sigma_add_const_block: bad arguments");
+    cudaSetDevice(c->device);
+    int rc = check_inds(c, nc, inds);
+    if (rc) return rc;
+    c->contacts.emplace_back();
+    Contact& ct = c->contacts.back();
+    ct.kind = GNB_C_CONST;
+    ct.nc = nc;
+    ct.h_inds.assign(inds, inds + nc);
+    if ((rc = put(c, ct.d_inds, inds, nc * sizeof(int), GNB_HOST))) return rc;
+    if ((rc = put(c, ct.d_const, blk, (size_t)nc * nc * sizeof(cplx), GNB_HOST))) return rc;
+    GNB_CK(ct.gam.ensure((size_t)nc * nc * sizeof(cplx)));
+    gnb_launch_gamma_from_sigma(c->stream, 1, ct.d_const.as<cplx>(), 0, nc, ct.gam.as<cplx>());
+    c->launches++;
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    return GNB_OK;
+}
+
+extern "C" int gnb_sigma_add_chain1d(gnb_ctx* c, int nc, const int32_t* inds, const double* alpha,
+                                     const double* Salpha, const double* beta, const double* Sbeta,
+                                     const double* tau, const double* stau, double eta, double conv,
+                                     double relax, int max_iter) {
+    if (!c || c->N <= 0 || !alpha || !Salpha || !beta || !Sbeta || !tau || !stau || max_iter < 0)
+        return gnb_fail(c, GNB_ERR_ARG, "sigma_add_chain1d: bad arguments");
+    cudaSetDevice(c->device);
+    int rc = check_inds(c, nc, inds);
+    if (rc) return rc;
+    c->contacts.emplace_back();
+    Contact& ct = c->contacts.back();
+    ct.kind = GNB_C_CHAIN1D;
+    ct.nc = nc;
+    ct.h_inds.assign(inds, inds + nc);
+    ct.eta = eta; ct.conv = conv; ct.relax = relax; ct.max_iter = max_iter;
+    const size_t bytes = (size_t)nc * nc * sizeof(cplx);
+    if ((rc = put(c, ct.d_inds, inds, nc * sizeof(int), GNB_HOST))) return rc;
+    const double* src[6] = {alpha, Salpha, beta, Sbeta, tau, stau};
+    DevBuf* dst[6] = {&ct.alpha, &ct.Salpha, &ct.beta, &ct.Sbeta, &ct.tau, &ct.stau};
+    for (int i = 0; i < 6; i++)
+        if ((rc = put(c, *dst[i], src[i], bytes, GNB_HOST))) return rc;
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    return GNB_OK;
+}
+
+extern "C" int gnb_sigma_add_bethe(gnb_ctx* c, int natoms, const int32_t* inds, const int32_t* nb_off,
+                                   const int32_t* nb_dirs, const double* H, const double* Slist,
+                                   const double* Vlist, double eta, double conv, double mix, int max_iter) {
+    if (!c || c->N <= 0 || natoms <= 0 || !nb_off || !H || !Slist || !Vlist)
+        return gnb_fail(c, GNB_ERR_ARG, "sigma_add_bethe: bad arguments");
+    cudaSetDevice(c->device);
+    int rc = check_inds(c, natoms * 9, inds);
+    if (rc) return rc;
+    for (int i = 0; i < nb_off[natoms]; i++)
+        if (nb_dirs[i] < 0 || nb_dirs[i] >= 9) return gnb_fail(c, GNB_ERR_ARG, "bethe: neighbour direction must be in 0..8");
+    c->contacts.emplace_back();
+    Contact& ct = c->contacts.back();
+    ct.kind = GNB_C_BETHE;
+    ct.natoms = natoms;
+    ct.nc = natoms * 9;
+    ct.h_inds.assign(inds, inds + ct.nc);
+    ct.nb_off.assign(nb_off, nb_off + natoms + 1);
+    ct.nb_dirs.assign(nb_dirs, nb_dirs + nb_off[natoms]);
+    ct.eta = eta; ct.conv = conv; ct.mix = mix; ct.max_iter = max_iter;
+    if ((rc = put(c, ct.d_inds, inds, ct.nc * sizeof(int), GNB_HOST))) return rc;
+    if ((rc = put(c, ct.d_nb_off, nb_off, (natoms + 1) * sizeof(int), GNB_HOST))) return rc;
+    if ((rc = put(c, ct.d_nb_dirs, nb_dirs, std::max(1, nb_off[natoms]) * sizeof(int), GNB_HOST))) return rc;
+    if ((rc = put(c, ct.H, H, 81 * sizeof(cplx), GNB_HOST))) return rc;
+    if ((rc = put(c, ct.Slist, Slist, 12 * 81 * sizeof(cplx), GNB_HOST))) return rc;
+    if ((rc = put(c, ct.Vlist, Vlist, 12 * 81 * sizeof(cplx), GNB_HOST))) return rc;
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    return GNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc) {
+    GnbElimWork w{};
+    *rc = GNB_OK;
+    const int cand_stride = std::max(GNB_NB, (N + 255) / 256 * GNB_NB);
+    cudaError_t e = cudaSuccess;
+    auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
+    need(c->cand0, (size_t)M * cand_stride * sizeof(int));
+    need(c->cand1, (size_t)M * cand_stride * sizeof(int));
+    need(c->LU, (size_t)M * GNB_NB * GNB_NB * sizeof(cplx));
+    need(c->moves, (size_t)M * GNB_MOVES_STRIDE * sizeof(int));
+    need(c->info, sizeof(int) * 4);
+    if (jordan) {
+        need(c->perm, (size_t)M * N * sizeof(int));
+        need(c->invperm, (size_t)M * N * sizeof(int));
+        need(c->Pws, (size_t)M * N * GNB_NB * sizeof(cplx));
+    }
+    if (e != cudaSuccess) { *rc = gnb_cuda_fail(c, e, "workspace allocation"); return w; }
+    w.cand0 = c->cand0.as<int>(); w.cand1 = c->cand1.as<int>(); w.cand_stride = cand_stride;
+    w.LU = c->LU.as<cplx>(); w.moves = c->moves.as<int>();
+    w.perm = c->perm.as<int>(); w.perm_stride = N; w.Pws = c->Pws.as<cplx>();
+    w.info = c->info.as<int>();
+    return w;
+}
+
+static int begin_call(gnb_ctx* c) {
+    cudaSetDevice(c->device);
+    c->elim_ms = 0.0;
+    GNB_CK(c->info.ensure(sizeof(int) * 4));
+    GNB_CK(cudaMemsetAsync(c->info.p, 0, sizeof(int) * 4, c->stream));
+    return GNB_OK;
+}
+
+static int end_call(gnb_ctx* c) {
+    int info = 0;
+    GNB_CK(cudaMemcpyAsync(&info, c->info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    GNB_CK(cudaGetLastError());
+    if (info) return gnb_fail(c, GNB_ERR_SINGULAR, "Singular matrix");
+    return GNB_OK;
+}
+
+// timed elimination (events on the context's stream; accumulates into elim_ms when timing is on)
+static int run_eliminate(gnb_ctx* c, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan) {
+    int rc;
+    GnbElimWork w = gnb_elim_work(c, M, N, jordan != 0, &rc);
+    if (rc) return rc;
+    if (c->timing) GNB_CK(cudaEventRecord(c->ev0, c->stream));
+    c->launches += gnb_eliminate(c->stream, M, N, naug, A, strideA, ld, jordan, w);
+    if (c->timing) {
+        GNB_CK(cudaEventRecord(c->ev1, c->stream));
+        GNB_CK(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        GNB_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->elim_ms += ms;
+    }
+    GNB_CK(cudaGetLastError());
+    return GNB_OK;
+}
+
+static int chunk_size(gnb_ctx* c, int M, size_t bytes_per_energy) {
+    size_t m = c->ws_limit / std::max<size_t>(bytes_per_energy, 1);
+    m = std::max<size_t>(1, std::min<size_t>(m, 8192));
+    return (int)std::min<size_t>(m, (size_t)M);
+}
+
+static int resolve_contact(gnb_ctx* c, int idx) {
+    const int n = (int)c->contacts.size();
+    if (idx < 0) idx += n;
+    return (idx >= 0 && idx < n) ? idx : -1;
+}
+
+// Sigma blocks (and Gammas) of every contact for the energies of this chunk
+static int prepare_sigma(gnb_ctx* c, int M, const cplx* dE, int want_gamma) {
+    for (auto& ct : c->contacts) {
+        if (ct.kind == GNB_C_CONST) {
+            ct.blk_ptr = ct.d_const.as<cplx>(); ct.blk_stride = 0;
+            ct.gam_ptr = ct.gam.as<cplx>(); ct.gam_stride = 0;
+        } else {
+            int rc = gnb_contact_eval(c, ct, M, dE, want_gamma);
+            if (rc) return rc;
+        }
+    }
+    return GNB_OK;
+}
+
+// A_k = E_k S - F - Sigma_tot(E_k) for the chunk, from the context's self-energy description or
+// from caller-provided dense matrices.
+static int assemble_chunk(gnb_ctx* c, int M, const cplx* dE, cplx* A, long strideA, int ld, bool use_desc,
+                          const cplx* sig_const, const cplx* sig_batch) {
+    const int N = c->N;
+    const cplx* s0 = use_desc ? (c->has_sig0 ? c->dSig0.as<cplx>() : nullptr) : sig_const;
+    gnb_launch_assemble(c->stream, M, A, strideA, ld, N, c->dF.as<cplx>(), c->dS.as<cplx>(), s0, sig_batch,
+                        (long)N * N, dE);
+    c->launches++;
+    if (use_desc)
+        for (auto& ct : c->contacts) {
+            gnb_launch_scatter_sub(c->stream, M, A, strideA, ld, ct.d_inds.as<int>(), ct.nc, ct.blk_ptr, ct.blk_stride);
+            c->launches++;
+        }
+    GNB_CK(cudaGetLastError());
+    return GNB_OK;
+}
+
+struct DenseSrc {            // caller-provided per-energy (stride != 0) or constant (stride 0) dense matrix, host
+    const double* p; long stride;
+};
+
+static int stage_dense(gnb_ctx* c, DevBuf& buf, const DenseSrc& s, int k0, int m, const cplx** d_const,
+                       const cplx** d_batch) {
+    const size_t nn = (size_t)c->N * c->N;
+    *d_const = nullptr; *d_batch = nullptr;
+    if (!s.p) return GNB_OK;
+    if (s.stride == 0) {
+        int rc = put(c, buf, s.p, nn * sizeof(cplx), GNB_HOST);
+        *d_const = buf.as<cplx>();
+        return rc;
+    }
+    if (s.stride != (long)nn) return gnb_fail(c, GNB_ERR_ARG, "dense stride must be 0 or N*N");
+    int rc = put(c, buf, s.p + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), GNB_HOST);
+    *d_batch = buf.as<cplx>();
+    return rc;
+}
+
+static int get_out(gnb_ctx* c, double* out, int loc, cplx** d_out) {
+    if (loc == GNB_DEVICE) { *d_out = reinterpret_cast<cplx*>(out); return GNB_OK; }
+    GNB_CK(c->out.ensure((size_t)c->N * c->N * sizeof(cplx)));
+    *d_out = c->out.as<cplx>();
+    return GNB_OK;
+}
+
+static int put_chunk_scalars(gnb_ctx* c, const double* E, const double* w, int k0, int m) {
+    int rc;
+    if ((rc = put(c, c->dE, E + 2 * (size_t)k0, (size_t)m * sizeof(cplx), GNB_HOST))) return rc;
+    if (w && (rc = put(c, c->dW, w + 2 * (size_t)k0, (size_t)m * sizeof(cplx), GNB_HOST))) return rc;
+    return GNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Full-inverse family: green / dos / gr_int (+ dense variants)
+// ---------------------------------------------------------------------------------------------
+enum { MODE_GREEN = 0, MODE_DOS = 1, MODE_GRINT = 2, MODE_T_DENSE = 3, MODE_GLESS_DENSE = 4 };
+
+static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double* w, bool use_desc,
+                      DenseSrc sig, DenseSrc g1, DenseSrc g2, double* out0, double* out1, int loc) {
+    if (!c || c->N <= 0) return gnb_fail(c, GNB_ERR_ARG, "set_system first");
+    if (M < 0 || (M > 0 && !E)) return gnb_fail(c, GNB_ERR_ARG, "bad energy list");
+    int rc = begin_call(c);
+    if (rc) return rc;
+    const int N = c->N, ld = round_up(N, 2);
+    const size_t nn = (size_t)N * N;
+    const bool needG = mode == MODE_GREEN || mode == MODE_T_DENSE || mode == MODE_GLESS_DENSE;
+    size_t per = (size_t)N * ld * 16 + (size_t)N * GNB_NB * 16 + 8 * (size_t)N + 16384;
+    if (needG && !(mode == MODE_GREEN && loc == GNB_DEVICE)) per += nn * 16;
+    if (mode == MODE_T_DENSE) per += 2 * nn * 16;
+    if (mode == MODE_GLESS_DENSE) per += nn * 16;
+    if (sig.p && sig.stride) per += nn * 16;
+    if (g1.p && g1.stride) per += nn * 16;
+    if (g2.p && g2.stride) per += nn * 16;
+    const int Mc = chunk_size(c, std::max(M, 1), per);
+    cplx* d_out = nullptr;
+    if (mode == MODE_GRINT || mode == MODE_GLESS_DENSE) {
+        if ((rc = get_out(c, out0, loc, &d_out))) return rc;
+        if (M == 0) GNB_CK(cudaMemsetAsync(d_out, 0, nn * sizeof(cplx), c->stream));
+    }
+    for (int k0 = 0; k0 < M; k0 += Mc) {
+        const int m = std::min(Mc, M - k0);
+        if ((rc = put_chunk_scalars(c, E, w, k0, m))) return rc;
+        const cplx* dE = c->dE.as<cplx>();
+        GNB_CK(c->A.ensure((size_t)m * N * ld * sizeof(cplx)));
+        cplx* A = c->A.as<cplx>();
+        const long strideA = (long)N * ld;
+        const cplx *sc = nullptr, *sb = nullptr;
+        if (use_desc) {
+            if ((rc = prepare_sigma(c, m, dE, 0))) return rc;
+        } else if ((rc = stage_dense(c, c->sigB, sig, k0, m, &sc, &sb))) return rc;
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, use_desc, sc, sb))) return rc;
+        if ((rc = run_eliminate(c, m, N, 0, A, strideA, ld, 1))) return rc;
+        gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), N, N);
+        c->launches++;
+        const int* inv = c->invperm.as<int>();
+        cplx* G = nullptr;
+        if (needG) {
+            if (mode == MODE_GREEN && loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(out0) + (size_t)k0 * nn;
+            else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
+            gnb_launch_unpermute(c->stream, m, N, A, strideA, ld, inv, N, G, (long)nn);
+            c->launches++;
+        }
+        if (mode == MODE_GREEN) {
+            if (loc == GNB_HOST)
+                GNB_CK(cudaMemcpyAsync(out0 + (size_t)k0 * nn * 2, G, (size_t)m * nn * sizeof(cplx),
+                                       cudaMemcpyDeviceToHost, c->stream));
+        } else if (mode == MODE_DOS) {
+            GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
+            if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
+            gnb_launch_dos(c->stream, m, N, A, strideA, ld, inv, N, c->dDosT.as<double>(),
+                           out1 ? c->dDosP.as<double>() : nullptr);
+            c->launches++;
+            GNB_CK(cudaMemcpyAsync(out0 + k0, c->dDosT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if (out1)
+                GNB_CK(cudaMemcpyAsync(out1 + (size_t)k0 * N, c->dDosP.p, (size_t)m * N * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->stream));
+        } else if (mode == MODE_GRINT) {
+            gnb_launch_weighted_sum(c->stream, m, N, A, strideA, ld, inv, N, c->dW.as<cplx>(), d_out, k0 > 0);
+            c->launches++;
+        } else if (mode == MODE_T_DENSE) {
+            const cplx *g1c, *g1b, *g2c, *g2b;
+            if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &g1c, &g1b))) return rc;
+            if ((rc = stage_dense(c, c->gam2B, g2, k0, m, &g2c, &g2b))) return rc;
+            GNB_CK(c->Y.ensure((size_t)m * nn * sizeof(cplx)));
+            GNB_CK(c->Z.ensure((size_t)m * nn * sizeof(cplx)));
+            GNB_CK(c->dT.ensure((size_t)m * sizeof(double)));
+            GnbGemmArgs g{};
+            g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = N; g.kdim = N; g.skip_lo = g.skip_hi = -1;
+            g.zero_init = 1; g.plus = 1;
+            g.C = c->Y.as<cplx>(); g.strideC = nn; g.ldc = N;          // Y = G Gamma2
+            g.P = G; g.strideP = nn; g.ldp = N;
+            g.W = g2b ? g2b : g2c; g.strideW = g2b ? (long)nn : 0; g.ldw = N;
+            gnb_launch_gemm(c->stream, g, m, false, false);
+            g.C = c->Z.as<cplx>();                                      // Z = Gamma1 Y
+            g.P = g1b ? g1b : g1c; g.strideP = g1b ? (long)nn : 0; g.ldp = N;
+            g.W = c->Y.as<cplx>(); g.strideW = nn; g.ldw = N;
+            gnb_launch_gemm(c->stream, g, m, false, false);
+            gnb_launch_trace_dot(c->stream, m, c->Z.as<cplx>(), G, (long)nn, (int)nn, c->dT.as<double>());
+            c->launches += 3;
+            GNB_CK(cudaMemcpyAsync(out0 + k0, c->dT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        } else if (mode == MODE_GLESS_DENSE) {
+            const cplx *gc, *gb;
+            if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &gc, &gb))) return rc;
+            GNB_CK(c->Y.ensure((size_t)m * nn * sizeof(cplx)));
+            GnbGemmArgs g{};
+            g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = N; g.kdim = N; g.skip_lo = g.skip_hi = -1;
+            g.zero_init = 1; g.plus = 1;
+            g.C = c->Y.as<cplx>(); g.strideC = nn; g.ldc = N;          // Y = G Gamma
+            g.P = G; g.strideP = nn; g.ldp = N;
+            g.W = gb ? gb : gc; g.strideW = gb ? (long)nn : 0; g.ldw = N;
+            gnb_launch_gemm(c->stream, g, m, false, false);
+            g.C = d_out; g.strideC = 0; g.ldc = N;                      // out += sum_b w_b Y_b G_b^H
+            g.P = c->Y.as<cplx>(); g.strideP = nn; g.ldp = N;
+            g.W = G; g.strideW = nn; g.ldw = N;
+            g.zero_init = k0 == 0; g.wscale = c->dW.as<cplx>(); g.nbatch_k = m;
+            gnb_launch_gemm(c->stream, g, m, true, true);
+            c->launches += 2;
+        }
+        GNB_CK(cudaGetLastError());
+        if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));   // staging buffers are reused per chunk
+    }
+    if ((mode == MODE_GRINT || mode == MODE_GLESS_DENSE) && loc == GNB_HOST)
+        GNB_CK(cudaMemcpyAsync(out0, d_out, nn * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    return end_call(c);
+}
+
+extern "C" int gnb_green(gnb_ctx* c, int M, const double* E, double* G, int loc) {
+    return run_jordan(c, MODE_GREEN, M, E, nullptr, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, G, nullptr, loc);
+}
+extern "C" int gnb_dos(gnb_ctx* c, int M, const double* E, double* tot, double* per_site) {
+    return run_jordan(c, MODE_DOS, M, E, nullptr, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, tot, per_site, GNB_HOST);
+}
+extern "C" int gnb_gr_int(gnb_ctx* c, int M, const double* E, const double* w, double* out, int loc) {
+    if (M > 0 && !w) return gnb_fail(c, GNB_ERR_ARG, "weights required");
+    return run_jordan(c, MODE_GRINT, M, E, w, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, out, nullptr, loc);
+}
+extern "C" int gnb_green_dense(gnb_ctx* c, int M, const double* E, const double* sig, long ss, double* G, int loc) {
+    return run_jordan(c, MODE_GREEN, M, E, nullptr, false, {sig, ss}, {nullptr, 0}, {nullptr, 0}, G, nullptr, loc);
+}
+extern "C" int gnb_dos_dense(gnb_ctx* c, int M, const double* E, const double* sig, long ss, double* tot, double* per) {
+    return run_jordan(c, MODE_DOS, M, E, nullptr, false, {sig, ss}, {nullptr, 0}, {nullptr, 0}, tot, per, GNB_HOST);
+}
+extern "C" int gnb_gr_int_dense(gnb_ctx* c, int M, const double* E, const double* w, const double* sig, long ss,
+                                double* out, int loc) {
+    if (M > 0 && !w) return gnb_fail(c, GNB_ERR_ARG, "weights required");
+    return run_jordan(c, MODE_GRINT, M, E, w, false, {sig, ss}, {nullptr, 0}, {nullptr, 0}, out, nullptr, loc);
+}
+extern "C" int gnb_transmission_dense(gnb_ctx* c, int M, const double* E, const double* sig, long ss,
+                                      const double* gam1, long s1, const double* gam2, long s2, double* T) {
+    if (!gam1 || !gam2) return gnb_fail(c, GNB_ERR_ARG, "gamma matrices required");
+    return run_jordan(c, MODE_T_DENSE, M, E, nullptr, false, {sig, ss}, {gam1, s1}, {gam2, s2}, T, nullptr, GNB_HOST);
+}
+extern "C" int gnb_gless_int_dense(gnb_ctx* c, int M, const double* E, const double* w, const double* sig, long ss,
+                                   const double* gam, long gs, double* out, int loc) {
+    if ((M > 0 && !w) || !gam) return gnb_fail(c, GNB_ERR_ARG, "weights and gamma required");
+    return run_jordan(c, MODE_GLESS_DENSE, M, E, w, false, {sig, ss}, {gam, gs}, {nullptr, 0}, out, nullptr, loc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Contact-column family (FORWARD mode): transmission / gless_int on the low-rank Gammas
+// ---------------------------------------------------------------------------------------------
+extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int cb_, double* T) {
+    if (!c || c->N <= 0) return gnb_fail(c, GNB_ERR_ARG, "set_system first");
+    const int ca = resolve_contact(c, ca_), cb = resolve_contact(c, cb_);
+    if (ca < 0 || cb < 0) return gnb_fail(c, GNB_ERR_ARG, "transmission: invalid contact index");
+    if (M < 0 || (M > 0 && (!E || !T))) return gnb_fail(c, GNB_ERR_ARG, "bad energy list");
+    int rc = begin_call(c);
+    if (rc) return rc;
+    const int N = c->N;
+    const int n1 = c->contacts[ca].nc, n2 = c->contacts[cb].nc;
+    const int ld = round_up(N + n2, 2);
+    const size_t per = (size_t)N * ld * 16 + 3 * (size_t)n1 * n2 * 16 + 16384 +
+                       2 * ((size_t)n1 * n1 + (size_t)n2 * n2) * 16 * 4;
+    const int Mc = chunk_size(c, std::max(M, 1), per);
+    for (int k0 = 0; k0 < M; k0 += Mc) {
+        const int m = std::min(Mc, M - k0);
+        if ((rc = put_chunk_scalars(c, E, nullptr, k0, m))) return rc;
+        const cplx* dE = c->dE.as<cplx>();
+        GNB_CK(c->A.ensure((size_t)m * N * ld * sizeof(cplx)));
+        cplx* A = c->A.as<cplx>();
+        const long strideA = (long)N * ld;
+        if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
+        Contact& A1 = c->contacts[ca];
+        Contact& A2 = c->contacts[cb];
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr))) return rc;
+        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, A2.d_inds.as<int>(), n2);
+        c->launches++;
+        if ((rc = run_eliminate(c, m, N, n2, A, strideA, ld, 0))) return rc;
+        const long s12 = (long)n1 * n2;
+        GNB_CK(c->Xr.ensure((size_t)m * s12 * sizeof(cplx)));
+        GNB_CK(c->Y.ensure((size_t)m * s12 * sizeof(cplx)));
+        GNB_CK(c->Z.ensure((size_t)m * s12 * sizeof(cplx)));
+        GNB_CK(c->dT.ensure((size_t)m * sizeof(double)));
+        gnb_launch_gather_rows(c->stream, m, A + N, strideA, ld, A1.d_inds.as<int>(), n1, n2, c->Xr.as<cplx>(), s12);
+        GnbGemmArgs g{};
+        g.skip_lo = g.skip_hi = -1; g.zero_init = 1; g.plus = 1;
+        g.ilo = 0; g.ihi = n1; g.jlo = 0; g.jhi = n2;
+        g.C = c->Y.as<cplx>(); g.strideC = s12; g.ldc = n2;            // Y = G12 Gamma2
+        g.P = c->Xr.as<cplx>(); g.strideP = s12; g.ldp = n2;
+        g.W = A2.gam_ptr; g.strideW = A2.gam_stride; g.ldw = n2; g.kdim = n2;
+        gnb_launch_gemm(c->stream, g, m, false, false);
+        g.C = c->Z.as<cplx>();                                          // Z = Gamma1 Y
+        g.P = A1.gam_ptr; g.strideP = A1.gam_stride; g.ldp = n1;
+        g.W = c->Y.as<cplx>(); g.strideW = s12; g.ldw = n2; g.kdim = n1;
+        gnb_launch_gemm(c->stream, g, m, false, false);
+        gnb_launch_trace_dot(c->stream, m, c->Z.as<cplx>(), c->Xr.as<cplx>(), s12, (int)s12, c->dT.as<double>());
+        c->launches += 4;
+        GNB_CK(cudaMemcpyAsync(T + k0, c->dT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GNB_CK(cudaGetLastError());
+        if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));
+    }
+    return end_call(c);
+}
+
+extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w, int contact, double* out, int loc) {
+    if (!c || c->N <= 0) return gnb_fail(c, GNB_ERR_ARG, "set_system first");
+    if (c->contacts.empty()) return gnb_fail(c, GNB_ERR_ARG, "gless_int: no contacts described (use gnb_gless_int_dense)");
+    if (M < 0 || (M > 0 && (!E || !w)) || !out) return gnb_fail(c, GNB_ERR_ARG, "bad arguments");
+    std::vector<int> use;
+    if (contact == -1) for (int i = 0; i < (int)c->contacts.size(); i++) use.push_back(i);
+    else {
+        if (contact < 0 || contact >= (int)c->contacts.size()) return gnb_fail(c, GNB_ERR_ARG, "gless_int: invalid contact");
+        use.push_back(contact);
+    }
+    int rc = begin_call(c);
+    if (rc) return rc;
+    const int N = c->N;
+    std::vector<int> cols, off;
+    int nmax = 0;
+    for (int ci : use) {
+        off.push_back((int)cols.size());
+        cols.insert(cols.end(), c->contacts[ci].h_inds.begin(), c->contacts[ci].h_inds.end());
+        nmax = std::max(nmax, c->contacts[ci].nc);
+    }
+    const int naug = (int)cols.size();
+    const int ld = round_up(N + naug, 2);
+    if ((rc = put(c, c->cols, cols.data(), cols.size() * sizeof(int), GNB_HOST))) return rc;
+    cplx* d_out = nullptr;
+    if ((rc = get_out(c, out, loc, &d_out))) return rc;
+    if (M == 0) GNB_CK(cudaMemsetAsync(d_out, 0, (size_t)N * N * sizeof(cplx), c->stream));
+    const size_t per = (size_t)N * ld * 16 + (size_t)N * nmax * 16 + 16384 + 8 * (size_t)naug * nmax * 16;
+    const int Mc = chunk_size(c, std::max(M, 1), per);
+    bool first = true;
+    for (int k0 = 0; k0 < M; k0 += Mc) {
+        const int m = std::min(Mc, M - k0);
+        if ((rc = put_chunk_scalars(c, E, w, k0, m))) return rc;
+        const cplx* dE = c->dE.as<cplx>();
+        GNB_CK(c->A.ensure((size_t)m * N * ld * sizeof(cplx)));
+        cplx* A = c->A.as<cplx>();
+        const long strideA = (long)N * ld;
+        if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr))) return rc;
+        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, c->cols.as<int>(), naug);
+        c->launches++;
+        if ((rc = run_eliminate(c, m, N, naug, A, strideA, ld, 0))) return rc;
+        GNB_CK(c->Y.ensure((size_t)m * N * nmax * sizeof(cplx)));
+        for (size_t u = 0; u < use.size(); u++) {
+            Contact& ct = c->contacts[use[u]];
+            const int nc = ct.nc;
+            const cplx* X = A + N + off[u];
+            GnbGemmArgs g{};
+            g.skip_lo = g.skip_hi = -1; g.zero_init = 1; g.plus = 1;
+            g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = nc; g.kdim = nc;
+            g.C = c->Y.as<cplx>(); g.strideC = (long)N * nc; g.ldc = nc;   // Y = G[:,C] Gamma_c
+            g.P = X; g.strideP = strideA; g.ldp = ld;
+            g.W = ct.gam_ptr; g.strideW = ct.gam_stride; g.ldw = nc;
+            gnb_launch_gemm(c->stream, g, m, false, false);
+            g.C = d_out; g.strideC = 0; g.ldc = N;                          // out += sum_b w_b Y_b G[:,C]^H
+            g.jhi = N;
+            g.P = c->Y.as<cplx>(); g.strideP = (long)N * nc; g.ldp = nc;
+            g.W = X; g.strideW = strideA; g.ldw = ld;
+            g.zero_init = first ? 1 : 0; g.wscale = c->dW.as<cplx>(); g.nbatch_k = m;
+            gnb_launch_gemm(c->stream, g, m, true, true);
+            c->launches += 2;
+            first = false;
+        }
+        GNB_CK(cudaGetLastError());
+        if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));
+    }
+    if (loc == GNB_HOST)
+        GNB_CK(cudaMemcpyAsync(out, d_out, (size_t)N * N * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    return end_call(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// utils.inv drop-in: batched inverse of arbitrary matrices
+// ---------------------------------------------------------------------------------------------
+extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, double* Aout, int loc) {
+    if (!c || n <= 0 || M < 0 || (M > 0 && (!Ain || !Aout))) return gnb_fail(c, GNB_ERR_ARG, "inverse_batch: bad arguments");
+    int rc = begin_call(c);
+    if (rc) return rc;
+    const size_t nn = (size_t)n * n;
+    const size_t per = 2 * nn * 16 + (size_t)n * GNB_NB * 16 + 8 * (size_t)n + 16384;
+    const int Mc = chunk_size(c, std::max(M, 1), per);
+    for (int k0 = 0; k0 < M; k0 += Mc) {
+        const int m = std::min(Mc, M - k0);
+        if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;
+        cplx* A = c->A.as<cplx>();
+        if ((rc = run_eliminate(c, m, n, 0, A, (long)nn, n, 1))) return rc;
+        gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), n, n);
+        cplx* G;
+        if (loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(Aout) + (size_t)k0 * nn;
+        else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
+        gnb_launch_unpermute(c->stream, m, n, A, (long)nn, n, c->invperm.as<int>(), n, G, (long)nn);
+        c->launches += 2;
+        if (loc == GNB_HOST)
+            GNB_CK(cudaMemcpyAsync(Aout + (size_t)k0 * nn * 2, G, (size_t)m * nn * sizeof(cplx),
+                                   cudaMemcpyDeviceToHost, c->stream));
+        if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));
+    }
+    return end_call(c);
+}

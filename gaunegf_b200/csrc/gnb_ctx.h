@@ -1,0 +1,79 @@
+// Context object behind the C ABI (include/gaunegf_b200.h).  Internal to the library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "gnb_kernels.h"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { GNB_C_CONST = 0, GNB_C_CHAIN1D = 1, GNB_C_BETHE = 2 };
+
+struct Contact {
+    int kind = GNB_C_CONST;
+    int nc = 0;
+    std::vector<int> h_inds;
+    DevBuf d_inds;
+    DevBuf d_const;                 // nc*nc block (CONST)
+    // CHAIN1D parameters (device, nc*nc each)
+    DevBuf alpha, Salpha, beta, Sbeta, tau, stau;
+    double eta = 0, conv = 0, relax = 0, mix = 0;
+    int max_iter = 0;
+    // BETHE parameters
+    int natoms = 0;
+    std::vector<int> nb_off, nb_dirs;
+    DevBuf d_nb_off, d_nb_dirs, H, Slist, Vlist;
+    // per-chunk products
+    DevBuf blk, gam, iters, diffs, surf;
+    const cplx* blk_ptr = nullptr; long blk_stride = 0;   // valid after prepare
+    const cplx* gam_ptr = nullptr; long gam_stride = 0;
+};
+
+struct gnb_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    size_t ws_limit = (size_t)16 << 30;
+    std::string err;
+    int64_t launches = 0;
+    int N = 0;
+    DevBuf dF, dS, dSig0;
+    bool has_sig0 = false;
+    std::vector<Contact> contacts;
+    // workspaces
+    DevBuf A, Pws, LU, moves, cand0, cand1, perm, invperm, info, dE, dW, G, Y, Z, Xr, out, dT, dDosT, dDosP,
+        sigB, gam1B, gam2B, cols, rows, in_stage;
+    // chain1d fixed-point workspaces
+    DevBuf cA, cB, cg, cgn, cT1, cM, cflags, ct;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double elim_ms = 0.0;
+    bool timing = false;
+};
+
+// gnb_sigma.cu
+int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma);
+int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE);     // leaves g in c->cg
+int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cplx* d_out);
+GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc);
+int gnb_fail(gnb_ctx* c, int code, const std::string& msg);
+int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where);
+
+#define GNB_CK(expr)                                                              \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) return gnb_cuda_fail(c, _e, #expr);                \
+    } while (0)

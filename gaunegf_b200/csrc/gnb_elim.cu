@@ -1,0 +1,493 @@
+// Batched complex128 block-elimination engine for sm_100a (B200).
+//
+// One launch family serves every large-N Green's-function reduction of the reference
+// (utils.py:52-54 `inv`, integrate.py:67-82, transport.py:150-190):
+//   * JORDAN mode  : in-place block Gauss-Jordan inverse  G = A^-1            (8 N^3 flops)
+//   * FORWARD mode : block Gaussian elimination of [A | B] + unit-block-upper back-substitution,
+//                    i.e. only the contact columns of G                      (8/3 N^3 + 8 N^2 m)
+// Each block step (width NB = 32) is: tournament pivoting (parallel GEPP over 256-row groups, rows
+// held in registers), a row-permutation + triangular solve of the pivot row block, and a rank-NB
+// update of the whole batch on the FP64 tensor pipe (mma.sync m8n8k4 -> SASS DMMA.8x8x4; tcgen05
+// has no f64 kind).  All energies of a chunk advance in lock-step so that every launch fills the
+// 148 SMs.  Matrices are row-major interleaved complex128.
+#include "gnb_common.cuh"
+#include "gnb_kernels.h"
+
+// ------------------------------------------------------------------------------------------
+// Assembly  A_k = E_k * S - F - Sigma0 - SigmaB_k   (integrate.py:70,77; transport.py:153,186)
+// HBM-bound: 16 N^2 B written per energy, F/S/Sigma0 stay L2-resident.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(cplx* __restrict__ A, long strideA, int ld, int N,
+                                                  const cplx* __restrict__ F, const cplx* __restrict__ S,
+                                                  const cplx* __restrict__ Sig0,
+                                                  const cplx* __restrict__ SigB, long strideSigB,
+                                                  const cplx* __restrict__ E) {
+    const int b = blockIdx.y;
+    const cplx e = E[b];
+    cplx* Ab = A + (long)b * strideA;
+    const long total = (long)N * N;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / N), j = (int)(idx - (long)i * N);
+        cplx v = csub(cmul(e, S[idx]), F[idx]);
+        if (Sig0) v = csub(v, Sig0[idx]);
+        if (SigB) v = csub(v, SigB[(long)b * strideSigB + idx]);
+        Ab[(long)i * ld + j] = v;
+    }
+}
+
+// A[b][inds[p]][inds[q]] -= blk[b][p][q]   (surfG1D.py:372, surfGBethe.py:527 scatter of contact blocks)
+__global__ void __launch_bounds__(256) k_scatter_sub(cplx* __restrict__ A, long strideA, int ld,
+                                                     const int* __restrict__ inds, int nc,
+                                                     const cplx* __restrict__ blk, long strideBlk) {
+    const int b = blockIdx.y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nc * nc; idx += gridDim.x * blockDim.x) {
+        const int p = idx / nc, q = idx - p * nc;
+        cplx* a = A + (long)b * strideA + (long)inds[p] * ld + inds[q];
+        *a = csub(*a, blk[(long)b * strideBlk + idx]);
+    }
+}
+
+// Augmented right-hand side: A[b][i][N + c] = (i == cols[c])
+__global__ void __launch_bounds__(256) k_set_aug(cplx* __restrict__ A, long strideA, int ld, int N,
+                                                 const int* __restrict__ cols, int m) {
+    const int b = blockIdx.y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * m; idx += gridDim.x * blockDim.x) {
+        const int i = idx / m, c = idx - i * m;
+        A[(long)b * strideA + (long)i * ld + N + c] = cmake(i == cols[c] ? 1.0 : 0.0, 0.0);
+    }
+}
+
+__global__ void k_init_perm(int* __restrict__ perm, int stride, int N) {
+    const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        perm[(long)b * stride + i] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tournament pivoting round.  One CTA = one group of <= 256 candidate rows of one matrix; each
+// thread keeps its row of the NB-wide panel in registers and the CTA runs Gaussian elimination
+// with partial pivoting (LAPACK izamax metric |re|+|im|) WITHOUT physical swaps: a thread whose
+// row is chosen publishes it through shared memory and retires.  The w chosen rows go to the next
+// round; the final round (a single group) also emits the compact LU of the pivot block, the net
+// row moves of this step and updates the running row permutation.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A, long strideA, int ld,
+                                                     int c0, int w, int r0, int n_in,
+                                                     const int* __restrict__ cand_in, int cand_in_stride,
+                                                     int* __restrict__ cand_out, int cand_out_stride,
+                                                     int final_round, cplx* __restrict__ LU,
+                                                     int* __restrict__ moves, int* __restrict__ perm,
+                                                     int perm_stride, int* __restrict__ info) {
+    const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const int i = g * GNB_GROUP + t;
+    const bool valid = i < n_in;
+    int row = -1;
+    if (valid) row = cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i;
+
+    cplx a[GNB_NB];
+    {
+        const cplx* src = A + (long)b * strideA + (long)(valid ? row : 0) * ld + c0;
+#pragma unroll
+        for (int c = 0; c < GNB_NB; c++) a[c] = (valid && c < w) ? src[c] : cmake(0.0, 0.0);
+    }
+    const int ngroup = min(GNB_GROUP, n_in - g * GNB_GROUP);
+    const int nsel = min(w, ngroup);
+
+    __shared__ double s_wm[GNB_GROUP / 32];
+    __shared__ int s_wi[GNB_GROUP / 32];
+    __shared__ cplx s_prow[GNB_NB];
+    __shared__ int s_win[GNB_NB];
+    bool alive = valid;
+
+#pragma unroll
+    for (int j = 0; j < GNB_NB; j++) {
+        if (j < nsel) {   // block-uniform
+            double m = alive ? cabs1(a[j]) : -1.0;
+            int idx = t;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double m2 = __shfl_down_sync(0xffffffffu, m, off);
+                const int i2 = __shfl_down_sync(0xffffffffu, idx, off);
+                if (m2 > m || (m2 == m && i2 < idx)) { m = m2; idx = i2; }
+            }
+            if (lane == 0) { s_wm[warp] = m; s_wi[warp] = idx; }
+            __syncthreads();
+            double bm = s_wm[0];
+            int bi = s_wi[0];
+#pragma unroll
+            for (int q = 1; q < GNB_GROUP / 32; q++)
+                if (s_wm[q] > bm) { bm = s_wm[q]; bi = s_wi[q]; }
+            if (t == bi) {
+                alive = false;
+#pragma unroll
+                for (int c = 0; c < GNB_NB; c++)
+                    if (c >= j) s_prow[c] = a[c];
+                s_win[j] = row;
+                if (final_round) {
+                    cplx* lu = LU + ((long)b * GNB_NB + j) * GNB_NB;
+#pragma unroll
+                    for (int c = 0; c < GNB_NB; c++) lu[c] = a[c];
+                    if (bm == 0.0) *info = 1;      // exactly singular pivot (LAPACK info > 0)
+                }
+            }
+            __syncthreads();
+            if (alive) {
+                const cplx piv = s_prow[j];
+                if (piv.x != 0.0 || piv.y != 0.0) {
+                    const cplx l = cdiv(a[j], piv);
+                    a[j] = l;
+#pragma unroll
+                    for (int c = 0; c < GNB_NB; c++)
+                        if (c > j) a[c] = cfnma(a[c], l, s_prow[c]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!final_round) {
+        if (t < nsel) cand_out[(long)b * cand_out_stride + g * w + t] = s_win[t];
+        return;
+    }
+    // ---- final round: net row moves + permutation bookkeeping (warp 0) -----------------------
+    if (t < 32) {
+        const bool act = t < w;
+        const int ch = act ? s_win[t] : -1;                    // chosen global row, pivot order
+        const bool in_blk = act && ch < c0 + w;                // ch >= c0 always
+        const unsigned chosen_pos = __reduce_or_sync(0xffffffffu, in_blk ? (1u << (ch - c0)) : 0u);
+        const unsigned vacmask = __ballot_sync(0xffffffffu, act && !in_blk);
+        const unsigned blkmask = (w == 32) ? 0xffffffffu : ((1u << w) - 1u);
+        const unsigned dismask = blkmask & ~chosen_pos;        // block rows that were not chosen
+        int* mv = moves + (long)b * GNB_MOVES_STRIDE;
+        int d2 = -1, s2 = -1;
+        if (act) { mv[1 + 2 * t] = c0 + t; mv[2 + 2 * t] = ch; }
+        if (act && !in_blk) {
+            const int rank = __popc(vacmask & ((1u << t) - 1u));
+            const int p = __fns(dismask, 0, rank + 1);
+            d2 = ch; s2 = c0 + p;                              // displaced block row fills the vacated slot
+            mv[1 + 2 * (w + rank)] = d2;
+            mv[2 + 2 * (w + rank)] = s2;
+        }
+        if (t == 0) mv[0] = w + __popc(vacmask);
+        if (perm) {
+            int* pb = perm + (long)b * perm_stride;
+            const int o1 = act ? pb[ch] : 0;
+            const int o2 = (s2 >= 0) ? pb[s2] : 0;
+            __syncwarp();
+            if (act) pb[c0 + t] = o1;
+            __syncwarp();
+            if (d2 >= 0) pb[d2] = o2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row moves of one step applied to a 64-column tile, fused with the triangular solves that turn
+// the pivot row block into  W = (L11 U11)^-1 A[k,:]  (thread per column, LU broadcast from smem).
+// JORDAN: columns of the pivot block get the identity as right-hand side (in-place inverse trick).
+// ------------------------------------------------------------------------------------------
+#define PS_TC 64
+__global__ void __launch_bounds__(256) k_permute_solve(cplx* __restrict__ A, long strideA, int ld,
+                                                       int c0, int w, int col_lo, int col_hi,
+                                                       const int* __restrict__ moves,
+                                                       const cplx* __restrict__ LU, int jordan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);                 // [2*NB][PS_TC]
+    cplx* sLU = tile + 2 * GNB_NB * PS_TC;                          // [NB][NB]
+    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int cs = col_lo + blockIdx.x * PS_TC;
+    cplx* Ab = A + (long)b * strideA;
+    const int* mv = moves + (long)b * GNB_MOVES_STRIDE;
+    const int nm = mv[0];
+    if (t < nm) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
+    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) sLU[idx] = LU[(long)b * GNB_NB * GNB_NB + idx];
+    __syncthreads();
+    for (int idx = t; idx < nm * PS_TC; idx += 256) {
+        const int m = idx / PS_TC, c = idx - m * PS_TC, col = cs + c;
+        tile[idx] = (col < col_hi) ? Ab[(long)s_src[m] * ld + col] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    if (t < PS_TC) {
+        const int col = cs + t;
+        const bool in_piv = (col >= c0 && col < c0 + w);
+        const bool do_solve = (col < col_hi) && (jordan ? true : (col >= c0 + w));
+        if (do_solve) {
+            if (in_piv) {
+                for (int i = 0; i < w; i++) tile[i * PS_TC + t] = cmake(i == col - c0 ? 1.0 : 0.0, 0.0);
+            }
+            for (int i = 1; i < w; i++) {                       // L11 y = x (unit lower)
+                cplx acc = tile[i * PS_TC + t];
+                for (int j = 0; j < i; j++) acc = cfnma(acc, sLU[i * GNB_NB + j], tile[j * PS_TC + t]);
+                tile[i * PS_TC + t] = acc;
+            }
+            for (int i = w - 1; i >= 0; i--) {                  // U11 w = y
+                cplx acc = tile[i * PS_TC + t];
+                for (int j = i + 1; j < w; j++) acc = cfnma(acc, sLU[i * GNB_NB + j], tile[j * PS_TC + t]);
+                tile[i * PS_TC + t] = cdiv(acc, sLU[i * GNB_NB + i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = t; idx < nm * PS_TC; idx += 256) {
+        const int m = idx / PS_TC, c = idx - m * PS_TC, col = cs + c;
+        if (col < col_hi) Ab[(long)s_dst[m] * ld + col] = tile[idx];
+    }
+}
+
+// JORDAN: save the (permuted) panel column as the left GEMM operand and clear it in place, so that
+// the rank-NB update  A <- A - P W  writes  -P W[:,K]  there (in-place inverse).
+__global__ void __launch_bounds__(256) k_save_panel(cplx* __restrict__ A, long strideA, int ld, int nrows,
+                                                    int c0, int w, cplx* __restrict__ Pws, long stridePws) {
+    const int b = blockIdx.y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nrows * GNB_NB; idx += gridDim.x * blockDim.x) {
+        const int i = idx / GNB_NB, c = idx - i * GNB_NB;
+        const bool piv_row = (i >= c0 && i < c0 + w);
+        cplx v = cmake(0.0, 0.0);
+        if (!piv_row && c < w) {
+            cplx* a = A + (long)b * strideA + (long)i * ld + c0 + c;
+            v = *a;
+            *a = cmake(0.0, 0.0);
+        }
+        Pws[(long)b * stridePws + idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Complex rank-K update on the FP64 tensor pipe:   C (+/-)= (scale * P) * W
+// CTA tile 64x64, 8 warps as 4(M) x 2(N), warp tile 16x32 = 2x4 DMMA.8x8x4 tiles, each complex
+// tile product = 4 real DMMAs.  Shared-memory row strides are chosen == 64 B (P) / 32 B (W)
+// modulo 128 B so that every LDS.128 fragment load is bank-conflict free.
+// WT     : W is given as rows [n][k] and used conjugate-transposed (G Gamma G^dagger products).
+// BATCHK : the batch is folded into the K loop (deterministic on-device reduction over energies),
+//          P scaled by wscale[b] (quadrature weight).
+// ------------------------------------------------------------------------------------------
+#define GM_T 64
+#define GM_KC 32
+#define GM_PS (GM_KC + 4)      // P tile row stride (cplx): 36*16 = 576 B == 64 mod 128
+#define GM_WS (GM_T + 2)       // W tile row stride (cplx): 66*16 = 1056 B == 32 mod 128
+
+template <bool WT, bool BATCHK>
+__global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* Ps = reinterpret_cast<cplx*>(smem_raw);                   // [64][GM_PS]
+    cplx* Ws = Ps + GM_T * GM_PS;                                   // [32][GM_WS] or [64][GM_PS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int i0 = g.ilo + blockIdx.y * GM_T, j0 = g.jlo + blockIdx.x * GM_T;
+    const int bz = blockIdx.z;
+    cplx* Cb = g.C + (BATCHK ? 0 : (long)bz * g.strideC);
+
+    double cre[2][4][2], cim[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int r = i0 + wm * 16 + mi * 8 + gid;
+            const int c = j0 + wn * 32 + ni * 8 + tig * 2;
+            cplx v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
+            if (!g.zero_init && r < g.ihi) {
+                if (c < g.jhi) v0 = Cb[(long)r * g.ldc + c];
+                if (c + 1 < g.jhi) v1 = Cb[(long)r * g.ldc + c + 1];
+            }
+            cre[mi][ni][0] = v0.x; cim[mi][ni][0] = v0.y;
+            cre[mi][ni][1] = v1.x; cim[mi][ni][1] = v1.y;
+        }
+
+    const int nb = BATCHK ? g.nbatch_k : 1;
+    for (int bb = 0; bb < nb; bb++) {
+        const int b = BATCHK ? bb : bz;
+        const cplx* Pb = g.P + (long)b * g.strideP;
+        const cplx* Wb = g.W + (long)b * g.strideW;
+        cplx sc = cmake(g.plus ? 1.0 : -1.0, 0.0);
+        if (g.wscale) { const cplx ws = g.wscale[b]; sc = g.plus ? ws : cneg(ws); }
+        for (int k0 = 0; k0 < g.kdim; k0 += GM_KC) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < (GM_T * GM_KC) / 256; q++) {
+                const int idx = tid + q * 256;
+                const int r = idx / GM_KC, k = idx - r * GM_KC;
+                cplx v = cmake(0.0, 0.0);
+                if (i0 + r < g.ihi && k0 + k < g.kdim) v = cmul(sc, Pb[(long)(i0 + r) * g.ldp + k0 + k]);
+                Ps[r * GM_PS + k] = v;
+            }
+            if (WT) {
+#pragma unroll
+                for (int q = 0; q < (GM_T * GM_KC) / 256; q++) {
+                    const int idx = tid + q * 256;
+                    const int n = idx / GM_KC, k = idx - n * GM_KC;
+                    cplx v = cmake(0.0, 0.0);
+                    if (j0 + n < g.jhi && k0 + k < g.kdim) v = cconj(Wb[(long)(j0 + n) * g.ldw + k0 + k]);
+                    Ws[n * GM_PS + k] = v;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < (GM_T * GM_KC) / 256; q++) {
+                    const int idx = tid + q * 256;
+                    const int k = idx / GM_T, n = idx - k * GM_T;
+                    cplx v = cmake(0.0, 0.0);
+                    if (k0 + k < g.kdim && j0 + n < g.jhi) v = Wb[(long)(k0 + k) * g.ldw + j0 + n];
+                    Ws[k * GM_WS + n] = v;
+                }
+            }
+            __syncthreads();
+            const int kend = min(GM_KC, ((g.kdim - k0) + 3) & ~3);
+            for (int kk = 0; kk < kend; kk += 4) {
+                cplx af[2], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) af[mi] = Ps[(wm * 16 + mi * 8 + gid) * GM_PS + kk + tig];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+                    bf[ni] = WT ? Ws[(wn * 32 + ni * 8 + gid) * GM_PS + kk + tig]
+                                : Ws[(kk + tig) * GM_WS + wn * 32 + ni * 8 + gid];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+                    const double nim = -af[mi].y;
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) {
+                        dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi].x, bf[ni].x);
+                        dmma884(cre[mi][ni][0], cre[mi][ni][1], nim, bf[ni].y);
+                        dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].x, bf[ni].y);
+                        dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].y, bf[ni].x);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int r = i0 + wm * 16 + mi * 8 + gid;
+            const int c = j0 + wn * 32 + ni * 8 + tig * 2;
+            if (r < g.ihi && !(r >= g.skip_lo && r < g.skip_hi)) {
+                if (c < g.jhi) Cb[(long)r * g.ldc + c] = cmake(cre[mi][ni][0], cim[mi][ni][0]);
+                if (c + 1 < g.jhi) Cb[(long)r * g.ldc + c + 1] = cmake(cre[mi][ni][1], cim[mi][ni][1]);
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-side launchers
+// ------------------------------------------------------------------------------------------
+static inline int cdiv_i(long a, long b) { return (int)((a + b - 1) / b); }
+
+static const size_t kGemmSmemN = (size_t)(GM_T * GM_PS + GM_KC * GM_WS) * sizeof(cplx);
+static const size_t kGemmSmemT = (size_t)(2 * GM_T * GM_PS) * sizeof(cplx);
+static const size_t kPsSmem = (size_t)(2 * GNB_NB * PS_TC + GNB_NB * GNB_NB) * sizeof(cplx);
+
+cudaError_t gnb_kernels_init() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemN))) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemN))) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemT))) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemT))) return e;
+    if ((e = cudaFuncSetAttribute(k_permute_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmem))) return e;
+    return cudaSuccess;
+}
+
+void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
+                         const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E) {
+    if (M <= 0) return;
+    dim3 grid(min(cdiv_i((long)N * N, 256 * 4), 4096), M);
+    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E);
+}
+
+void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,
+                            const cplx* blk, long strideBlk) {
+    if (M <= 0 || nc <= 0) return;
+    dim3 grid(min(cdiv_i((long)nc * nc, 256), 1024), M);
+    k_scatter_sub<<<grid, 256, 0, st>>>(A, strideA, ld, inds, nc, blk, strideBlk);
+}
+
+void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const int* cols, int m) {
+    if (M <= 0 || m <= 0) return;
+    dim3 grid(min(cdiv_i((long)N * m, 256), 1024), M);
+    k_set_aug<<<grid, 256, 0, st>>>(A, strideA, ld, N, cols, m);
+}
+
+void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk) {
+    const int ni = g.ihi - g.ilo, nj = g.jhi - g.jlo;
+    if (ni <= 0 || nj <= 0 || g.kdim <= 0 || nbatch <= 0) return;
+    dim3 grid(cdiv_i(nj, GM_T), cdiv_i(ni, GM_T), batchk ? 1 : nbatch);
+    if (wt) {
+        if (batchk) k_gemm<true, true><<<grid, 256, kGemmSmemT, st>>>(g);
+        else k_gemm<true, false><<<grid, 256, kGemmSmemT, st>>>(g);
+    } else {
+        if (batchk) k_gemm<false, true><<<grid, 256, kGemmSmemN, st>>>(g);
+        else k_gemm<false, false><<<grid, 256, kGemmSmemN, st>>>(g);
+    }
+}
+
+// Block elimination of a batch of M matrices  [A | B]  (N x (N + naug), leading dimension ld).
+//   jordan = 1 : A <- (P A)^-1 in place, perm[pos] = original row now at pos  (A^-1[:, perm[pos]] = stored[:, pos])
+//   jordan = 0 : forward elimination + back-substitution; the naug augmented columns end up holding A^-1 B
+long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
+                   const GnbElimWork& ws) {
+    long launches = 0;
+    if (M <= 0) return 0;
+    if (jordan) {
+        dim3 grid(cdiv_i(N, 256), M);
+        k_init_perm<<<grid, 256, 0, st>>>(ws.perm, ws.perm_stride, N);
+        launches++;
+    }
+    const int nblk = (N + GNB_NB - 1) / GNB_NB;
+    for (int blk = 0; blk < nblk; blk++) {
+        const int c0 = blk * GNB_NB, w = min(GNB_NB, N - c0);
+        // --- tournament rounds
+        int n = N - c0;
+        const int* cin = nullptr;
+        int* cout = ws.cand0;
+        for (;;) {
+            const int groups = cdiv_i(n, GNB_GROUP);
+            const int fin = groups == 1;
+            dim3 grid(groups, M);
+            k_tourn<<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, ws.cand_stride, cout,
+                                                  ws.cand_stride, fin, ws.LU, ws.moves,
+                                                  jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+            launches++;
+            if (fin) break;
+            n = (groups - 1) * w + min(w, n - (groups - 1) * GNB_GROUP);
+            cin = cout;
+            cout = (cout == ws.cand0) ? ws.cand1 : ws.cand0;
+        }
+        // --- row moves + W
+        const int col_lo = jordan ? 0 : c0, col_hi = jordan ? N : N + naug;
+        {
+            dim3 grid(cdiv_i(col_hi - col_lo, PS_TC), M);
+            k_permute_solve<<<grid, 256, kPsSmem, st>>>(A, strideA, ld, c0, w, col_lo, col_hi, ws.moves, ws.LU, jordan);
+            launches++;
+        }
+        GnbGemmArgs g{};
+        g.C = A; g.strideC = strideA; g.ldc = ld;
+        g.W = A + (long)c0 * ld; g.strideW = strideA; g.ldw = ld;
+        g.kdim = w; g.zero_init = 0; g.plus = 0; g.wscale = nullptr; g.nbatch_k = 0;
+        if (jordan) {
+            dim3 grid(min(cdiv_i((long)N * GNB_NB, 256), 1024), M);
+            k_save_panel<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, w, ws.Pws, (long)N * GNB_NB);
+            launches++;
+            g.P = ws.Pws; g.strideP = (long)N * GNB_NB; g.ldp = GNB_NB;
+            g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = N; g.skip_lo = c0; g.skip_hi = c0 + w;
+        } else {
+            g.P = A + c0; g.strideP = strideA; g.ldp = ld;
+            g.ilo = c0 + w; g.ihi = N; g.jlo = c0 + w; g.jhi = N + naug; g.skip_lo = g.skip_hi = -1;
+        }
+        if (g.ihi > g.ilo && g.jhi > g.jlo) { gnb_launch_gemm(st, g, M, false, false); launches++; }
+    }
+    if (!jordan && naug > 0) {
+        // X[0:c0,:] -= Wstored[0:c0, K] X[K,:]  from the last block upwards (unit block upper triangular)
+        for (int blk = nblk - 1; blk >= 1; blk--) {
+            const int c0 = blk * GNB_NB, w = min(GNB_NB, N - c0);
+            GnbGemmArgs g{};
+            g.C = A + N; g.strideC = strideA; g.ldc = ld;
+            g.P = A + c0; g.strideP = strideA; g.ldp = ld;
+            g.W = A + (long)c0 * ld + N; g.strideW = strideA; g.ldw = ld;
+            g.ilo = 0; g.ihi = c0; g.jlo = 0; g.jhi = naug; g.kdim = w;
+            g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
+            gnb_launch_gemm(st, g, M, false, false);
+            launches++;
+        }
+    }
+    return launches;
+}

@@ -1,0 +1,187 @@
+"""GPU parity of the C-ABI (libgaunegf_b200.so, called through ctypes) against the numpy oracle.
+Tolerance: 1e-10 relative (to the largest element) in complex128, as BASELINE.json states."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from gaunegf_b200 import synthetic as sy
+from oracle import negf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gaunegf_b200._native import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def const_system(ctx, N, nc, seed=0, complex_F=False):
+    F, S = sy.hermitian_pair(N, seed=seed, complex_F=complex_F)
+    inds = sy.end_contacts(N, nc)
+    rng = np.random.default_rng(seed + 100)
+    blks = []
+    for _ in inds:
+        b = rng.standard_normal((nc, nc)) * 0.02
+        blks.append((b + b.T) / 2 - 0.1j * np.eye(nc))
+    ctx.set_system(F, S)
+    ctx.sigma_clear()
+    sig = []
+    for i, b in zip(inds, blks):
+        ctx.sigma_add_const_block(i, b)
+        s = np.zeros((N, N), dtype=complex)
+        s[np.ix_(i, i)] = b
+        sig.append(s)
+    return F, S, inds, sig
+
+
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 64, 100, 257, 300, 520])
+def test_inverse_batch(ctx, n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((7, n, n)) + 1j * rng.standard_normal((7, n, n))
+    Ai = ctx.inverse_batch(A)
+    ref = np.linalg.inv(A)
+    for k in range(7):
+        assert relerr(Ai[k], ref[k]) < 1e-11 * max(1.0, np.linalg.cond(A[k]) / 100)
+
+
+def test_inverse_singular_raises(ctx):
+    A = np.zeros((2, 40, 40), dtype=complex)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.inverse_batch(A)
+
+
+@pytest.mark.parametrize("N,nc", [(48, 6), (64, 1), (130, 16), (300, 40)])
+def test_green_dos_transmission(ctx, N, nc):
+    F, S, inds, sig = const_system(ctx, N, nc, seed=N, complex_F=(N == 130))
+    E = np.concatenate([np.linspace(-1, 1, 9), [0.3 + 0.7j, -2 + 0.01j]])
+    st = sig[0] + sig[1]
+    G = ctx.green(E)
+    Gref = np.array([O.gr_matrix(st, e, F, S) for e in E])
+    for k in range(len(E)):
+        assert relerr(G[k], Gref[k]) < TOL
+    tot, per = ctx.dos(E)
+    assert relerr(per, np.array([-np.imag(np.diag(g)) / np.pi for g in Gref])) < TOL
+    assert relerr(tot, np.array([-np.imag(np.trace(g)) / np.pi for g in Gref])) < TOL
+    Er = E[:9].real
+    T = ctx.transmission(Er, 0, -1)
+    g1 = 1j * (sig[0] - sig[0].conj().T)
+    g2 = 1j * (sig[1] - sig[1].conj().T)
+    Tref = np.array([O.transmission_restricted(e, F, S, st, g1, g2) for e in Er])
+    assert np.allclose(T, Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
+    Td = ctx.transmission_dense(Er, st, g1, g2)
+    assert np.allclose(Td, Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
+
+
+@pytest.mark.parametrize("N,nc", [(48, 6), (200, 24)])
+def test_integrals(ctx, N, nc):
+    F, S, inds, sig = const_system(ctx, N, nc, seed=3)
+    g = type("G", (), {})()
+    g.sigmaTot = lambda E: sig[0] + sig[1]
+    g.sigma = lambda E, i: sig[i]
+    z, w = sy.contour_points(18, -12.0, 0.0)
+    assert relerr(ctx.gr_int(z, w), O.GrInt(F, S, g, z, w)) < TOL
+    Er = np.linspace(-0.4, 0.4, 11)
+    wr = np.linspace(0.1, 0.3, 11)
+    assert relerr(ctx.gless_int(Er, wr, 1), O.GrLessInt(F, S, g, Er, wr, 1)) < TOL
+    assert relerr(ctx.gless_int(Er, wr, -1), O.GrLessInt(F, S, g, Er, wr, None)) < TOL
+    st = sig[0] + sig[1]
+    gam = 1j * (st - st.conj().T)
+    assert relerr(ctx.gless_int_dense(Er, wr, st, gam), O.GrLessInt(F, S, g, Er, wr, None)) < TOL
+    assert relerr(ctx.gr_int_dense(z, w, np.broadcast_to(st, (len(z), N, N)).copy()), O.GrInt(F, S, g, z, w)) < TOL
+
+
+def test_chunking_matches_single_pass(ctx):
+    F, S, inds, sig = const_system(ctx, 96, 8, seed=9)
+    z, w = sy.contour_points(54, -12.0, 0.0)
+    full = ctx.gr_int(z, w)
+    ctx.set_workspace_limit(64 << 20)
+    try:
+        small = ctx.gr_int(z, w)
+        T1 = ctx.transmission(np.linspace(-1, 1, 300))
+    finally:
+        ctx.set_workspace_limit(16 << 30)
+    assert relerr(small, full) < 1e-13
+    T2 = ctx.transmission(np.linspace(-1, 1, 300))
+    assert np.array_equal(T1, T2)
+
+
+def test_cfg1_golden_transmission(ctx, golden):
+    G = golden("cfg1_chain")
+    F, S, s1, s2 = sy.chain(64)
+    ctx.set_system(F, S)
+    ctx.sigma_clear()
+    ctx.sigma_add_const_block([0], [[s1[0]]])
+    ctx.sigma_add_const_block([63], [[s2[63]]])
+    T = ctx.transmission(G["E"])
+    assert np.allclose(T, G["T"], rtol=1e-9, atol=1e-12 * G["T"].max())
+    tot, per = ctx.dos(G["Ed"])
+    assert relerr(tot, G["dos_tot"]) < TOL and relerr(per, G["dos_site"]) < TOL
+
+
+@pytest.mark.parametrize("tag,eta", [("a", 0.05), ("b", 1e-4)])
+def test_chain1d_sigma(ctx, golden, tag, eta):
+    G = golden("cfg4_surfg1d")
+    F, S, inds, taus = sy.lead_device_lead(16, 32, seed=2, s_off=0.05)
+    og = O.surfG1D(F, S, inds, taus, eta=eta)
+    ctx.set_system(F, S)
+    ctx.sigma_clear()
+    for i in range(2):
+        ctx.sigma_add_chain1d(inds[i], og.aList[i], og.aSList[i], og.bList[i], og.bSList[i], og.tauList[i],
+                              og.stauList[i], eta, 1e-5, 0.1, 2000)
+    E4 = G["E4"]
+    g0, iters, diffs = ctx.sigma_eval(0, 1, E4, (16, 16))
+    ref_it = []
+    for e in E4:
+        og.g(e, 0)
+        ref_it.append(og.last_iters[(complex(e), 0)][0])
+    ref_it = np.array(ref_it)
+    assert np.array_equal(iters, ref_it), (iters, ref_it)
+    conv = ref_it < 2000
+    assert relerr(g0[conv], G["g0_" + tag][conv]) < TOL
+    s0, _, _ = ctx.sigma_eval(0, 0, E4, (16, 16))
+    assert relerr(s0[conv], G["sig0_" + tag][conv]) < TOL
+    if tag == "a":
+        T = ctx.transmission(E4)
+        assert relerr(T, G["T4"]) < TOL
+        assert relerr(ctx.gr_int(G["zc"], np.array([1.0, 0.5j, -0.25])), G["GI4"]) < TOL
+        assert relerr(ctx.gless_int(E4[:4], np.ones(4) * 0.1, 1), G["GL4"]) < TOL
+        assert relerr(ctx.dos(E4)[0], G["dos4"]) < TOL
+
+
+def test_bethe_sigma(ctx, golden):
+    G = golden("cfg5_bethe")
+    Nb = int(G["Nb"])
+    F, S = sy.hermitian_pair(Nb, seed=3)
+    ctx.set_system(F, S)
+    ctx.sigma_clear()
+    lens, flat = G["nInd_len"], list(G["nInd_flat"])
+    p = 0
+    for c in range(2):
+        nbl = []
+        for n in lens[c]:
+            nbl.append(flat[p:p + n])
+            p += n
+        ctx.sigma_add_bethe(G["indsLists"][c], nbl, G["H"][c], G["Slist"][c], G["Vlist"][c], float(G["eta"]), 1e-5, 0.5, 1000)
+    E5 = G["E5"]
+    sK, _, _ = ctx.sigma_eval(0, 1, E5, (12, 9, 9))
+    assert relerr(sK, G["sigK"]) < TOL
+    sS, _, _ = ctx.sigma_eval(0, 2, E5, (9, 9, 9))
+    assert relerr(sS, G["sigS"]) < TOL
+    blk, _, _ = ctx.sigma_eval(0, 0, E5, (27, 27))
+    ii = np.asarray(G["indsLists"][0]).reshape(-1)
+    ref = G["sigB0"][:, ii][:, :, ii]
+    assert relerr(blk, ref) < TOL
+    Gd = ctx.green(E5)
+    for k, e in enumerate(E5):
+        assert relerr(Gd[k], O.gr_matrix(G["sigBt"][k], e, F, S)) < TOL
+    mu = float(G["fermi"])
+    from scipy.special import roots_legendre
+    x, w = roots_legendre(6)
+    mid = 0.25
+    Eg = mid * (x + 1) + mu - 0.25
+    out = ctx.gless_int(Eg, mid * w * 1.0, 1) / (2 * np.pi)
+    assert relerr(out, G["PgB"]) < TOL
