@@ -46,6 +46,7 @@ SIGNATURES = {
     "gnb_gless_int": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int]),
     "gnb_green_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_int]),
     "gnb_transmission_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
+    "gnb_transmission_spin": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
     "gnb_dos_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, _vp]),
     "gnb_gr_int_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp, C.c_int]),
     "gnb_gless_int_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_int]),
@@ -262,6 +263,15 @@ class Context:
         T = np.empty(E.size, dtype=np.float64)
         self.check(self.lib.gnb_transmission_dense(self.h, E.size, ptr(E), ptr(s), ss, ptr(g1), s1, ptr(g2), s2, ptr(T)))
         return T
+
+    def transmission_spin(self, E, sig, gam1, gam2):
+        E = c128(np.atleast_1d(E))
+        s, ss = self._dense(sig, E.size)
+        g1, s1 = self._dense(gam1, E.size)
+        g2, s2 = self._dense(gam2, E.size)
+        T4 = np.empty((E.size, 4), dtype=np.float64)
+        self.check(self.lib.gnb_transmission_spin(self.h, E.size, ptr(E), ptr(s), ss, ptr(g1), s1, ptr(g2), s2, ptr(T4)))
+        return T4
 
     def dos_dense(self, E, sig, per_site=True):
         E = c128(np.atleast_1d(E))

@@ -343,7 +343,7 @@ static int put_chunk_scalars(gnb_ctx* c, const double* E, const double* w, int k
 // ---------------------------------------------------------------------------------------------
 // Full-inverse family: green / dos / gr_int (+ dense variants)
 // ---------------------------------------------------------------------------------------------
-enum { MODE_GREEN = 0, MODE_DOS = 1, MODE_GRINT = 2, MODE_T_DENSE = 3, MODE_GLESS_DENSE = 4 };
+enum { MODE_GREEN = 0, MODE_DOS = 1, MODE_GRINT = 2, MODE_T_DENSE = 3, MODE_GLESS_DENSE = 4, MODE_T_SPIN = 5 };
 
 static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double* w, bool use_desc,
                       DenseSrc sig, DenseSrc g1, DenseSrc g2, double* out0, double* out1, int loc) {
@@ -353,10 +353,10 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     if (rc) return rc;
     const int N = c->N, ld = round_up(N, 2);
     const size_t nn = (size_t)N * N;
-    const bool needG = mode == MODE_GREEN || mode == MODE_T_DENSE || mode == MODE_GLESS_DENSE;
+    const bool needG = mode == MODE_GREEN || mode == MODE_T_DENSE || mode == MODE_GLESS_DENSE || mode == MODE_T_SPIN;
     size_t per = (size_t)N * ld * 16 + (size_t)N * GNB_NB * 16 + 8 * (size_t)N + 16384;
     if (needG && !(mode == MODE_GREEN && loc == GNB_DEVICE)) per += nn * 16;
-    if (mode == MODE_T_DENSE) per += 2 * nn * 16;
+    if (mode == MODE_T_DENSE || mode == MODE_T_SPIN) per += 2 * nn * 16;
     if (mode == MODE_GLESS_DENSE) per += nn * 16;
     if (sig.p && sig.stride) per += nn * 16;
     if (g1.p && g1.stride) per += nn * 16;
@@ -428,6 +428,38 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
             gnb_launch_trace_dot(c->stream, m, c->Z.as<cplx>(), G, (long)nn, (int)nn, c->dT.as<double>());
             c->launches += 3;
             GNB_CK(cudaMemcpyAsync(out0 + k0, c->dT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        } else if (mode == MODE_T_SPIN) {
+            // four spin-block traces of one 2N x 2N inverse (transport.py:159-181):
+            // T_i = Re sum_ij (Gamma1[r,r] G[r,c] Gamma2[c,c])[i,j] conj(G[c,r][i,j])
+            const cplx *g1c, *g1b, *g2c, *g2b;
+            if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &g1c, &g1b))) return rc;
+            if ((rc = stage_dense(c, c->gam2B, g2, k0, m, &g2c, &g2b))) return rc;
+            const int h = N / 2;
+            const long hh = (long)h * h;
+            GNB_CK(c->Y.ensure((size_t)m * hh * sizeof(cplx)));
+            GNB_CK(c->Z.ensure((size_t)m * hh * sizeof(cplx)));
+            GNB_CK(c->dT.ensure((size_t)m * 4 * sizeof(double)));
+            const cplx* G1 = g1b ? g1b : g1c; const long s1 = g1b ? (long)nn : 0;
+            const cplx* G2 = g2b ? g2b : g2c; const long s2 = g2b ? (long)nn : 0;
+            for (int blk = 0; blk < 4; blk++) {
+                const int r0 = (blk / 2) * h, c0 = (blk % 2) * h;
+                GnbGemmArgs g{};
+                g.ilo = 0; g.ihi = h; g.jlo = 0; g.jhi = h; g.kdim = h; g.skip_lo = g.skip_hi = -1;
+                g.zero_init = 1; g.plus = 1;
+                g.C = c->Y.as<cplx>(); g.strideC = hh; g.ldc = h;
+                g.P = G + (long)r0 * N + c0; g.strideP = nn; g.ldp = N;
+                g.W = G2 + (long)c0 * N + c0; g.strideW = s2; g.ldw = N;
+                gnb_launch_gemm(c->stream, g, m, false, false);
+                g.C = c->Z.as<cplx>();
+                g.P = G1 + (long)r0 * N + r0; g.strideP = s1; g.ldp = N;
+                g.W = c->Y.as<cplx>(); g.strideW = hh; g.ldw = h;
+                gnb_launch_gemm(c->stream, g, m, false, false);
+                gnb_launch_trace_dot_strided(c->stream, m, c->Z.as<cplx>(), hh, h, G + (long)c0 * N + r0, (long)nn, N,
+                                             h, h, c->dT.as<double>(), 4, blk);
+                c->launches += 3;
+            }
+            GNB_CK(cudaMemcpyAsync(out0 + (size_t)k0 * 4, c->dT.p, (size_t)m * 4 * sizeof(double),
+                                   cudaMemcpyDeviceToHost, c->stream));
         } else if (mode == MODE_GLESS_DENSE) {
             const cplx *gc, *gb;
             if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &gc, &gb))) return rc;
@@ -479,6 +511,12 @@ extern "C" int gnb_transmission_dense(gnb_ctx* c, int M, const double* E, const 
                                       const double* gam1, long s1, const double* gam2, long s2, double* T) {
     if (!gam1 || !gam2) return gnb_fail(c, GNB_ERR_ARG, "gamma matrices required");
     return run_jordan(c, MODE_T_DENSE, M, E, nullptr, false, {sig, ss}, {gam1, s1}, {gam2, s2}, T, nullptr, GNB_HOST);
+}
+extern "C" int gnb_transmission_spin(gnb_ctx* c, int M, const double* E, const double* sig, long ss,
+                                     const double* gam1, long s1, const double* gam2, long s2, double* T4) {
+    if (!gam1 || !gam2) return gnb_fail(c, GNB_ERR_ARG, "gamma matrices required");
+    if (c && (c->N % 2)) return gnb_fail(c, GNB_ERR_ARG, "spin-resolved transmission needs an even (2N) dimension");
+    return run_jordan(c, MODE_T_SPIN, M, E, nullptr, false, {sig, ss}, {gam1, s1}, {gam2, s2}, T4, nullptr, GNB_HOST);
 }
 extern "C" int gnb_gless_int_dense(gnb_ctx* c, int M, const double* E, const double* w, const double* sig, long ss,
                                    const double* gam, long gs, double* out, int loc) {

@@ -92,6 +92,28 @@ __global__ void __launch_bounds__(256) k_trace_dot(const cplx* __restrict__ Z, c
     if (t == 0) T[b] = red[0];
 }
 
+// strided variant for spin-block traces: T[b*tstride + toff] = Re sum_ij Z[i][j] conj(X[i][j])
+__global__ void __launch_bounds__(256) k_trace_dot_strided(const cplx* __restrict__ Z, long strideZ, int ldz,
+                                                           const cplx* __restrict__ X, long strideX, int ldx,
+                                                           int nr, int ncols, double* __restrict__ T, int tstride,
+                                                           int toff) {
+    const int b = blockIdx.x, t = threadIdx.x;
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int idx = t; idx < nr * ncols; idx += 256) {
+        const int i = idx / ncols, j = idx - i * ncols;
+        const cplx z = Z[(long)b * strideZ + (long)i * ldz + j], x = X[(long)b * strideX + (long)i * ldx + j];
+        acc += z.x * x.x + z.y * x.y;
+    }
+    red[t] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) red[t] += red[t + s];
+        __syncthreads();
+    }
+    if (t == 0) T[(long)b * tstride + toff] = red[0];
+}
+
 // Gamma = i (Sigma - Sigma^dagger) on compact n x n contact blocks (transport.py:143-146, integrate.py:80)
 __global__ void __launch_bounds__(256) k_gamma(const cplx* __restrict__ sig, long stride, int n, cplx* __restrict__ gam) {
     const int b = blockIdx.y;
@@ -138,4 +160,9 @@ void gnb_launch_gamma_from_sigma(cudaStream_t st, int M, const cplx* sig, long s
     if (M <= 0 || n <= 0) return;
     dim3 grid(min(cdiv_i((long)n * n, 256), 1024), M);
     k_gamma<<<grid, 256, 0, st>>>(sig, stride, n, gam);
+}
+void gnb_launch_trace_dot_strided(cudaStream_t st, int M, const cplx* Z, long strideZ, int ldz, const cplx* X,
+                                  long strideX, int ldx, int nr, int ncols, double* T, int tstride, int toff) {
+    if (M <= 0) return;
+    k_trace_dot_strided<<<M, 256, 0, st>>>(Z, strideZ, ldz, X, strideX, ldx, nr, ncols, T, tstride, toff);
 }

@@ -1,0 +1,104 @@
+"""Turn the reference's self-energy inputs (arrays, or duck-typed surfG objects: SURVEY.md §1) into
+the device-side description the C ABI evaluates: constant contact blocks, 1-D chain / Bethe fixed
+points, or — for arbitrary Python objects with sigmaTot()/sigma() — per-energy dense matrices that
+the caller evaluates on the host and the GPU inverts (API compatibility, not a compute fallback)."""
+import numpy as np
+
+from .config import (SURFACE_GREEN_CONVERGENCE, SURFACE_RELAXATION_FACTOR, SURFACE_GREEN_MAX_ITER,
+                     BETHE_MAX_ITER, BETHE_MIXING)
+
+DESC, DENSE_CONST, DENSE_CALL = "desc", "dense_const", "dense_call"
+
+
+def support(mat, tol=0.0):
+    """orbitals on which a self-energy matrix (or its adjoint) is non-zero"""
+    m = np.abs(np.asarray(mat)) > tol
+    return np.nonzero(m.any(axis=0) | m.any(axis=1))[0]
+
+
+def gamma_of(sig):
+    return 1j * (sig - sig.conj().T)
+
+
+class ArrayPlan:
+    """energy-independent sig1 / sig2 arrays (vectors -> diagonal): transport.SigmaCalculator inputs"""
+
+    def __init__(self, sigs, N):
+        self.N = N
+        self.full = []
+        for s in sigs:
+            s = np.asarray(s)
+            self.full.append(np.diag(s).astype(complex) if s.ndim == 1 else s.astype(complex))
+        for f in self.full:
+            if f.shape != (N, N):
+                raise ValueError(f"self-energy of shape {f.shape} does not match a {N}x{N} system")
+        self.inds = [support(f) for f in self.full]
+        # compact (low-rank) path when every contact touches at most half of the orbitals
+        self.kind = DESC if all(0 < len(i) <= max(1, N // 2) for i in self.inds) else DENSE_CONST
+
+    def install(self, ctx):
+        ctx.sigma_clear()
+        if self.kind == DESC:
+            for f, i in zip(self.full, self.inds):
+                ctx.sigma_add_const_block(i, f[np.ix_(i, i)])
+
+    def sigma_total(self, E=None):
+        return sum(self.full)
+
+    def sigma(self, E, i):
+        return self.full[i]
+
+    def ncontacts(self):
+        return len(self.full)
+
+
+class ObjectPlan:
+    """surfG-protocol objects: g.sigmaTot(E), g.sigma(E, i)"""
+
+    def __init__(self, g, N):
+        self.g, self.N = g, N
+        self.kind = DENSE_CALL
+        self.full = None
+        if hasattr(g, "_gnb_install"):                      # our own surfG / surfGB / surfGBAt
+            self.kind = DESC
+        elif all(hasattr(g, a) for a in ("aList", "aSList", "bList", "bSList", "tauList", "stauList", "indsList", "eta")) \
+                and all(np.shape(t)[0] == np.shape(t)[1] == len(i) for t, i in zip(g.tauList, g.indsList)):
+            self.kind = DESC                                 # a reference-style surfG1D object
+        elif isinstance(getattr(g, "sig", None), list) and all(np.shape(s) == (N, N) for s in g.sig):
+            self.kind = DENSE_CONST                          # surfGTest-style constant matrices
+            self.full = [np.asarray(s, dtype=complex) for s in g.sig]
+
+    def install(self, ctx):
+        ctx.sigma_clear()
+        if self.kind != DESC:
+            return
+        g = self.g
+        if hasattr(g, "_gnb_install"):
+            g._gnb_install(ctx)
+            return
+        for i in range(len(g.indsList)):
+            ctx.sigma_add_chain1d(np.asarray(g.indsList[i]), g.aList[i], g.aSList[i], g.bList[i], g.bSList[i],
+                                  g.tauList[i], g.stauList[i], g.eta, SURFACE_GREEN_CONVERGENCE,
+                                  SURFACE_RELAXATION_FACTOR, SURFACE_GREEN_MAX_ITER)
+
+    def sigma_total(self, E=None):
+        if self.full is not None:
+            return sum(self.full)
+        return np.asarray(self.g.sigmaTot(E), dtype=complex)
+
+    def sigma(self, E, i):
+        if self.full is not None:
+            return self.full[i]
+        return np.asarray(self.g.sigma(E, i), dtype=complex)
+
+    def ncontacts(self):
+        for attr in ("indsList", "indsLists", "sig", "gList"):
+            if hasattr(self.g, attr):
+                return len(getattr(self.g, attr))
+        return 2
+
+    def sigma_total_batch(self, Elist):
+        return np.stack([self.sigma_total(E) for E in Elist])
+
+    def sigma_batch(self, Elist, i):
+        return np.stack([self.sigma(E, i) for E in Elist])

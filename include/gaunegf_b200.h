@@ -110,6 +110,10 @@ int gnb_gless_int(gnb_ctx* ctx, int M, const double* E, const double* w, int con
 int gnb_green_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride, double* G, int loc);
 int gnb_transmission_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride,
                            const double* gam1, long g1_stride, const double* gam2, long g2_stride, double* T);
+/* spin-resolved transmission (transport.py:159-181): the system is 2N x 2N in block order; T4: M x 4
+ * = [T_uu, T_ud, T_du, T_dd] with T_i = Re Tr[Gamma1[r,r] G[r,c] Gamma2[c,c] Ga[r,c]] */
+int gnb_transmission_spin(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride,
+                          const double* gam1, long g1_stride, const double* gam2, long g2_stride, double* T4);
 int gnb_dos_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride,
                   double* dos_total, double* dos_per_site);
 int gnb_gr_int_dense(gnb_ctx* ctx, int M, const double* E, const double* w, const double* sig,

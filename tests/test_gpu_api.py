@@ -1,0 +1,256 @@
+"""GPU parity of the drop-in Python API (gaunegf_b200.transport / density / integrate / surfG*)
+against golden vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py) and the
+numpy oracle.  Reads like the reference's own consistency tests (tests/test_transport_checkpointing.py
+:339-344,396,431-433: driver == single point, resume == full run, per-site DOS sums to total).
+Tolerance 1e-10 relative, complex128."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+from gaunegf_b200 import synthetic as sy
+from oracle import negf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def quiet(f, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+def test_cfg1_cohTrans_DOS_current(golden):
+    from gaunegf_b200 import transport as tr
+    G = golden("cfg1_chain")
+    F, S, s1, s2 = sy.chain(64)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        T = tr.cohTrans(G["E"], F, S, s1, s2)
+    assert isinstance(T, list) and len(T) == 1000
+    assert buf.getvalue().count("Transmission=") == 1000           # legacy per-energy print is kept
+    assert np.allclose(T, G["T"], rtol=1e-9, atol=1e-12 * G["T"].max())
+    assert min(T) >= -1e-15
+    tot, per = tr.DOS(G["Ed"], F, S, s1, s2)
+    assert isinstance(tot, list) and per.shape == (40, 64)
+    assert relerr(tot, G["dos_tot"]) < TOL and relerr(per, G["dos_site"]) < TOL
+    assert np.allclose(per.sum(axis=1), tot, rtol=1e-9)
+    for (qV, Tk), ref in zip(G["cur_args"], G["cur"]):
+        assert abs(tr.current(F, S, s1, s2, 0.0, qV, T=Tk, dE=0.01) - ref) <= 1e-10 * abs(ref)
+    assert tr.current(F, S, s1, s2, 0.0, 0.0) == 0.0
+    Ip, Im = tr.current(F, S, s1, s2, 0.0, 0.3, dE=0.01), tr.current(F, S, s1, s2, 0.0, -0.3, dE=0.01)
+    assert np.isclose(abs(Ip), abs(Im), rtol=1e-6)
+    # matrix-form self-energies on contact blocks, complex F
+    F2, S2, _, _ = sy.chain(40)
+    Tm = quiet(tr.cohTrans, G["E2"], F2.astype(complex), S2, G["sm1"], G["sm2"])
+    assert relerr(Tm, G["Tm"]) < TOL
+
+
+def test_driver_equals_single_point_and_errors():
+    from gaunegf_b200 import transport as tr
+    F, S, s1, s2 = sy.chain(30)
+    calc = tr.SigmaCalculator(s1, s2)
+    E = np.linspace(-1.5, 1.5, 7)
+    T = tr.calculate_transmission(F, S, calc, E)
+    single = [tr.transmission_single_energy(e, F, S, calc) for e in E]
+    assert np.allclose(T, single, rtol=1e-10)
+    tot, per = tr.calculate_dos(F, S, calc, E)
+    for k, e in enumerate(E):
+        t1, p1 = tr.dos_single_energy(e, F, S, calc)
+        assert np.isclose(t1, tot[k], rtol=1e-10) and np.allclose(p1, per[k], rtol=1e-10)
+    with pytest.raises(ValueError):
+        tr.SigmaCalculator(s1)
+    with pytest.raises(ValueError):
+        tr.calculate_transmission(F, S, calc, E, spin='x')
+    with pytest.raises(ValueError):
+        tr.calculate_current(F, S, calc, None, 0.1)
+    with pytest.raises(ValueError):
+        tr.SigmaCalculator(s1, s2).get_sigma(0.0, 5)
+
+
+def test_checkpoint_resume(tmp_path):
+    from gaunegf_b200 import transport as tr
+    F, S, s1, s2 = sy.chain(24)
+    calc = tr.SigmaCalculator(s1, s2)
+    E = np.linspace(-2, 2, 23)
+    full = tr.calculate_transmission(F, S, calc, E)
+    ck = str(tmp_path / "t.npz")
+    first = tr.calculate_transmission(F, S, calc, E, checkpoint_file=ck, checkpoint_interval=5)
+    assert np.allclose(first, full, rtol=1e-10)
+    data = np.load(ck)
+    assert set(data.files) == {"transmission", "energy_list"}
+    part = data["transmission"].copy()
+    part[7:] = -1                                            # pretend the run died after 7 energies
+    np.savez(ck, transmission=part, energy_list=E)
+    resumed = tr.calculate_transmission(F, S, calc, E, checkpoint_file=ck, checkpoint_interval=5)
+    assert np.allclose(resumed, full, rtol=1e-10)
+    other = tr.calculate_transmission(F, S, calc, E + 0.01, checkpoint_file=ck)   # grid mismatch -> fresh
+    assert not np.allclose(other, full)
+    dk = str(tmp_path / "d.npz")
+    tot, per = tr.calculate_dos(F, S, calc, E, checkpoint_file=dk, checkpoint_interval=4)
+    assert set(np.load(dk).files) == {"dos_total", "dos_per_site", "energy_list"}
+    tot2, per2 = tr.calculate_dos(F, S, calc, E, checkpoint_file=dk)
+    assert np.array_equal(tot, tot2) and np.array_equal(per, per2)
+
+
+def test_cfg1_spin(golden):
+    from gaunegf_b200 import transport as tr
+    G = golden("cfg1_spin")
+    Fs, Ss = sy.hermitian_pair(24, seed=5, complex_F=True)
+    su1, su2 = sy.block_sigma_vectors(12, 3, 0.1)
+    for spin, kT, k4 in (("u", "Tu", "Tu4"), ("g", "Tg", "Tg4")):
+        T, T4 = quiet(tr.cohTransSpin, G["Es"], Fs, Ss, su1, su2, spin)
+        assert relerr(T, G[kT]) < TOL and relerr(T4, G[k4]) < TOL
+    calc = tr.SigmaCalculator(su1, su2)
+    tot, per, sp = tr.calculate_dos(Fs, Ss, calc, G["Es"], spin='u')
+    assert np.allclose(sp.sum(axis=1), tot) and per.shape == (7, 24)
+
+
+def test_cfg2_density48(golden):
+    from gaunegf_b200 import density as de, integrate as it
+    from gaunegf_b200.surfGTester import surfGTest
+    G = golden("cfg2_density48")
+    N = 48
+    F, S = sy.hermitian_pair(N, seed=0)
+    inds = sy.end_contacts(N, 6)
+    g = surfGTest(F, S, [list(inds[0]), list(inds[1])], -0.1j, -0.1j)
+    assert relerr(quiet(de.densityComplex, F, S, g, -30.0, 0.0, 1e-4, 0.0), G["Pc"]) < TOL
+    assert relerr(quiet(de.densityComplexN, F, S, g, -30.0, 0.0, 54, 300.0, False, 'ant'), G["PcN"]) < TOL
+    assert relerr(quiet(de.densityComplexN, F, S, g, -30.0, 0.0, 40, 0.0, False, 'legendre'), G["PcNl"]) < TOL
+    assert relerr(quiet(de.densityRealN, F, S, g, -8.0, 0.0, 64, 0.0, False), G["PrN"]) < TOL
+    assert relerr(quiet(de.densityReal, F, S, g, -8.0, 0.0, 1e-2, 0.0), G["Pr"]) < TOL
+    assert relerr(quiet(de.densityGridN, F, S, g, -0.25, 0.25, -1, 60, 0.0, False), G["PgN"]) < TOL
+    assert relerr(quiet(de.densityGridN, F, S, g, 0.25, -0.25, None, 60, 300.0, False), G["PgN0"]) < TOL
+    assert relerr(quiet(de.densityGrid, F, S, g, -0.25, 0.25, 0, 1e-4, 0.0), G["Pg"]) < TOL
+    assert relerr(it.GrInt(F, S, g, G["z"], G["w"]), G["GI"]) < TOL
+    assert relerr(it.GrLessInt(F, S, g, G["z"].real, G["w"].real, 0), G["GL"]) < TOL
+    assert relerr(it.GrLessInt(F, S, g, G["z"].real, G["w"].real, None), G["GLn"]) < TOL
+    with pytest.raises(AssertionError):
+        it.GrInt(F, S, g, G["z"], G["w"][:2])
+    # an arbitrary Python object with the surfG protocol (the reference tests' MockSurfaceGreen style)
+    class Mock:
+        def sigmaTot(self, E):
+            return g.sigmaTot(E) + 1j * (0.01 * E * np.eye(N) + 0.001)
+        def sigma(self, E, i):
+            return g.sigma(E, i)
+    m = Mock()
+    assert relerr(it.GrInt(F, S, m, G["z"], G["w"]), O.GrInt(F, S, m, G["z"], G["w"])) < TOL
+    assert relerr(it.GrLessInt(F, S, m, G["z"].real, G["w"].real, 1), O.GrLessInt(F, S, m, G["z"].real, G["w"].real, 1)) < TOL
+
+
+def test_cfg2_density256(golden):
+    from gaunegf_b200 import density as de
+    from gaunegf_b200.surfGTester import surfGTest
+    G = golden("cfg2_density256")
+    N = 256
+    F, S = sy.hermitian_pair(N, seed=0)
+    inds = sy.end_contacts(N, 16)
+    g = surfGTest(F, S, [list(inds[0]), list(inds[1])], -0.1j, -0.1j)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        P = de.densityComplex(F, S, g, -30.0, 0.0, 1e-4, 0.0)
+    assert "in 162 points" in buf.getvalue()
+    assert abs(np.trace(P @ S) - G["trPS"]) < 1e-10 * abs(G["trPS"])
+    assert relerr(P[G["ii"], G["jj"]], G["samp"]) < TOL
+    assert abs(np.linalg.norm(P) - G["fro"]) < 1e-10 * G["fro"]
+
+
+def test_cfg3_transmission_current(golden):
+    from gaunegf_b200 import transport as tr
+    G = golden("cfg3_trans")
+    N = 1024
+    F, S = sy.hermitian_pair(N, seed=1)
+    s1, s2 = sy.block_sigma_vectors(N, 64, 0.1)
+    T = quiet(tr.cohTrans, G["E3"], F, S, s1, s2)
+    assert relerr(T, G["T3"]) < TOL
+    N = 256
+    F, S = sy.hermitian_pair(N, seed=1)
+    s1, s2 = sy.block_sigma_vectors(N, 16, 0.1)
+    assert relerr(quiet(tr.cohTrans, G["E3b"], F, S, s1, s2), G["T3b"]) < TOL
+    I = tr.current(F, S, s1, s2, 0.0, 0.4, T=0.0, dE=0.01)
+    assert abs(I - G["I3b"]) < 1e-10 * abs(G["I3b"])
+
+
+@pytest.mark.parametrize("tag,eta", [("a", 0.05), ("b", 1e-4)])
+def test_cfg4_surfg1d(golden, tag, eta):
+    from gaunegf_b200 import transport as tr, integrate as it
+    from gaunegf_b200.surfG1D import surfG
+    G = golden("cfg4_surfg1d")
+    F, S, inds, taus = sy.lead_device_lead(16, 32, seed=2, s_off=0.05)
+    g = surfG(F, S, [list(i) for i in inds], [list(t) for t in taus], eta=eta)
+    og = O.surfG1D(F, S, inds, taus, eta=eta)
+    E4 = G["E4"]
+    g0 = g.g(E4, 0)
+    its = np.array([g.last_iters[(complex(e), 0)][0] for e in E4])
+    ref = []
+    for e in E4:
+        og.g(e, 0)
+        ref.append(og.last_iters[(complex(e), 0)][0])
+    assert np.array_equal(its, ref)                       # iteration counts match the oracle's
+    conv = its < 2000
+    assert relerr(g0[conv], G["g0_" + tag][conv]) < TOL
+    assert relerr(g.g(E4[2], 0), G["g0_" + tag][2]) < TOL   # scalar-energy call, like the reference
+    sig1 = g.sigma(E4, 1)
+    conv1 = np.array([g.last_iters[(complex(e), 1)][0] for e in E4]) < 2000
+    assert relerr(sig1[conv1][:, inds[1]][:, :, inds[1]], G["sig1_" + tag][conv1]) < TOL
+    if tag == "a":
+        assert relerr(quiet(tr.cohTransE, E4, F, S, g), G["T4"]) < TOL
+        assert relerr(it.GrInt(F, S, g, G["zc"], np.array([1.0, 0.5j, -0.25])), G["GI4"]) < TOL
+        assert relerr(it.GrLessInt(F, S, g, E4[:4], np.ones(4) * 0.1, -1), G["GL4"]) < TOL
+        assert relerr(quiet(tr.DOSE, E4, F, S, g)[0], G["dos4"]) < TOL
+        # a reference-style object (attributes only, numpy methods) takes the same device path
+        assert relerr(quiet(tr.cohTransE, E4, F, S, og), G["T4"]) < TOL
+
+
+def test_cfg5_bethe(golden):
+    from gaunegf_b200 import density as de
+    from gaunegf_b200.surfGBethe import surfGB, surfGBAt
+    G = golden("cfg5_bethe")
+    Nb = int(G["Nb"])
+    F, S = sy.hermitian_pair(Nb, seed=3)
+    gl = [surfGBAt(G["H"][i], G["Slist"][i], G["Vlist"][i], float(G["eta"])) for i in range(2)]
+    lens, flat = G["nInd_len"], list(G["nInd_flat"])
+    nil, p = [], 0
+    for c in lens:
+        cl = []
+        for n in c:
+            cl.append(flat[p:p + n])
+            p += n
+        nil.append(cl)
+    gB = surfGB.from_parts(F, S, gl, G["indsLists"], nil, eta=float(G["eta"]))
+    at = gl[0]
+    E5 = G["E5"]
+    assert relerr(at.sigmaK(E5), G["sigK"]) < TOL
+    assert relerr(at.sigma(E5), G["sigS"]) < TOL
+    for k, E in enumerate(E5):
+        assert relerr(gB.sigma(E, 0), G["sigB0"][k]) < TOL
+        assert relerr(gB.sigmaTot(E), G["sigBt"][k]) < TOL
+        assert abs(at.DOS(E) - G["dosB"][k]) < 1e-9 * abs(G["dosB"][k])
+    mu = float(G["fermi"])
+    P = quiet(de.densityGridN, F, S, gB, mu - 0.25, mu + 0.25, -1, 6, 0.0, False)
+    assert relerr(P, G["PgB"]) < TOL
+
+
+def test_utils_inv_and_size_independent_properties():
+    """full-size property checks: G A = I, linearity of GrInt in the weights, T >= 0"""
+    from gaunegf_b200 import utils, integrate as it, transport as tr
+    from gaunegf_b200.surfGTester import surfGTest
+    N = 512
+    F, S = sy.hermitian_pair(N, seed=4)
+    A = (0.2 + 0.05j) * S - F
+    Ai = utils.inv(A)
+    assert np.abs(Ai @ A - np.eye(N)).max() < 1e-9
+    inds = sy.end_contacts(N, 32)
+    g = surfGTest(F, S, [list(inds[0]), list(inds[1])], -0.1j, -0.1j)
+    z, w = sy.contour_points(18, -20.0, 0.0)
+    a = it.GrInt(F, S, g, z, w)
+    b = it.GrInt(F, S, g, z, 2 * w)
+    assert relerr(b, 2 * a) < 1e-13
+    c = it.GrInt(F, S, g, z[:9], w[:9]) + it.GrInt(F, S, g, z[9:], w[9:])
+    assert relerr(c, a) < 1e-12
+    s1, s2 = sy.block_sigma_vectors(N, 32, 0.1)
+    T = tr.calculate_transmission(F, S, tr.SigmaCalculator(s1, s2), np.linspace(-1, 1, 64))
+    assert np.all(T > -1e-12) and np.all(np.isfinite(T))
