@@ -30,6 +30,7 @@ SIGNATURES = {
     "gnb_launch_count": (C.c_int64, [_vp]),
     "gnb_last_elim_ms": (C.c_double, [_vp]),
     "gnb_set_timing": (C.c_int, [_vp, C.c_int]),
+    "gnb_gemm_stats": (C.c_int, [_vp, _dp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "gnb_set_system": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
     "gnb_sigma_clear": (C.c_int, [_vp]),
     "gnb_sigma_set_dense0": (C.c_int, [_vp, _vp, C.c_int]),
@@ -131,6 +132,12 @@ class Context:
 
     def set_timing(self, on):
         self.check(self.lib.gnb_set_timing(self.h, int(bool(on))))
+
+    def gemm_stats(self, reset=False):
+        """(ms, algorithmic flops, launches) of the rank-K update kernel while timing was on"""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self.check(self.lib.gnb_gemm_stats(self.h, C.byref(ms), C.byref(fl), C.byref(n), int(reset)))
+        return ms.value, fl.value, n.value
 
     @property
     def launches(self):

@@ -76,6 +76,14 @@ extern "C" int gnb_set_workspace_limit(gnb_ctx* c, size_t bytes) {
 }
 extern "C" int64_t gnb_launch_count(const gnb_ctx* c) { return c ? c->launches : 0; }
 extern "C" double gnb_last_elim_ms(const gnb_ctx* c) { return c ? c->elim_ms : 0.0; }
+extern "C" int gnb_gemm_stats(gnb_ctx* c, double* ms, double* flops, int64_t* launches, int reset) {
+    if (!c) return GNB_ERR_ARG;
+    if (ms) *ms = c->gemm_timer.total_ms;
+    if (flops) *flops = c->gemm_timer.total_flops;
+    if (launches) *launches = c->gemm_timer.count;
+    if (reset) c->gemm_timer.reset();
+    return GNB_OK;
+}
 extern "C" int gnb_set_timing(gnb_ctx* c, int on) { if (!c) return GNB_ERR_ARG; c->timing = on != 0; return GNB_OK; }
 
 static int put(gnb_ctx* c, DevBuf& buf, const void* src, size_t bytes, int loc) {
@@ -224,12 +232,14 @@ GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc) {
     w.LU = c->LU.as<cplx>(); w.moves = c->moves.as<int>();
     w.perm = c->perm.as<int>(); w.perm_stride = N; w.Pws = c->Pws.as<cplx>();
     w.info = c->info.as<int>();
+    w.timer = c->timing ? &c->gemm_timer : nullptr;
     return w;
 }
 
 static int begin_call(gnb_ctx* c) {
     cudaSetDevice(c->device);
     c->elim_ms = 0.0;
+    c->gemm_timer.used = 0; c->gemm_timer.flops.clear();
     GNB_CK(c->info.ensure(sizeof(int) * 4));
     GNB_CK(cudaMemsetAsync(c->info.p, 0, sizeof(int) * 4, c->stream));
     return GNB_OK;
@@ -240,6 +250,7 @@ static int end_call(gnb_ctx* c) {
     GNB_CK(cudaMemcpyAsync(&info, c->info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     GNB_CK(cudaStreamSynchronize(c->stream));
     GNB_CK(cudaGetLastError());
+    if (c->timing) c->gemm_timer.resolve();
     if (info) return gnb_fail(c, GNB_ERR_SINGULAR, "Singular matrix");
     return GNB_OK;
 }

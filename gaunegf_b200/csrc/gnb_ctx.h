@@ -44,7 +44,33 @@ struct Contact {
     const cplx* gam_ptr = nullptr; long gam_stride = 0;
 };
 
+struct EventTimer : GnbGemmTimer {
+    std::vector<cudaEvent_t> pool;
+    std::vector<double> flops;
+    size_t used = 0;
+    double total_ms = 0.0, total_flops = 0.0;
+    long count = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+    void begin(cudaStream_t st) override { cudaEventRecord(get(), st); }
+    void end(cudaStream_t st, double fl) override { cudaEventRecord(get(), st); flops.push_back(fl); }
+    void resolve() {          // call after the stream is synchronised
+        for (size_t i = 0; i + 1 < used; i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, pool[i], pool[i + 1]) == cudaSuccess) {
+                total_ms += ms; total_flops += flops[i / 2]; count++;
+            }
+        }
+        used = 0; flops.clear();
+    }
+    void reset() { used = 0; flops.clear(); total_ms = total_flops = 0.0; count = 0; }
+    ~EventTimer() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
 struct gnb_ctx {
+    EventTimer gemm_timer;
     int device = 0;
     cudaStream_t stream = 0;
     size_t ws_limit = (size_t)16 << 30;

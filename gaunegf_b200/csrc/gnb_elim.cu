@@ -473,7 +473,12 @@ long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long stride
             g.P = A + c0; g.strideP = strideA; g.ldp = ld;
             g.ilo = c0 + w; g.ihi = N; g.jlo = c0 + w; g.jhi = N + naug; g.skip_lo = g.skip_hi = -1;
         }
-        if (g.ihi > g.ilo && g.jhi > g.jlo) { gnb_launch_gemm(st, g, M, false, false); launches++; }
+        if (g.ihi > g.ilo && g.jhi > g.jlo) {
+            if (ws.timer) ws.timer->begin(st);
+            gnb_launch_gemm(st, g, M, false, false);
+            if (ws.timer) ws.timer->end(st, 8.0 * (double)(g.ihi - g.ilo) * (double)(g.jhi - g.jlo) * g.kdim * M);
+            launches++;
+        }
     }
     if (!jordan && naug > 0) {
         // X[0:c0,:] -= Wstored[0:c0, K] X[K,:]  from the last block upwards (unit block upper triangular)
@@ -485,7 +490,9 @@ long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long stride
             g.W = A + (long)c0 * ld + N; g.strideW = strideA; g.ldw = ld;
             g.ilo = 0; g.ihi = c0; g.jlo = 0; g.jhi = naug; g.kdim = w;
             g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
+            if (ws.timer) ws.timer->begin(st);
             gnb_launch_gemm(st, g, M, false, false);
+            if (ws.timer) ws.timer->end(st, 8.0 * (double)c0 * (double)naug * g.kdim * M);
             launches++;
         }
     }

@@ -20,7 +20,15 @@ struct GnbGemmArgs {
     const cplx* wscale;          // optional per-batch complex scale applied to P
 };
 
+// Optional per-launch CUDA-event timing of the rank-K update kernel (bench.py's roofline leg).
+struct GnbGemmTimer {
+    virtual void begin(cudaStream_t st) = 0;
+    virtual void end(cudaStream_t st, double flops) = 0;
+    virtual ~GnbGemmTimer() {}
+};
+
 struct GnbElimWork {
+    GnbGemmTimer* timer;                       // nullptr = no per-kernel timing
     int* cand0; int* cand1; int cand_stride;   // tournament candidate lists
     cplx* LU;                                  // [M][NB][NB] compact LU of the pivot block
     int* moves;                                // [M][GNB_MOVES_STRIDE]

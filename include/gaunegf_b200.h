@@ -53,6 +53,10 @@ int64_t gnb_launch_count(const gnb_ctx* ctx);
 double gnb_last_elim_ms(const gnb_ctx* ctx);
 /* enable/disable the event timing above (adds one event synchronisation per energy chunk) */
 int gnb_set_timing(gnb_ctx* ctx, int on);
+/* with timing on: accumulated device time (ms, CUDA events around each launch), algorithmic real
+ * flops (8 per complex multiply-add) and launch count of the rank-K update kernel (the dominant
+ * kernel) inside eliminations since the last reset */
+int gnb_gemm_stats(gnb_ctx* ctx, double* ms, double* flops, int64_t* launches, int reset);
 
 /* ---- system: F, S  (jnp.asarray(F), jnp.asarray(S): integrate.py:92-93, transport.py:418-419) -- */
 int gnb_set_system(gnb_ctx* ctx, int N, const double* F, const double* S, int loc);
