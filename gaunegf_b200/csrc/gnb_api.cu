@@ -689,3 +689,34 @@ extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, do
     }
     return end_call(c);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Developer hook (tools/gemm_bench.py): time the rank-K update kernel alone on random data.
+// ---------------------------------------------------------------------------------------------
+extern "C" int gnb_dev_gemm_bench(gnb_ctx* c, int M, int n, int k, int bm, int iters, double* ms_out) {
+    if (!c || M <= 0 || n <= 0 || k <= 0 || iters <= 0 || !ms_out) return gnb_fail(c, GNB_ERR_ARG, "gemm_bench: bad arguments");
+    cudaSetDevice(c->device);
+    const size_t nn = (size_t)n * n;
+    GNB_CK(c->A.ensure((size_t)M * nn * sizeof(cplx)));
+    GNB_CK(c->Pws.ensure((size_t)M * n * k * sizeof(cplx)));
+    GNB_CK(c->G.ensure((size_t)M * n * k * sizeof(cplx)));
+    GNB_CK(cudaMemsetAsync(c->A.p, 0, (size_t)M * nn * sizeof(cplx), c->stream));
+    GNB_CK(cudaMemsetAsync(c->Pws.p, 0, (size_t)M * n * k * sizeof(cplx), c->stream));
+    GNB_CK(cudaMemsetAsync(c->G.p, 0, (size_t)M * n * k * sizeof(cplx), c->stream));
+    gnb_set_gemm_bm(bm);
+    GnbGemmArgs g{};
+    g.C = c->A.as<cplx>(); g.strideC = nn; g.ldc = n;
+    g.P = c->Pws.as<cplx>(); g.strideP = (long)n * k; g.ldp = k;
+    g.W = c->G.as<cplx>(); g.strideW = (long)n * k; g.ldw = n;
+    g.ilo = 0; g.ihi = n; g.jlo = 0; g.jhi = n; g.kdim = k; g.skip_lo = g.skip_hi = -1;
+    gnb_launch_gemm(c->stream, g, M, false, false);
+    GNB_CK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < iters; i++) gnb_launch_gemm(c->stream, g, M, false, false);
+    GNB_CK(cudaEventRecord(c->ev1, c->stream));
+    GNB_CK(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    GNB_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_out = ms / iters;
+    gnb_set_gemm_bm(64);
+    return GNB_OK;
+}

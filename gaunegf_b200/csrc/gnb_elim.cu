@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
     __shared__ double s_wm[GNB_GROUP / 32];
     __shared__ int s_wi[GNB_GROUP / 32];
     __shared__ cplx s_prow[GNB_NB];
+    __shared__ cplx s_rinv;
     __shared__ int s_win[GNB_NB];
+    __shared__ cplx s_lu[GNB_NB][GNB_NB + 1];      // final round: compact LU of the pivot block
+    __shared__ cplx s_y[2][GNB_NB];
     bool alive = valid;
 
 #pragma unroll
@@ -124,23 +127,21 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
                 for (int c = 0; c < GNB_NB; c++)
                     if (c >= j) s_prow[c] = a[c];
                 s_win[j] = row;
+                // LAPACK zgetf2 scales the column by the reciprocal of the pivot
+                s_rinv = (bm > 0.0) ? cdiv(cmake(1.0, 0.0), a[j]) : cmake(0.0, 0.0);
                 if (final_round) {
-                    cplx* lu = LU + ((long)b * GNB_NB + j) * GNB_NB;
 #pragma unroll
-                    for (int c = 0; c < GNB_NB; c++) lu[c] = a[c];
+                    for (int c = 0; c < GNB_NB; c++) s_lu[j][c] = a[c];
                     if (bm == 0.0) *info = 1;      // exactly singular pivot (LAPACK info > 0)
                 }
             }
             __syncthreads();
             if (alive) {
-                const cplx piv = s_prow[j];
-                if (piv.x != 0.0 || piv.y != 0.0) {
-                    const cplx l = cdiv(a[j], piv);
-                    a[j] = l;
+                const cplx l = cmul(a[j], s_rinv);
+                a[j] = l;
 #pragma unroll
-                    for (int c = 0; c < GNB_NB; c++)
-                        if (c > j) a[c] = cfnma(a[c], l, s_prow[c]);
-                }
+                for (int c = 0; c < GNB_NB; c++)
+                    if (c > j) a[c] = cfnma(a[c], l, s_prow[c]);
             }
         }
     }
@@ -149,7 +150,53 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
         if (t < nsel) cand_out[(long)b * cand_out_stride + g * w + t] = s_win[t];
         return;
     }
-    // ---- final round: net row moves + permutation bookkeeping (warp 0) -----------------------
+    // ---- final round: explicit inverse of the pivot block, X = (L11 U11)^-1, by column-oriented
+    // substitution on all 256 threads: thread -> column c = t % 32, rows t/32 + 8 q.
+    {
+        const int c = t & 31, rg = t >> 5;
+        cplx x[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[q] = cmake((rg + 8 * q == c) ? 1.0 : 0.0, 0.0);
+        for (int j = 0; j < w; j++) {                       // L11 y = e_c (unit lower)
+            if ((j & 7) == rg) {
+                const int jq = j >> 3;
+                s_y[j & 1][c] = jq == 0 ? x[0] : jq == 1 ? x[1] : jq == 2 ? x[2] : x[3];
+            }
+            __syncthreads();
+            const cplx yj = s_y[j & 1][c];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = rg + 8 * q;
+                if (i > j && i < w) x[q] = cfnma(x[q], s_lu[i][j], yj);
+            }
+        }
+        for (int j = w - 1; j >= 0; j--) {                  // U11 x = y
+            if ((j & 7) == rg) {
+                const int jq = j >> 3;
+                const cplx d = s_lu[j][j];
+                const cplx xv = jq == 0 ? x[0] : jq == 1 ? x[1] : jq == 2 ? x[2] : x[3];
+                const cplx v = (d.x != 0.0 || d.y != 0.0) ? cdiv(xv, d) : xv;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q == jq) x[q] = v;
+                s_y[j & 1][c] = v;
+            }
+            __syncthreads();
+            const cplx xj = s_y[j & 1][c];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = rg + 8 * q;
+                if (i < j) x[q] = cfnma(x[q], s_lu[i][j], xj);
+            }
+        }
+        cplx* inv = LU + (long)b * GNB_NB * GNB_NB;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = rg + 8 * q;
+            inv[i * GNB_NB + c] = (i < w && c < w) ? x[q] : cmake(0.0, 0.0);
+        }
+    }
+    // ---- net row moves + permutation bookkeeping (warp 0) ---------------------------------------
     if (t < 32) {
         const bool act = t < w;
         const int ch = act ? s_win[t] : -1;                    // chosen global row, pivot order
@@ -182,8 +229,9 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
 }
 
 // ------------------------------------------------------------------------------------------
-// Row moves of one step applied to a 64-column tile, fused with the triangular solves that turn
-// the pivot row block into  W = (L11 U11)^-1 A[k,:]  (thread per column, LU broadcast from smem).
+// Row moves of one step applied to a 64-column tile, fused with the product that turns the pivot row
+// block into  W = (L11 U11)^-1 A[k,:]  (explicit 32x32 inverse from the tournament's final round,
+// broadcast from smem; 8 independent accumulators per thread).
 // JORDAN: columns of the pivot block get the identity as right-hand side (in-place inverse trick).
 // ------------------------------------------------------------------------------------------
 #define PS_TC 64
@@ -208,24 +256,31 @@ __global__ void __launch_bounds__(256) k_permute_solve(cplx* __restrict__ A, lon
         tile[idx] = (col < col_hi) ? Ab[(long)s_src[m] * ld + col] : cmake(0.0, 0.0);
     }
     __syncthreads();
-    if (t < PS_TC) {
-        const int col = cs + t;
+    {
+        // W = (L11 U11)^-1 R : thread -> column c = t % 64, rows t/64 + 4 q (8 independent accumulators)
+        const int c = t & (PS_TC - 1), rg = t >> 6, col = cs + c;
         const bool in_piv = (col >= c0 && col < c0 + w);
         const bool do_solve = (col < col_hi) && (jordan ? true : (col >= c0 + w));
+        cplx acc[8];
         if (do_solve) {
-            if (in_piv) {
-                for (int i = 0; i < w; i++) tile[i * PS_TC + t] = cmake(i == col - c0 ? 1.0 : 0.0, 0.0);
+            if (in_piv) {                                       // identity right-hand side: W[:, K] = inverse
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = sLU[(rg + 4 * q) * GNB_NB + (col - c0)];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = cmake(0.0, 0.0);
+                for (int j = 0; j < w; j++) {
+                    const cplx r = tile[j * PS_TC + c];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc[q] = cfma(acc[q], sLU[(rg + 4 * q) * GNB_NB + j], r);
+                }
             }
-            for (int i = 1; i < w; i++) {                       // L11 y = x (unit lower)
-                cplx acc = tile[i * PS_TC + t];
-                for (int j = 0; j < i; j++) acc = cfnma(acc, sLU[i * GNB_NB + j], tile[j * PS_TC + t]);
-                tile[i * PS_TC + t] = acc;
-            }
-            for (int i = w - 1; i >= 0; i--) {                  // U11 w = y
-                cplx acc = tile[i * PS_TC + t];
-                for (int j = i + 1; j < w; j++) acc = cfnma(acc, sLU[i * GNB_NB + j], tile[j * PS_TC + t]);
-                tile[i * PS_TC + t] = cdiv(acc, sLU[i * GNB_NB + i]);
-            }
+        }
+        __syncthreads();
+        if (do_solve) {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (rg + 4 * q < w) tile[(rg + 4 * q) * PS_TC + c] = acc[q];
         }
     }
     __syncthreads();
@@ -267,15 +322,16 @@ __global__ void __launch_bounds__(256) k_save_panel(cplx* __restrict__ A, long s
 #define GM_PS (GM_KC + 4)      // P tile row stride (cplx): 36*16 = 576 B == 64 mod 128
 #define GM_WS (GM_T + 2)       // W tile row stride (cplx): 66*16 = 1056 B == 32 mod 128
 
-template <bool WT, bool BATCHK>
-__global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
+template <bool WT, bool BATCHK, int BM>
+__global__ void __launch_bounds__(BM * 4, BM == 64 ? 2 : 4) k_gemm(GnbGemmArgs g) {
+    constexpr int NT = BM * 4;                                      // 8 warps (BM=64) or 4 warps (BM=32)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* Ps = reinterpret_cast<cplx*>(smem_raw);                   // [64][GM_PS]
-    cplx* Ws = Ps + GM_T * GM_PS;                                   // [32][GM_WS] or [64][GM_PS]
+    cplx* Ps = reinterpret_cast<cplx*>(smem_raw);                   // [BM][GM_PS]
+    cplx* Ws = Ps + BM * GM_PS;                                     // [32][GM_WS] or [64][GM_PS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    const int i0 = g.ilo + blockIdx.y * GM_T, j0 = g.jlo + blockIdx.x * GM_T;
+    const int i0 = g.ilo + blockIdx.y * BM, j0 = g.jlo + blockIdx.x * GM_T;
     const int bz = blockIdx.z;
     cplx* Cb = g.C + (BATCHK ? 0 : (long)bz * g.strideC);
 
@@ -305,8 +361,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
         for (int k0 = 0; k0 < g.kdim; k0 += GM_KC) {
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < (GM_T * GM_KC) / 256; q++) {
-                const int idx = tid + q * 256;
+            for (int q = 0; q < (BM * GM_KC) / NT; q++) {
+                const int idx = tid + q * NT;
                 const int r = idx / GM_KC, k = idx - r * GM_KC;
                 cplx v = cmake(0.0, 0.0);
                 if (i0 + r < g.ihi && k0 + k < g.kdim) v = cmul(sc, Pb[(long)(i0 + r) * g.ldp + k0 + k]);
@@ -314,8 +370,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
             }
             if (WT) {
 #pragma unroll
-                for (int q = 0; q < (GM_T * GM_KC) / 256; q++) {
-                    const int idx = tid + q * 256;
+                for (int q = 0; q < (GM_T * GM_KC) / NT; q++) {
+                    const int idx = tid + q * NT;
                     const int n = idx / GM_KC, k = idx - n * GM_KC;
                     cplx v = cmake(0.0, 0.0);
                     if (j0 + n < g.jhi && k0 + k < g.kdim) v = cconj(Wb[(long)(j0 + n) * g.ldw + k0 + k]);
@@ -323,8 +379,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < (GM_T * GM_KC) / 256; q++) {
-                    const int idx = tid + q * 256;
+                for (int q = 0; q < (GM_T * GM_KC) / NT; q++) {
+                    const int idx = tid + q * NT;
                     const int k = idx / GM_T, n = idx - k * GM_T;
                     cplx v = cmake(0.0, 0.0);
                     if (k0 + k < g.kdim && j0 + n < g.jhi) v = Wb[(long)(k0 + k) * g.ldw + j0 + n];
@@ -341,16 +397,21 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
                 for (int ni = 0; ni < 4; ni++)
                     bf[ni] = WT ? Ws[(wn * 32 + ni * 8 + gid) * GM_PS + kk + tig]
                                 : Ws[(kk + tig) * GM_WS + wn * 32 + ni * 8 + gid];
+                // 16 independent accumulators are touched between two uses of the same one
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].x, bf[ni].y);
+                }
 #pragma unroll
                 for (int mi = 0; mi < 2; mi++) {
                     const double nim = -af[mi].y;
 #pragma unroll
-                    for (int ni = 0; ni < 4; ni++) {
-                        dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi].x, bf[ni].x);
-                        dmma884(cre[mi][ni][0], cre[mi][ni][1], nim, bf[ni].y);
-                        dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].x, bf[ni].y);
-                        dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].y, bf[ni].x);
-                    }
+                    for (int ni = 0; ni < 4; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nim, bf[ni].y);
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].y, bf[ni].x);
                 }
             }
         }
@@ -373,16 +434,20 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GnbGemmArgs g) {
 // ------------------------------------------------------------------------------------------
 static inline int cdiv_i(long a, long b) { return (int)((a + b - 1) / b); }
 
-static const size_t kGemmSmemN = (size_t)(GM_T * GM_PS + GM_KC * GM_WS) * sizeof(cplx);
-static const size_t kGemmSmemT = (size_t)(2 * GM_T * GM_PS) * sizeof(cplx);
+static int g_gemm_bm = 32;     // rows per CTA of the rank-K update (64: 8 warps x 2 CTAs/SM, 32: 4 warps x 4 CTAs/SM)
+void gnb_set_gemm_bm(int bm) { g_gemm_bm = (bm == 32) ? 32 : 64; }
+static size_t gemm_smem(bool wt, int bm) {
+    return (size_t)(bm * GM_PS + (wt ? GM_T * GM_PS : GM_KC * GM_WS)) * sizeof(cplx);
+}
 static const size_t kPsSmem = (size_t)(2 * GNB_NB * PS_TC + GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_kernels_init() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemN))) return e;
-    if ((e = cudaFuncSetAttribute(k_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemN))) return e;
-    if ((e = cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemT))) return e;
-    if ((e = cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemT))) return e;
+#define GNB_SET_SMEM(WT_, BK_, BM_)                                                                      \
+    if ((e = cudaFuncSetAttribute(k_gemm<WT_, BK_, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)gemm_smem(WT_, BM_)))) return e;
+    GNB_SET_SMEM(false, false, 64) GNB_SET_SMEM(false, true, 64) GNB_SET_SMEM(true, false, 64) GNB_SET_SMEM(true, true, 64)
+    GNB_SET_SMEM(false, false, 32) GNB_SET_SMEM(false, true, 32) GNB_SET_SMEM(true, false, 32) GNB_SET_SMEM(true, true, 32)
     if ((e = cudaFuncSetAttribute(k_permute_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmem))) return e;
     return cudaSuccess;
 }
@@ -410,14 +475,16 @@ void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, i
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk) {
     const int ni = g.ihi - g.ilo, nj = g.jhi - g.jlo;
     if (ni <= 0 || nj <= 0 || g.kdim <= 0 || nbatch <= 0) return;
-    dim3 grid(cdiv_i(nj, GM_T), cdiv_i(ni, GM_T), batchk ? 1 : nbatch);
-    if (wt) {
-        if (batchk) k_gemm<true, true><<<grid, 256, kGemmSmemT, st>>>(g);
-        else k_gemm<true, false><<<grid, 256, kGemmSmemT, st>>>(g);
-    } else {
-        if (batchk) k_gemm<false, true><<<grid, 256, kGemmSmemN, st>>>(g);
-        else k_gemm<false, false><<<grid, 256, kGemmSmemN, st>>>(g);
-    }
+    const int bm = g_gemm_bm;
+    dim3 grid(cdiv_i(nj, GM_T), cdiv_i(ni, bm), batchk ? 1 : nbatch);
+    const size_t sm = gemm_smem(wt, bm);
+#define GNB_GO(WT_, BK_)                                                         \
+    do {                                                                         \
+        if (bm == 64) k_gemm<WT_, BK_, 64><<<grid, 256, sm, st>>>(g);            \
+        else k_gemm<WT_, BK_, 32><<<grid, 128, sm, st>>>(g);                     \
+    } while (0)
+    if (wt) { if (batchk) GNB_GO(true, true); else GNB_GO(true, false); }
+    else { if (batchk) GNB_GO(false, true); else GNB_GO(false, false); }
 }
 
 // Block elimination of a batch of M matrices  [A | B]  (N x (N + naug), leading dimension ld).
