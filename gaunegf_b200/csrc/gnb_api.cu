@@ -703,7 +703,8 @@ extern "C" int gnb_dev_gemm_bench(gnb_ctx* c, int M, int n, int k, int bm, int i
     GNB_CK(cudaMemsetAsync(c->A.p, 0, (size_t)M * nn * sizeof(cplx), c->stream));
     GNB_CK(cudaMemsetAsync(c->Pws.p, 0, (size_t)M * n * k * sizeof(cplx), c->stream));
     GNB_CK(cudaMemsetAsync(c->G.p, 0, (size_t)M * n * k * sizeof(cplx), c->stream));
-    gnb_set_gemm_bm(bm);
+    gnb_set_gemm_bm(bm > 0 ? bm : 32);
+    gnb_set_gemm_pipe(bm == 0 ? 1 : 0);          // bm = 0 selects the pipelined persistent kernel
     GnbGemmArgs g{};
     g.C = c->A.as<cplx>(); g.strideC = nn; g.ldc = n;
     g.P = c->Pws.as<cplx>(); g.strideP = (long)n * k; g.ldp = k;
@@ -717,6 +718,7 @@ extern "C" int gnb_dev_gemm_bench(gnb_ctx* c, int M, int n, int k, int bm, int i
     float ms = 0;
     GNB_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_out = ms / iters;
-    gnb_set_gemm_bm(64);
+    gnb_set_gemm_bm(32);
+    gnb_set_gemm_pipe(1);
     return GNB_OK;
 }

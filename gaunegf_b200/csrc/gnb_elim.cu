@@ -10,6 +10,7 @@
 // update of the whole batch on the FP64 tensor pipe (mma.sync m8n8k4 -> SASS DMMA.8x8x4; tcgen05
 // has no f64 kind).  All energies of a chunk advance in lock-step so that every launch fills the
 // 148 SMs.  Matrices are row-major interleaved complex128.
+#include <algorithm>
 #include "gnb_common.cuh"
 #include "gnb_kernels.h"
 
@@ -430,10 +431,159 @@ __global__ void __launch_bounds__(BM * 4, BM == 64 ? 2 : 4) k_gemm(GnbGemmArgs g
 }
 
 // ------------------------------------------------------------------------------------------
+// Pipelined variant of the rank-K (K <= 32) update used by the elimination hot path.
+// Persistent CTAs (2 per SM) walk the (matrix, row tile, col tile) space; per CTA tile 64x32,
+// 8 warps as 4(M) x 2(N), warp tile 16x16.  While a tile is being multiplied, the P / W operands of
+// the CTA's next tile stream into the other shared-memory stage with cp.async (LDGSTS, L2-only) and
+// its C fragment is prefetched into a second register set, so global-memory latency is overlapped
+// with DMMA issue inside each CTA instead of relying on CTA-level interleaving.
+// ------------------------------------------------------------------------------------------
+#define GP_BM 64
+#define GP_BN 32
+#define GP_PS (GM_KC + 4)      // 36 cplx: 576 B == 64 mod 128
+#define GP_WS (GP_BN + 2)      // 34 cplx: 544 B == 32 mod 128
+#define GP_STAGE (GP_BM * GP_PS + GM_KC * GP_WS)
+
+__device__ __forceinline__ double flipsign(double x, unsigned mask) {
+    return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, int ntj, int total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int per_mat = nti * ntj;
+
+    auto issue_loads = [&](int tile, int stage) {
+        const int b = tile / per_mat, rem = tile - b * per_mat;
+        const int ti = rem / ntj, tj = rem - ti * ntj;
+        const int i0 = g.ilo + ti * GP_BM, j0 = g.jlo + tj * GP_BN;
+        const cplx* Pb = g.P + (long)b * g.strideP;
+        const cplx* Wb = g.W + (long)b * g.strideW;
+        cplx* Ps = sm + stage * GP_STAGE;
+        cplx* Ws = Ps + GP_BM * GP_PS;
+#pragma unroll
+        for (int q = 0; q < (GP_BM * GM_KC) / 256; q++) {
+            const int idx = tid + q * 256;
+            const int r = idx / GM_KC, k = idx - r * GM_KC;
+            const bool ok = (i0 + r < g.ihi) && (k < g.kdim);
+            cp_async16(&Ps[r * GP_PS + k], ok ? (const void*)(Pb + (long)(i0 + r) * g.ldp + k) : (const void*)g.P, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int q = 0; q < (GM_KC * GP_BN) / 256; q++) {
+            const int idx = tid + q * 256;
+            const int k = idx / GP_BN, n = idx - k * GP_BN;
+            const bool ok = (k < g.kdim) && (j0 + n < g.jhi);
+            cp_async16(&Ws[k * GP_WS + n], ok ? (const void*)(Wb + (long)k * g.ldw + j0 + n) : (const void*)g.W, ok ? 16 : 0);
+        }
+    };
+    auto load_c = [&](int tile, double (&cr)[2][2][2], double (&ci)[2][2][2]) {
+        const int b = tile / per_mat, rem = tile - b * per_mat;
+        const int ti = rem / ntj, tj = rem - ti * ntj;
+        const int i0 = g.ilo + ti * GP_BM, j0 = g.jlo + tj * GP_BN;
+        const cplx* Cb = g.C + (long)b * g.strideC;
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) {
+                const int r = i0 + wm * 16 + mi * 8 + gid;
+                const int c = j0 + wn * 16 + ni * 8 + tig * 2;
+                cplx v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
+                if (!g.zero_init && r < g.ihi) {
+                    if (c < g.jhi) v0 = Cb[(long)r * g.ldc + c];
+                    if (c + 1 < g.jhi) v1 = Cb[(long)r * g.ldc + c + 1];
+                }
+                cr[mi][ni][0] = v0.x; ci[mi][ni][0] = v0.y;
+                cr[mi][ni][1] = v1.x; ci[mi][ni][1] = v1.y;
+            }
+    };
+
+    int tile = blockIdx.x;
+    if (tile >= total) return;
+    double cre[2][2][2], cim[2][2][2], pre[2][2][2], pim[2][2][2];
+    issue_loads(tile, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    load_c(tile, cre, cim);
+    const unsigned smask = g.plus ? 0u : 0x80000000u;     // C -= P W : flip the sign bit of the A fragments
+    int stage = 0;
+    for (;;) {
+        const int next = tile + gridDim.x;
+        const bool has_next = next < total;
+        if (has_next) issue_loads(next, stage ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (has_next) load_c(next, pre, pim);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const cplx* Ps = sm + stage * GP_STAGE;
+        const cplx* Ws = Ps + GP_BM * GP_PS;
+        const int kend = min(GM_KC, (g.kdim + 3) & ~3);
+#pragma unroll 2
+        for (int kk = 0; kk < kend; kk += 4) {
+            cplx af[2], bf[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) af[mi] = Ps[(wm * 16 + mi * 8 + gid) * GP_PS + kk + tig];
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) bf[ni] = Ws[(kk + tig) * GP_WS + wn * 16 + ni * 8 + gid];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const double ax = flipsign(af[mi].x, smask), ay = flipsign(af[mi].y, smask);
+                const double nay = flipsign(ay, 0x80000000u);
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], ax, bf[ni].x);
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ax, bf[ni].y);
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nay, bf[ni].y);
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ay, bf[ni].x);
+            }
+        }
+        {
+            const int b = tile / per_mat, rem = tile - b * per_mat;
+            const int ti = rem / ntj, tj = rem - ti * ntj;
+            const int i0 = g.ilo + ti * GP_BM, j0 = g.jlo + tj * GP_BN;
+            cplx* Cb = g.C + (long)b * g.strideC;
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) {
+                    const int r = i0 + wm * 16 + mi * 8 + gid;
+                    const int c = j0 + wn * 16 + ni * 8 + tig * 2;
+                    if (r < g.ihi && !(r >= g.skip_lo && r < g.skip_hi)) {
+                        if (c < g.jhi) Cb[(long)r * g.ldc + c] = cmake(cre[mi][ni][0], cim[mi][ni][0]);
+                        if (c + 1 < g.jhi) Cb[(long)r * g.ldc + c + 1] = cmake(cre[mi][ni][1], cim[mi][ni][1]);
+                    }
+                }
+        }
+        if (!has_next) break;
+        __syncthreads();                 // every warp is done with this stage before it is refilled
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) {
+                cre[mi][ni][0] = pre[mi][ni][0]; cre[mi][ni][1] = pre[mi][ni][1];
+                cim[mi][ni][0] = pim[mi][ni][0]; cim[mi][ni][1] = pim[mi][ni][1];
+            }
+        tile = next;
+        stage ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host-side launchers
 // ------------------------------------------------------------------------------------------
 static inline int cdiv_i(long a, long b) { return (int)((a + b - 1) / b); }
 
+static int g_gemm_pipe = 1;    // 1: pipelined persistent kernel for the K <= 32 hot path
+static int g_num_sms = 148;
+void gnb_set_gemm_pipe(int on) { g_gemm_pipe = on; }
+static const size_t kPipeSmem = (size_t)2 * GP_STAGE * sizeof(cplx);
 static int g_gemm_bm = 32;     // rows per CTA of the rank-K update (64: 8 warps x 2 CTAs/SM, 32: 4 warps x 4 CTAs/SM)
 void gnb_set_gemm_bm(int bm) { g_gemm_bm = (bm == 32) ? 32 : 64; }
 static size_t gemm_smem(bool wt, int bm) {
@@ -446,6 +596,8 @@ cudaError_t gnb_kernels_init() {
 #define GNB_SET_SMEM(WT_, BK_, BM_)                                                                      \
     if ((e = cudaFuncSetAttribute(k_gemm<WT_, BK_, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)gemm_smem(WT_, BM_)))) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem))) return e;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
     GNB_SET_SMEM(false, false, 64) GNB_SET_SMEM(false, true, 64) GNB_SET_SMEM(true, false, 64) GNB_SET_SMEM(true, true, 64)
     GNB_SET_SMEM(false, false, 32) GNB_SET_SMEM(false, true, 32) GNB_SET_SMEM(true, false, 32) GNB_SET_SMEM(true, true, 32)
     if ((e = cudaFuncSetAttribute(k_permute_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmem))) return e;
@@ -475,6 +627,15 @@ void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, i
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk) {
     const int ni = g.ihi - g.ilo, nj = g.jhi - g.jlo;
     if (ni <= 0 || nj <= 0 || g.kdim <= 0 || nbatch <= 0) return;
+    if (g_gemm_pipe && !wt && !batchk && g.kdim <= GM_KC && !g.wscale) {
+        const int nti = cdiv_i(ni, GP_BM), ntj = cdiv_i(nj, GP_BN);
+        const long total = (long)nbatch * nti * ntj;
+        if (total < (1L << 31)) {
+            const int grid = (int)std::min<long>(total, 2L * g_num_sms);
+            k_gemm_pipe<<<grid, 256, kPipeSmem, st>>>(g, nti, ntj, (int)total);
+            return;
+        }
+    }
     const int bm = g_gemm_bm;
     dim3 grid(cdiv_i(nj, GM_T), cdiv_i(ni, bm), batchk ? 1 : nbatch);
     const size_t sm = gemm_smem(wt, bm);

@@ -39,6 +39,7 @@ struct GnbElimWork {
 
 cudaError_t gnb_kernels_init();
 void gnb_set_gemm_bm(int bm);
+void gnb_set_gemm_pipe(int on);
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E);
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,

@@ -8,8 +8,8 @@ fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
 out = {}
 for n, M in ((1024, 296), (512, 1184)):
-    for k in (32, 64, 128):
-        for bm in (64, 32):
+    for k in (32, 64):
+        for bm in (64, 32, 0):
             ms = C.c_double()
             rc = fn(ctx.h, M, n, k, bm, 5, C.byref(ms))
             assert rc == 0, ctx.lib.gnb_last_error(ctx.h)
