@@ -84,6 +84,14 @@ extern "C" int gnb_gemm_stats(gnb_ctx* c, double* ms, double* flops, int64_t* la
     if (reset) c->gemm_timer.reset();
     return GNB_OK;
 }
+extern "C" int gnb_dev_set_option(const char* name, int value) {     // developer A/B switches
+    if (!name) return GNB_ERR_ARG;
+    if (!strcmp(name, "two_level")) gnb_set_two_level(value);
+    else if (!strcmp(name, "gemm_pipe")) gnb_set_gemm_pipe(value);
+    else if (!strcmp(name, "gemm_bm")) gnb_set_gemm_bm(value);
+    else return GNB_ERR_ARG;
+    return GNB_OK;
+}
 extern "C" int gnb_set_timing(gnb_ctx* c, int on) { if (!c) return GNB_ERR_ARG; c->timing = on != 0; return GNB_OK; }
 
 static int put(gnb_ctx* c, DevBuf& buf, const void* src, size_t bytes, int loc) {
@@ -219,13 +227,13 @@ GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc) {
     auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
     need(c->cand0, (size_t)M * cand_stride * sizeof(int));
     need(c->cand1, (size_t)M * cand_stride * sizeof(int));
-    need(c->LU, (size_t)M * GNB_NB * GNB_NB * sizeof(cplx));
-    need(c->moves, (size_t)M * GNB_MOVES_STRIDE * sizeof(int));
+    need(c->LU, (size_t)2 * M * GNB_NB * GNB_NB * sizeof(cplx));
+    need(c->moves, (size_t)2 * M * GNB_MOVES_STRIDE * sizeof(int));
     need(c->info, sizeof(int) * 4);
     if (jordan) {
         need(c->perm, (size_t)M * N * sizeof(int));
         need(c->invperm, (size_t)M * N * sizeof(int));
-        need(c->Pws, (size_t)M * N * GNB_NB * sizeof(cplx));
+        need(c->Pws, (size_t)M * N * 2 * GNB_NB * sizeof(cplx));
     }
     if (e != cudaSuccess) { *rc = gnb_cuda_fail(c, e, "workspace allocation"); return w; }
     w.cand0 = c->cand0.as<int>(); w.cand1 = c->cand1.as<int>(); w.cand_stride = cand_stride;
@@ -365,7 +373,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     const int N = c->N, ld = round_up(N, 2);
     const size_t nn = (size_t)N * N;
     const bool needG = mode == MODE_GREEN || mode == MODE_T_DENSE || mode == MODE_GLESS_DENSE || mode == MODE_T_SPIN;
-    size_t per = (size_t)N * ld * 16 + (size_t)N * GNB_NB * 16 + 8 * (size_t)N + 16384;
+    size_t per = (size_t)N * ld * 16 + (size_t)N * 2 * GNB_NB * 16 + 8 * (size_t)N + 32768;
     if (needG && !(mode == MODE_GREEN && loc == GNB_DEVICE)) per += nn * 16;
     if (mode == MODE_T_DENSE || mode == MODE_T_SPIN) per += 2 * nn * 16;
     if (mode == MODE_GLESS_DENSE) per += nn * 16;
@@ -669,7 +677,7 @@ extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, do
     int rc = begin_call(c);
     if (rc) return rc;
     const size_t nn = (size_t)n * n;
-    const size_t per = 2 * nn * 16 + (size_t)n * GNB_NB * 16 + 8 * (size_t)n + 16384;
+    const size_t per = 2 * nn * 16 + (size_t)n * 2 * GNB_NB * 16 + 8 * (size_t)n + 32768;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     for (int k0 = 0; k0 < M; k0 += Mc) {
         const int m = std::min(Mc, M - k0);

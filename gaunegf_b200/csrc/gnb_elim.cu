@@ -236,13 +236,21 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
 // JORDAN: columns of the pivot block get the identity as right-hand side (in-place inverse trick).
 // ------------------------------------------------------------------------------------------
 #define PS_TC 64
+// mode 0: FORWARD rule (form W only for columns right of the pivot block), 1: JORDAN rule (all
+// columns; identity right-hand side in the pivot columns), 2: row moves only.
+// pre_L != nullptr (two-level elimination, second inner block on the far columns): the pivot rows
+// first receive the pending update of the first inner block, R -= pre_L * W_a, with pre_L the
+// w x pre_k block left of the pivot block and W_a = rows [pre_row, pre_row + pre_k) of A.
 __global__ void __launch_bounds__(256) k_permute_solve(cplx* __restrict__ A, long strideA, int ld,
                                                        int c0, int w, int col_lo, int col_hi,
                                                        const int* __restrict__ moves,
-                                                       const cplx* __restrict__ LU, int jordan) {
+                                                       const cplx* __restrict__ LU, int mode,
+                                                       const cplx* __restrict__ pre_L, long strideL, int ldL,
+                                                       int pre_row, int pre_k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);                 // [2*NB][PS_TC]
     cplx* sLU = tile + 2 * GNB_NB * PS_TC;                          // [NB][NB]
+    cplx* sL = sLU + GNB_NB * GNB_NB;                               // [NB][NB] (pre-update block)
     __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
     const int b = blockIdx.y, t = threadIdx.x;
     const int cs = col_lo + blockIdx.x * PS_TC;
@@ -250,21 +258,45 @@ __global__ void __launch_bounds__(256) k_permute_solve(cplx* __restrict__ A, lon
     const int* mv = moves + (long)b * GNB_MOVES_STRIDE;
     const int nm = mv[0];
     if (t < nm) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
-    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) sLU[idx] = LU[(long)b * GNB_NB * GNB_NB + idx];
+    if (mode != 2)
+        for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) sLU[idx] = LU[(long)b * GNB_NB * GNB_NB + idx];
+    if (pre_L)
+        for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) {
+            const int i = idx / GNB_NB, j = idx - i * GNB_NB;
+            sL[idx] = (i < w && j < pre_k) ? pre_L[(long)b * strideL + (long)i * ldL + j] : cmake(0.0, 0.0);
+        }
     __syncthreads();
     for (int idx = t; idx < nm * PS_TC; idx += 256) {
         const int m = idx / PS_TC, c = idx - m * PS_TC, col = cs + c;
         tile[idx] = (col < col_hi) ? Ab[(long)s_src[m] * ld + col] : cmake(0.0, 0.0);
     }
     __syncthreads();
-    {
-        // W = (L11 U11)^-1 R : thread -> column c = t % 64, rows t/64 + 4 q (8 independent accumulators)
+    if (mode != 2) {
+        // thread -> column c = t % 64, rows t/64 + 4 q (8 independent accumulators)
         const int c = t & (PS_TC - 1), rg = t >> 6, col = cs + c;
         const bool in_piv = (col >= c0 && col < c0 + w);
-        const bool do_solve = (col < col_hi) && (jordan ? true : (col >= c0 + w));
+        const bool do_solve = (col < col_hi) && (mode == 1 ? true : (col >= c0 + w));
         cplx acc[8];
-        if (do_solve) {
-            if (in_piv) {                                       // identity right-hand side: W[:, K] = inverse
+        if (pre_L) {                                             // R = rows - pre_L * W_a
+            if (do_solve && !in_piv) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = tile[(rg + 4 * q) * PS_TC + c];
+                for (int j = 0; j < pre_k; j++) {
+                    const cplx wa = Ab[(long)(pre_row + j) * ld + col];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc[q] = cfnma(acc[q], sL[(rg + 4 * q) * GNB_NB + j], wa);
+                }
+            }
+            __syncthreads();
+            if (do_solve && !in_piv) {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (rg + 4 * q < w) tile[(rg + 4 * q) * PS_TC + c] = acc[q];
+            }
+            __syncthreads();
+        }
+        if (do_solve) {                                          // W = (L11 U11)^-1 R
+            if (in_piv) {                                        // identity right-hand side: W[:, K] = inverse
 #pragma unroll
                 for (int q = 0; q < 8; q++) acc[q] = sLU[(rg + 4 * q) * GNB_NB + (col - c0)];
             } else {
@@ -294,7 +326,8 @@ __global__ void __launch_bounds__(256) k_permute_solve(cplx* __restrict__ A, lon
 // JORDAN: save the (permuted) panel column as the left GEMM operand and clear it in place, so that
 // the rank-NB update  A <- A - P W  writes  -P W[:,K]  there (in-place inverse).
 __global__ void __launch_bounds__(256) k_save_panel(cplx* __restrict__ A, long strideA, int ld, int nrows,
-                                                    int c0, int w, cplx* __restrict__ Pws, long stridePws) {
+                                                    int c0, int w, cplx* __restrict__ Pws, long stridePws,
+                                                    int pld, int pcol) {
     const int b = blockIdx.y;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nrows * GNB_NB; idx += gridDim.x * blockDim.x) {
         const int i = idx / GNB_NB, c = idx - i * GNB_NB;
@@ -305,7 +338,7 @@ __global__ void __launch_bounds__(256) k_save_panel(cplx* __restrict__ A, long s
             v = *a;
             *a = cmake(0.0, 0.0);
         }
-        Pws[(long)b * stridePws + idx] = v;
+        Pws[(long)b * stridePws + (long)i * pld + pcol + c] = v;
     }
 }
 
@@ -459,11 +492,12 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
     const int gid = lane >> 2, tig = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
     const int per_mat = nti * ntj;
+    const int nch = (g.kdim + GM_KC - 1) / GM_KC;               // K chunks of 32 = pipeline items per tile
 
-    auto issue_loads = [&](int tile, int stage) {
+    auto issue_loads = [&](int tile, int ch, int stage) {
         const int b = tile / per_mat, rem = tile - b * per_mat;
         const int ti = rem / ntj, tj = rem - ti * ntj;
-        const int i0 = g.ilo + ti * GP_BM, j0 = g.jlo + tj * GP_BN;
+        const int i0 = g.ilo + ti * GP_BM, j0 = g.jlo + tj * GP_BN, k0 = ch * GM_KC;
         const cplx* Pb = g.P + (long)b * g.strideP;
         const cplx* Wb = g.W + (long)b * g.strideW;
         cplx* Ps = sm + stage * GP_STAGE;
@@ -472,15 +506,15 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
         for (int q = 0; q < (GP_BM * GM_KC) / 256; q++) {
             const int idx = tid + q * 256;
             const int r = idx / GM_KC, k = idx - r * GM_KC;
-            const bool ok = (i0 + r < g.ihi) && (k < g.kdim);
-            cp_async16(&Ps[r * GP_PS + k], ok ? (const void*)(Pb + (long)(i0 + r) * g.ldp + k) : (const void*)g.P, ok ? 16 : 0);
+            const bool ok = (i0 + r < g.ihi) && (k0 + k < g.kdim);
+            cp_async16(&Ps[r * GP_PS + k], ok ? (const void*)(Pb + (long)(i0 + r) * g.ldp + k0 + k) : (const void*)g.P, ok ? 16 : 0);
         }
 #pragma unroll
         for (int q = 0; q < (GM_KC * GP_BN) / 256; q++) {
             const int idx = tid + q * 256;
             const int k = idx / GP_BN, n = idx - k * GP_BN;
-            const bool ok = (k < g.kdim) && (j0 + n < g.jhi);
-            cp_async16(&Ws[k * GP_WS + n], ok ? (const void*)(Wb + (long)k * g.ldw + j0 + n) : (const void*)g.W, ok ? 16 : 0);
+            const bool ok = (k0 + k < g.kdim) && (j0 + n < g.jhi);
+            cp_async16(&Ws[k * GP_WS + n], ok ? (const void*)(Wb + (long)(k0 + k) * g.ldw + j0 + n) : (const void*)g.W, ok ? 16 : 0);
         }
     };
     auto load_c = [&](int tile, double (&cr)[2][2][2], double (&ci)[2][2][2]) {
@@ -507,7 +541,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
     int tile = blockIdx.x;
     if (tile >= total) return;
     double cre[2][2][2], cim[2][2][2], pre[2][2][2], pim[2][2][2];
-    issue_loads(tile, 0);
+    issue_loads(tile, 0, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     load_c(tile, cre, cim);
     const unsigned smask = g.plus ? 0u : 0x80000000u;     // C -= P W : flip the sign bit of the A fragments
@@ -515,34 +549,40 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
     for (;;) {
         const int next = tile + gridDim.x;
         const bool has_next = next < total;
-        if (has_next) issue_loads(next, stage ^ 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (has_next) load_c(next, pre, pim);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
-        const cplx* Ps = sm + stage * GP_STAGE;
-        const cplx* Ws = Ps + GP_BM * GP_PS;
-        const int kend = min(GM_KC, (g.kdim + 3) & ~3);
+        for (int ch = 0; ch < nch; ch++) {
+            // item (tile, ch) has landed for this thread; the barrier also certifies that every warp
+            // is done with the other stage, which is refilled right away with the next item.
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (ch + 1 < nch) issue_loads(tile, ch + 1, stage ^ 1);
+            else if (has_next) issue_loads(next, 0, stage ^ 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (ch == 0 && has_next) load_c(next, pre, pim);          // C fragment of the next tile -> registers
+            const cplx* Ps = sm + stage * GP_STAGE;
+            const cplx* Ws = Ps + GP_BM * GP_PS;
+            const int kend = min(GM_KC, (g.kdim - ch * GM_KC + 3) & ~3);
 #pragma unroll 2
-        for (int kk = 0; kk < kend; kk += 4) {
-            cplx af[2], bf[2];
+            for (int kk = 0; kk < kend; kk += 4) {
+                cplx af[2], bf[2];
 #pragma unroll
-            for (int mi = 0; mi < 2; mi++) af[mi] = Ps[(wm * 16 + mi * 8 + gid) * GP_PS + kk + tig];
+                for (int mi = 0; mi < 2; mi++) af[mi] = Ps[(wm * 16 + mi * 8 + gid) * GP_PS + kk + tig];
 #pragma unroll
-            for (int ni = 0; ni < 2; ni++) bf[ni] = Ws[(kk + tig) * GP_WS + wn * 16 + ni * 8 + gid];
+                for (int ni = 0; ni < 2; ni++) bf[ni] = Ws[(kk + tig) * GP_WS + wn * 16 + ni * 8 + gid];
 #pragma unroll
-            for (int mi = 0; mi < 2; mi++) {
-                const double ax = flipsign(af[mi].x, smask), ay = flipsign(af[mi].y, smask);
-                const double nay = flipsign(ay, 0x80000000u);
+                for (int mi = 0; mi < 2; mi++) {
+                    const double ax = flipsign(af[mi].x, smask), ay = flipsign(af[mi].y, smask);
+                    const double nay = flipsign(ay, 0x80000000u);
 #pragma unroll
-                for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], ax, bf[ni].x);
+                    for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], ax, bf[ni].x);
 #pragma unroll
-                for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ax, bf[ni].y);
+                    for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ax, bf[ni].y);
 #pragma unroll
-                for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nay, bf[ni].y);
+                    for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nay, bf[ni].y);
 #pragma unroll
-                for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ay, bf[ni].x);
+                    for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ay, bf[ni].x);
+                }
             }
+            stage ^= 1;
         }
         {
             const int b = tile / per_mat, rem = tile - b * per_mat;
@@ -562,7 +602,6 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
                 }
         }
         if (!has_next) break;
-        __syncthreads();                 // every warp is done with this stage before it is refilled
 #pragma unroll
         for (int mi = 0; mi < 2; mi++)
 #pragma unroll
@@ -571,8 +610,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
                 cim[mi][ni][0] = pim[mi][ni][0]; cim[mi][ni][1] = pim[mi][ni][1];
             }
         tile = next;
-        stage ^= 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -589,7 +628,7 @@ void gnb_set_gemm_bm(int bm) { g_gemm_bm = (bm == 32) ? 32 : 64; }
 static size_t gemm_smem(bool wt, int bm) {
     return (size_t)(bm * GM_PS + (wt ? GM_T * GM_PS : GM_KC * GM_WS)) * sizeof(cplx);
 }
-static const size_t kPsSmem = (size_t)(2 * GNB_NB * PS_TC + GNB_NB * GNB_NB) * sizeof(cplx);
+static const size_t kPsSmem = (size_t)(2 * GNB_NB * PS_TC + 2 * GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_kernels_init() {
     cudaError_t e;
@@ -627,7 +666,7 @@ void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, i
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk) {
     const int ni = g.ihi - g.ilo, nj = g.jhi - g.jlo;
     if (ni <= 0 || nj <= 0 || g.kdim <= 0 || nbatch <= 0) return;
-    if (g_gemm_pipe && !wt && !batchk && g.kdim <= GM_KC && !g.wscale) {
+    if (g_gemm_pipe && !wt && !batchk && g.kdim <= 4 * GM_KC && !g.wscale) {
         const int nti = cdiv_i(ni, GP_BM), ntj = cdiv_i(nj, GP_BN);
         const long total = (long)nbatch * nti * ntj;
         if (total < (1L << 31)) {
@@ -651,19 +690,22 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
 // Block elimination of a batch of M matrices  [A | B]  (N x (N + naug), leading dimension ld).
 //   jordan = 1 : A <- (P A)^-1 in place, perm[pos] = original row now at pos  (A^-1[:, perm[pos]] = stored[:, pos])
 //   jordan = 0 : forward elimination + back-substitution; the naug augmented columns end up holding A^-1 B
-long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
-                   const GnbElimWork& ws) {
-    long launches = 0;
-    if (M <= 0) return 0;
-    if (jordan) {
-        dim3 grid(cdiv_i(N, 256), M);
-        k_init_perm<<<grid, 256, 0, st>>>(ws.perm, ws.perm_stride, N);
-        launches++;
-    }
-    const int nblk = (N + GNB_NB - 1) / GNB_NB;
-    for (int blk = 0; blk < nblk; blk++) {
-        const int c0 = blk * GNB_NB, w = min(GNB_NB, N - c0);
-        // --- tournament rounds
+// Two-level blocking: pivoting and the pivot-row products advance in 32-column inner blocks, but
+// only the 64 "near" columns of an outer step are updated block by block; every other ("far")
+// column receives ONE rank-64 update per outer step, which halves the C traffic of the dominant
+// kernel (tools/proto_blockgj.py: two_level_jordan / two_level_forward are the numpy models).
+static int g_two_level = 1;
+void gnb_set_two_level(int on) { g_two_level = on; }
+
+namespace {
+struct Elim {
+    cudaStream_t st; int M, N, naug; cplx* A; long strideA; int ld; int jordan;
+    const GnbElimWork& ws; long launches;
+
+    cplx* lu(int slot) const { return ws.LU + (long)slot * M * GNB_NB * GNB_NB; }
+    int* mv(int slot) const { return ws.moves + (long)slot * M * GNB_MOVES_STRIDE; }
+
+    void tournament(int c0, int w, int slot) {
         int n = N - c0;
         const int* cin = nullptr;
         int* cout = ws.cand0;
@@ -671,58 +713,130 @@ long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long stride
             const int groups = cdiv_i(n, GNB_GROUP);
             const int fin = groups == 1;
             dim3 grid(groups, M);
-            k_tourn<<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, ws.cand_stride, cout,
-                                                  ws.cand_stride, fin, ws.LU, ws.moves,
-                                                  jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+            k_tourn<<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, ws.cand_stride, cout, ws.cand_stride,
+                                                  fin, lu(slot), mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride,
+                                                  ws.info);
             launches++;
             if (fin) break;
             n = (groups - 1) * w + min(w, n - (groups - 1) * GNB_GROUP);
             cin = cout;
             cout = (cout == ws.cand0) ? ws.cand1 : ws.cand0;
         }
-        // --- row moves + W
-        const int col_lo = jordan ? 0 : c0, col_hi = jordan ? N : N + naug;
-        {
-            dim3 grid(cdiv_i(col_hi - col_lo, PS_TC), M);
-            k_permute_solve<<<grid, 256, kPsSmem, st>>>(A, strideA, ld, c0, w, col_lo, col_hi, ws.moves, ws.LU, jordan);
-            launches++;
-        }
+    }
+    void permute_solve(cplx* buf, long stride, int bld, int c0, int w, int lo, int hi, int slot, int mode,
+                       const cplx* preL = nullptr, long strideL = 0, int ldL = 0, int pre_row = 0, int pre_k = 0) {
+        if (hi <= lo) return;
+        dim3 grid(cdiv_i(hi - lo, PS_TC), M);
+        k_permute_solve<<<grid, 256, kPsSmem, st>>>(buf, stride, bld, c0, w, lo, hi, mv(slot), lu(slot), mode, preL,
+                                                     strideL, ldL, pre_row, pre_k);
+        launches++;
+    }
+    void save_panel(int c0, int w, int pld, int pcol) {
+        dim3 grid(min(cdiv_i((long)N * GNB_NB, 256), 1024), M);
+        k_save_panel<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, w, ws.Pws, (long)N * pld, pld, pcol);
+        launches++;
+    }
+    void gemm(int ilo, int ihi, int jlo, int jhi, const cplx* P, long strideP, int ldp, const cplx* W, int kdim,
+              int skip_lo, int skip_hi) {
+        if (ihi <= ilo || jhi <= jlo || kdim <= 0) return;
         GnbGemmArgs g{};
         g.C = A; g.strideC = strideA; g.ldc = ld;
-        g.W = A + (long)c0 * ld; g.strideW = strideA; g.ldw = ld;
-        g.kdim = w; g.zero_init = 0; g.plus = 0; g.wscale = nullptr; g.nbatch_k = 0;
+        g.P = P; g.strideP = strideP; g.ldp = ldp;
+        g.W = W; g.strideW = strideA; g.ldw = ld;
+        g.ilo = ilo; g.ihi = ihi; g.jlo = jlo; g.jhi = jhi; g.kdim = kdim;
+        g.skip_lo = skip_lo; g.skip_hi = skip_hi; g.zero_init = 0; g.plus = 0; g.wscale = nullptr; g.nbatch_k = 0;
+        if (ws.timer) ws.timer->begin(st);
+        gnb_launch_gemm(st, g, M, false, false);
+        if (ws.timer) ws.timer->end(st, 8.0 * (double)(ihi - ilo) * (double)(jhi - jlo) * kdim * M);
+        launches++;
+    }
+
+    void single_step(int c0, int w) {
+        tournament(c0, w, 0);
         if (jordan) {
-            dim3 grid(min(cdiv_i((long)N * GNB_NB, 256), 1024), M);
-            k_save_panel<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, w, ws.Pws, (long)N * GNB_NB);
-            launches++;
-            g.P = ws.Pws; g.strideP = (long)N * GNB_NB; g.ldp = GNB_NB;
-            g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = N; g.skip_lo = c0; g.skip_hi = c0 + w;
+            permute_solve(A, strideA, ld, c0, w, 0, N, 0, 1);
+            save_panel(c0, w, GNB_NB, 0);
+            gemm(0, N, 0, N, ws.Pws, (long)N * GNB_NB, GNB_NB, A + (long)c0 * ld, w, c0, c0 + w);
         } else {
-            g.P = A + c0; g.strideP = strideA; g.ldp = ld;
-            g.ilo = c0 + w; g.ihi = N; g.jlo = c0 + w; g.jhi = N + naug; g.skip_lo = g.skip_hi = -1;
+            permute_solve(A, strideA, ld, c0, w, c0, N + naug, 0, 0);
+            gemm(c0 + w, N, c0 + w, N + naug, A + c0, strideA, ld, A + (long)c0 * ld, w, -1, -1);
         }
-        if (g.ihi > g.ilo && g.jhi > g.jlo) {
-            if (ws.timer) ws.timer->begin(st);
-            gnb_launch_gemm(st, g, M, false, false);
-            if (ws.timer) ws.timer->end(st, 8.0 * (double)(g.ihi - g.ilo) * (double)(g.jhi - g.jlo) * g.kdim * M);
-            launches++;
+    }
+
+    void double_step(int c0, int wb) {
+        const int wa = GNB_NB, cb = c0 + GNB_NB, near_hi = cb + wb;
+        const cplx* Wa = A + (long)c0 * ld;                 // rows of inner block a (and b below it)
+        const cplx* Wb = A + (long)cb * ld;
+        if (!jordan) {
+            tournament(c0, wa, 0);
+            permute_solve(A, strideA, ld, c0, wa, c0, near_hi, 0, 0);
+            gemm(cb, N, cb, near_hi, A + c0, strideA, ld, Wa, wa, -1, -1);
+            tournament(cb, wb, 1);
+            permute_solve(A, strideA, ld, cb, wb, c0, near_hi, 1, 2);
+            const int far_lo = near_hi, far_hi = N + naug;
+            permute_solve(A, strideA, ld, c0, wa, far_lo, far_hi, 0, 0);
+            permute_solve(A, strideA, ld, cb, wb, far_lo, far_hi, 1, 0, A + (long)cb * ld + c0, strideA, ld, c0, wa);
+            gemm(near_hi, N, far_lo, far_hi, A + c0, strideA, ld, Wa, wa + wb, -1, -1);
+            return;
+        }
+        const long sP = (long)N * 64;
+        tournament(c0, wa, 0);
+        permute_solve(A, strideA, ld, c0, wa, c0, near_hi, 0, 1);
+        save_panel(c0, wa, 64, 0);
+        gemm(0, N, c0, near_hi, ws.Pws, sP, 64, Wa, wa, c0, cb);
+        tournament(cb, wb, 1);
+        permute_solve(A, strideA, ld, cb, wb, c0, near_hi, 1, 1);
+        permute_solve(ws.Pws, sP, 64, 0, 0, 0, GNB_NB, 1, 2);         // the saved panel follows the row moves
+        save_panel(cb, wb, 64, GNB_NB);
+        gemm(0, N, c0, near_hi, ws.Pws + GNB_NB, sP, 64, Wb, wb, cb, near_hi);
+        const int lo[2] = {0, near_hi}, hi[2] = {c0, N};
+        for (int r = 0; r < 2; r++) {
+            if (hi[r] <= lo[r]) continue;
+            permute_solve(A, strideA, ld, c0, wa, lo[r], hi[r], 0, 1);
+            permute_solve(A, strideA, ld, cb, wb, lo[r], hi[r], 1, 1, ws.Pws + (long)cb * 64, sP, 64, c0, wa);
+            gemm(0, N, lo[r], hi[r], ws.Pws, sP, 64, Wa, wa + wb, c0, near_hi);           // rows outside both blocks
+            gemm(c0, cb, lo[r], hi[r], ws.Pws + GNB_NB, sP, 64, Wb, wb, -1, -1);           // then W_a -= W_a[:,Kb] W_b
+        }
+    }
+};
+}  // namespace
+
+long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
+                   const GnbElimWork& ws) {
+    if (M <= 0) return 0;
+    Elim e{st, M, N, naug, A, strideA, ld, jordan, ws, 0};
+    if (jordan) {
+        dim3 grid(cdiv_i(N, 256), M);
+        k_init_perm<<<grid, 256, 0, st>>>(ws.perm, ws.perm_stride, N);
+        e.launches++;
+    }
+    int c0 = 0;
+    while (c0 < N) {
+        const int rest = N - c0;
+        if (g_two_level && rest > GNB_NB) {
+            e.double_step(c0, min(GNB_NB, rest - GNB_NB));
+            c0 += 2 * GNB_NB;
+        } else {
+            e.single_step(c0, min(GNB_NB, rest));
+            c0 += GNB_NB;
         }
     }
     if (!jordan && naug > 0) {
         // X[0:c0,:] -= Wstored[0:c0, K] X[K,:]  from the last block upwards (unit block upper triangular)
+        const int nblk = (N + GNB_NB - 1) / GNB_NB;
         for (int blk = nblk - 1; blk >= 1; blk--) {
-            const int c0 = blk * GNB_NB, w = min(GNB_NB, N - c0);
+            const int b0 = blk * GNB_NB, w = min(GNB_NB, N - b0);
             GnbGemmArgs g{};
             g.C = A + N; g.strideC = strideA; g.ldc = ld;
-            g.P = A + c0; g.strideP = strideA; g.ldp = ld;
-            g.W = A + (long)c0 * ld + N; g.strideW = strideA; g.ldw = ld;
-            g.ilo = 0; g.ihi = c0; g.jlo = 0; g.jhi = naug; g.kdim = w;
+            g.P = A + b0; g.strideP = strideA; g.ldp = ld;
+            g.W = A + (long)b0 * ld + N; g.strideW = strideA; g.ldw = ld;
+            g.ilo = 0; g.ihi = b0; g.jlo = 0; g.jhi = naug; g.kdim = w;
             g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
             if (ws.timer) ws.timer->begin(st);
             gnb_launch_gemm(st, g, M, false, false);
-            if (ws.timer) ws.timer->end(st, 8.0 * (double)c0 * (double)naug * g.kdim * M);
-            launches++;
+            if (ws.timer) ws.timer->end(st, 8.0 * (double)b0 * (double)naug * g.kdim * M);
+            e.launches++;
         }
     }
-    return launches;
+    return e.launches;
 }

@@ -30,16 +30,17 @@ struct GnbGemmTimer {
 struct GnbElimWork {
     GnbGemmTimer* timer;                       // nullptr = no per-kernel timing
     int* cand0; int* cand1; int cand_stride;   // tournament candidate lists
-    cplx* LU;                                  // [M][NB][NB] compact LU of the pivot block
-    int* moves;                                // [M][GNB_MOVES_STRIDE]
+    cplx* LU;                                  // [2][M][NB][NB] inverse of the pivot block (two slots)
+    int* moves;                                // [2][M][GNB_MOVES_STRIDE]
     int* perm; int perm_stride;                // [M][N] running row permutation (JORDAN)
-    cplx* Pws;                                 // [M][N][NB] saved panel (JORDAN)
+    cplx* Pws;                                 // [M][N][2*NB] saved panel columns (JORDAN)
     int* info;                                 // device flag: 1 = exactly singular pivot met
 };
 
 cudaError_t gnb_kernels_init();
 void gnb_set_gemm_bm(int bm);
 void gnb_set_gemm_pipe(int on);
+void gnb_set_two_level(int on);
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E);
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,

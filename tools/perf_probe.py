@@ -14,6 +14,10 @@ def ev(f, n=2):
     return best
 
 ctx = Context(0)
+import ctypes, os
+for opt in ("two_level", "gemm_pipe"):
+    if opt.upper() in os.environ:
+        ctx.lib.gnb_dev_set_option(opt.encode(), int(os.environ[opt.upper()]))
 ctx.set_timing(True)
 out = {}
 for N, nc, M in ((256, 16, 1184), (512, 32, 592), (1024, 64, 296), (2048, 64, 74)):
