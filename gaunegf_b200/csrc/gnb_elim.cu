@@ -561,13 +561,45 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
             const cplx* Ps = sm + stage * GP_STAGE;
             const cplx* Ws = Ps + GP_BM * GP_PS;
             const int kend = min(GM_KC, (g.kdim - ch * GM_KC + 3) & ~3);
+#ifndef GP_VARIANT
+#define GP_VARIANT 0
+#endif
+#if GP_VARIANT == 2 || GP_VARIANT == 3
+#pragma unroll
+#else
 #pragma unroll 2
-            for (int kk = 0; kk < kend; kk += 4) {
+#endif
+            for (int kk = 0; kk < GM_KC; kk += 4) {
+                if (kk < kend) {
                 cplx af[2], bf[2];
 #pragma unroll
                 for (int mi = 0; mi < 2; mi++) af[mi] = Ps[(wm * 16 + mi * 8 + gid) * GP_PS + kk + tig];
 #pragma unroll
                 for (int ni = 0; ni < 2; ni++) bf[ni] = Ws[(kk + tig) * GP_WS + wn * 16 + ni * 8 + gid];
+#if GP_VARIANT == 1 || GP_VARIANT == 3
+                double ax[2], ay[2], nay[2];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+                    ax[mi] = flipsign(af[mi].x, smask); ay[mi] = flipsign(af[mi].y, smask);
+                    nay[mi] = flipsign(ay[mi], 0x80000000u);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], ax[mi], bf[ni].x);
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ax[mi], bf[ni].y);
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nay[mi], bf[ni].y);
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ay[mi], bf[ni].x);
+#else
 #pragma unroll
                 for (int mi = 0; mi < 2; mi++) {
                     const double ax = flipsign(af[mi].x, smask), ay = flipsign(af[mi].y, smask);
@@ -580,6 +612,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm_pipe(GnbGemmArgs g, int nti, in
                     for (int ni = 0; ni < 2; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nay, bf[ni].y);
 #pragma unroll
                     for (int ni = 0; ni < 2; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], ay, bf[ni].x);
+                }
+#endif
                 }
             }
             stage ^= 1;
