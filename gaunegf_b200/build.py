@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libgaunegf_b200.so")
-SOURCES = ["gnb_elim.cu", "gnb_reduce.cu", "gnb_sigma.cu", "gnb_small.cu", "gnb_api.cu"]
+SOURCES = ["gnb_elim.cu", "gnb_rec.cu", "gnb_reduce.cu", "gnb_sigma.cu", "gnb_small.cu", "gnb_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -21,6 +21,7 @@ int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where) {
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
 
 extern "C" const char* gnb_version(void) { return "gaunegf_b200 0.1 (sm_100a)"; }
 
@@ -34,7 +35,7 @@ extern "C" int gnb_create(gnb_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GNB_ERR_CUDA; }
     gnb_ctx* c = new gnb_ctx();
     c->device = device;
-    if (gnb_kernels_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+    if (gnb_kernels_init() != cudaSuccess || gnb_rec_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
         cudaEventCreate(&c->ev1) != cudaSuccess) {
         cudaGetLastError();
         delete c;
@@ -59,7 +60,7 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     DevBuf* bufs[] = {&c->dF, &c->dS, &c->dSig0, &c->A, &c->Pws, &c->LU, &c->moves, &c->cand0, &c->cand1,
                       &c->perm, &c->invperm, &c->info, &c->dE, &c->dW, &c->G, &c->Y, &c->Z, &c->Xr, &c->out,
                       &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
-                      &c->in_stage, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
+                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
     for (DevBuf* b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -89,6 +90,8 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     if (!strcmp(name, "two_level")) gnb_set_two_level(value);
     else if (!strcmp(name, "gemm_pipe")) gnb_set_gemm_pipe(value);
     else if (!strcmp(name, "gemm_bm")) gnb_set_gemm_bm(value);
+    else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
+    else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
     else return GNB_ERR_ARG;
     return GNB_OK;
 }
@@ -281,6 +284,91 @@ static int run_eliminate(gnb_ctx* c, int M, int N, int naug, cplx* A, long strid
     return GNB_OK;
 }
 
+// Matrix layout of a chunk.  The recursive engine (default) works on dimensions padded to multiples of 32
+// (identity on the padded diagonal, zero augmented columns); the single/two-level engine of gnb_elim.cu takes
+// the matrices as they are.  xoff = column at which the augmented right-hand side starts.
+struct Lay {
+    int N, naug, Np, naugp, ld, xoff;
+    bool rec, padded;
+    size_t bytes_per_energy(bool jordan) const {
+        size_t b = (size_t)Np * ld * 16 + 8 * (size_t)Np + 32768;
+        if (rec) b += gnb_rec_pk_elems(Np) * 16 * (jordan ? 2 : 1) + gnb_rec_wk_elems(Np, ld) * 16 + (size_t)(Np / 32) * (16384 + 4 * GNB_MOVES_STRIDE);
+        else if (jordan) b += (size_t)N * 2 * GNB_NB * 16;
+        return b;
+    }
+};
+static Lay make_layout(int N, int naug) {
+    Lay L{};
+    L.N = N; L.naug = naug; L.rec = g_engine_rec != 0;
+    if (L.rec) {
+        L.Np = round_up(N, 32); L.naugp = round_up(naug, 32); L.ld = L.Np + L.naugp; L.xoff = L.Np;
+        L.padded = (L.Np != N) || (L.naugp != naug);
+    } else {
+        L.Np = N; L.naugp = naug; L.ld = round_up(N + naug, 2); L.xoff = N; L.padded = false;
+    }
+    return L;
+}
+
+static GnbRecWork rec_work(gnb_ctx* c, int M, const Lay& L, bool jordan, int* rc) {
+    GnbRecWork w{};
+    *rc = GNB_OK;
+    const int Np = L.Np, nblk = Np / 32;
+    const int cand_stride = std::max(GNB_NB, (Np + 255) / 256 * GNB_NB);
+    cudaError_t e = cudaSuccess;
+    auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
+    need(c->cand0, (size_t)M * cand_stride * sizeof(int));
+    need(c->cand1, (size_t)M * cand_stride * sizeof(int));
+    need(c->LU, (size_t)nblk * M * GNB_NB * GNB_NB * sizeof(cplx));
+    need(c->moves, (size_t)nblk * M * GNB_MOVES_STRIDE * sizeof(int));
+    need(c->info, sizeof(int) * 4);
+    const size_t pk = gnb_rec_pk_elems(Np), wk = gnb_rec_wk_elems(Np, L.ld);
+    need(c->Ppk, (size_t)M * pk * sizeof(cplx));
+    need(c->Wpk, (size_t)M * wk * sizeof(cplx));
+    if (jordan) {
+        need(c->Lpk, (size_t)M * pk * sizeof(cplx));
+        need(c->perm, (size_t)M * Np * sizeof(int));
+        need(c->invperm, (size_t)M * Np * sizeof(int));
+    }
+    if (e != cudaSuccess) { *rc = gnb_cuda_fail(c, e, "workspace allocation"); return w; }
+    w.cand0 = c->cand0.as<int>(); w.cand1 = c->cand1.as<int>(); w.cand_stride = cand_stride;
+    w.inv = c->LU.as<cplx>(); w.moves = c->moves.as<int>();
+    w.perm = c->perm.as<int>(); w.perm_stride = Np;
+    w.Ppk = c->Ppk.as<cplx>(); w.Lpk = c->Lpk.as<cplx>(); w.stridePk = (long)pk;
+    w.Wpk = c->Wpk.as<cplx>(); w.strideWk = (long)wk;
+    w.info = c->info.as<int>();
+    w.timer = c->timing ? &c->gemm_timer : nullptr;
+    return w;
+}
+
+// padded rows/columns of a chunk: everything zero, identity on the padded diagonal (call BEFORE assembly)
+static int pad_chunk(gnb_ctx* c, int M, const Lay& L, cplx* A) {
+    if (!L.padded) return GNB_OK;
+    GNB_CK(cudaMemsetAsync(A, 0, (size_t)M * L.Np * L.ld * sizeof(cplx), c->stream));
+    if (L.Np != L.N) { gnb_launch_pad_diag(c->stream, M, A, (long)L.Np * L.ld, L.ld, L.N, L.Np); c->launches++; }
+    return GNB_OK;
+}
+
+static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
+    int rc;
+    const long strideA = (long)L.Np * L.ld;
+    if (L.rec) {
+        GnbRecWork w = rec_work(c, M, L, jordan != 0, &rc);
+        if (rc) return rc;
+        if (c->timing) GNB_CK(cudaEventRecord(c->ev0, c->stream));
+        c->launches += gnb_eliminate_rec(c->stream, M, L.Np, L.naugp, A, strideA, L.ld, jordan, w);
+        if (c->timing) {
+            GNB_CK(cudaEventRecord(c->ev1, c->stream));
+            GNB_CK(cudaEventSynchronize(c->ev1));
+            float ms = 0;
+            GNB_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            c->elim_ms += ms;
+        }
+        GNB_CK(cudaGetLastError());
+        return GNB_OK;
+    }
+    return run_eliminate(c, M, L.N, L.naug, A, strideA, L.ld, jordan);
+}
+
 static int chunk_size(gnb_ctx* c, int M, size_t bytes_per_energy) {
     size_t m = c->ws_limit / std::max<size_t>(bytes_per_energy, 1);
     m = std::max<size_t>(1, std::min<size_t>(m, 8192));
@@ -370,10 +458,12 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     if (M < 0 || (M > 0 && !E)) return gnb_fail(c, GNB_ERR_ARG, "bad energy list");
     int rc = begin_call(c);
     if (rc) return rc;
-    const int N = c->N, ld = round_up(N, 2);
+    const int N = c->N;
+    const Lay L = make_layout(N, 0);
+    const int ld = L.ld, Np = L.Np;
     const size_t nn = (size_t)N * N;
     const bool needG = mode == MODE_GREEN || mode == MODE_T_DENSE || mode == MODE_GLESS_DENSE || mode == MODE_T_SPIN;
-    size_t per = (size_t)N * ld * 16 + (size_t)N * 2 * GNB_NB * 16 + 8 * (size_t)N + 32768;
+    size_t per = L.bytes_per_energy(true);
     if (needG && !(mode == MODE_GREEN && loc == GNB_DEVICE)) per += nn * 16;
     if (mode == MODE_T_DENSE || mode == MODE_T_SPIN) per += 2 * nn * 16;
     if (mode == MODE_GLESS_DENSE) per += nn * 16;
@@ -390,23 +480,25 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         const int m = std::min(Mc, M - k0);
         if ((rc = put_chunk_scalars(c, E, w, k0, m))) return rc;
         const cplx* dE = c->dE.as<cplx>();
-        GNB_CK(c->A.ensure((size_t)m * N * ld * sizeof(cplx)));
+        GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
         cplx* A = c->A.as<cplx>();
-        const long strideA = (long)N * ld;
+        const long strideA = (long)Np * ld;
         const cplx *sc = nullptr, *sb = nullptr;
         if (use_desc) {
             if ((rc = prepare_sigma(c, m, dE, 0))) return rc;
         } else if ((rc = stage_dense(c, c->sigB, sig, k0, m, &sc, &sb))) return rc;
+        if ((rc = pad_chunk(c, m, L, A))) return rc;
         if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, use_desc, sc, sb))) return rc;
-        if ((rc = run_eliminate(c, m, N, 0, A, strideA, ld, 1))) return rc;
-        gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), N, N);
+        if ((rc = run_eliminate(c, m, L, A, 1))) return rc;
+        gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), Np, Np);
         c->launches++;
         const int* inv = c->invperm.as<int>();
+        const int pst = Np;                      // stride of the permutation arrays
         cplx* G = nullptr;
         if (needG) {
             if (mode == MODE_GREEN && loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(out0) + (size_t)k0 * nn;
             else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
-            gnb_launch_unpermute(c->stream, m, N, A, strideA, ld, inv, N, G, (long)nn);
+            gnb_launch_unpermute(c->stream, m, N, A, strideA, ld, inv, pst, G, (long)nn);
             c->launches++;
         }
         if (mode == MODE_GREEN) {
@@ -416,7 +508,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         } else if (mode == MODE_DOS) {
             GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
             if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
-            gnb_launch_dos(c->stream, m, N, A, strideA, ld, inv, N, c->dDosT.as<double>(),
+            gnb_launch_dos(c->stream, m, N, A, strideA, ld, inv, pst, c->dDosT.as<double>(),
                            out1 ? c->dDosP.as<double>() : nullptr);
             c->launches++;
             GNB_CK(cudaMemcpyAsync(out0 + k0, c->dDosT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -424,7 +516,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
                 GNB_CK(cudaMemcpyAsync(out1 + (size_t)k0 * N, c->dDosP.p, (size_t)m * N * sizeof(double),
                                        cudaMemcpyDeviceToHost, c->stream));
         } else if (mode == MODE_GRINT) {
-            gnb_launch_weighted_sum(c->stream, m, N, A, strideA, ld, inv, N, c->dW.as<cplx>(), d_out, k0 > 0);
+            gnb_launch_weighted_sum(c->stream, m, N, A, strideA, ld, inv, pst, c->dW.as<cplx>(), d_out, k0 > 0);
             c->launches++;
         } else if (mode == MODE_T_DENSE) {
             const cplx *g1c, *g1b, *g2c, *g2b;
@@ -555,30 +647,32 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
     if (rc) return rc;
     const int N = c->N;
     const int n1 = c->contacts[ca].nc, n2 = c->contacts[cb].nc;
-    const int ld = round_up(N + n2, 2);
-    const size_t per = (size_t)N * ld * 16 + 3 * (size_t)n1 * n2 * 16 + 16384 +
+    const Lay L = make_layout(N, n2);
+    const int ld = L.ld, Np = L.Np;
+    const size_t per = L.bytes_per_energy(false) + 3 * (size_t)n1 * n2 * 16 + 16384 +
                        2 * ((size_t)n1 * n1 + (size_t)n2 * n2) * 16 * 4;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     for (int k0 = 0; k0 < M; k0 += Mc) {
         const int m = std::min(Mc, M - k0);
         if ((rc = put_chunk_scalars(c, E, nullptr, k0, m))) return rc;
         const cplx* dE = c->dE.as<cplx>();
-        GNB_CK(c->A.ensure((size_t)m * N * ld * sizeof(cplx)));
+        GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
         cplx* A = c->A.as<cplx>();
-        const long strideA = (long)N * ld;
+        const long strideA = (long)Np * ld;
         if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
         Contact& A1 = c->contacts[ca];
         Contact& A2 = c->contacts[cb];
+        if ((rc = pad_chunk(c, m, L, A))) return rc;
         if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr))) return rc;
-        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, A2.d_inds.as<int>(), n2);
+        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, A2.d_inds.as<int>(), n2);
         c->launches++;
-        if ((rc = run_eliminate(c, m, N, n2, A, strideA, ld, 0))) return rc;
+        if ((rc = run_eliminate(c, m, L, A, 0))) return rc;
         const long s12 = (long)n1 * n2;
         GNB_CK(c->Xr.ensure((size_t)m * s12 * sizeof(cplx)));
         GNB_CK(c->Y.ensure((size_t)m * s12 * sizeof(cplx)));
         GNB_CK(c->Z.ensure((size_t)m * s12 * sizeof(cplx)));
         GNB_CK(c->dT.ensure((size_t)m * sizeof(double)));
-        gnb_launch_gather_rows(c->stream, m, A + N, strideA, ld, A1.d_inds.as<int>(), n1, n2, c->Xr.as<cplx>(), s12);
+        gnb_launch_gather_rows(c->stream, m, A + L.xoff, strideA, ld, A1.d_inds.as<int>(), n1, n2, c->Xr.as<cplx>(), s12);
         GnbGemmArgs g{};
         g.skip_lo = g.skip_hi = -1; g.zero_init = 1; g.plus = 1;
         g.ilo = 0; g.ihi = n1; g.jlo = 0; g.jhi = n2;
@@ -620,31 +714,33 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         nmax = std::max(nmax, c->contacts[ci].nc);
     }
     const int naug = (int)cols.size();
-    const int ld = round_up(N + naug, 2);
+    const Lay L = make_layout(N, naug);
+    const int ld = L.ld, Np = L.Np;
     if ((rc = put(c, c->cols, cols.data(), cols.size() * sizeof(int), GNB_HOST))) return rc;
     cplx* d_out = nullptr;
     if ((rc = get_out(c, out, loc, &d_out))) return rc;
     if (M == 0) GNB_CK(cudaMemsetAsync(d_out, 0, (size_t)N * N * sizeof(cplx), c->stream));
-    const size_t per = (size_t)N * ld * 16 + (size_t)N * nmax * 16 + 16384 + 8 * (size_t)naug * nmax * 16;
+    const size_t per = L.bytes_per_energy(false) + (size_t)N * nmax * 16 + 16384 + 8 * (size_t)naug * nmax * 16;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     bool first = true;
     for (int k0 = 0; k0 < M; k0 += Mc) {
         const int m = std::min(Mc, M - k0);
         if ((rc = put_chunk_scalars(c, E, w, k0, m))) return rc;
         const cplx* dE = c->dE.as<cplx>();
-        GNB_CK(c->A.ensure((size_t)m * N * ld * sizeof(cplx)));
+        GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
         cplx* A = c->A.as<cplx>();
-        const long strideA = (long)N * ld;
+        const long strideA = (long)Np * ld;
         if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
+        if ((rc = pad_chunk(c, m, L, A))) return rc;
         if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr))) return rc;
-        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, c->cols.as<int>(), naug);
+        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, c->cols.as<int>(), naug);
         c->launches++;
-        if ((rc = run_eliminate(c, m, N, naug, A, strideA, ld, 0))) return rc;
+        if ((rc = run_eliminate(c, m, L, A, 0))) return rc;
         GNB_CK(c->Y.ensure((size_t)m * N * nmax * sizeof(cplx)));
         for (size_t u = 0; u < use.size(); u++) {
             Contact& ct = c->contacts[use[u]];
             const int nc = ct.nc;
-            const cplx* X = A + N + off[u];
+            const cplx* X = A + L.xoff + off[u];
             GnbGemmArgs g{};
             g.skip_lo = g.skip_hi = -1; g.zero_init = 1; g.plus = 1;
             g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = nc; g.kdim = nc;

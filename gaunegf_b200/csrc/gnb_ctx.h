@@ -82,7 +82,7 @@ struct gnb_ctx {
     std::vector<Contact> contacts;
     // workspaces
     DevBuf A, Pws, LU, moves, cand0, cand1, perm, invperm, info, dE, dW, G, Y, Z, Xr, out, dT, dDosT, dDosP,
-        sigB, gam1B, gam2B, cols, rows, in_stage;
+        sigB, gam1B, gam2B, cols, rows, in_stage, Ppk, Lpk, Wpk;
     // chain1d fixed-point workspaces
     DevBuf cA, cB, cg, cgn, cT1, cM, cflags, ct;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

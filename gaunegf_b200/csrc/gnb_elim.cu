@@ -48,14 +48,19 @@ __global__ void __launch_bounds__(256) k_scatter_sub(cplx* __restrict__ A, long 
     }
 }
 
-// Augmented right-hand side: A[b][i][N + c] = (i == cols[c])
-__global__ void __launch_bounds__(256) k_set_aug(cplx* __restrict__ A, long strideA, int ld, int N,
+// Augmented right-hand side: A[b][i][xoff + c] = (i == cols[c])
+__global__ void __launch_bounds__(256) k_set_aug(cplx* __restrict__ A, long strideA, int ld, int N, int xoff,
                                                  const int* __restrict__ cols, int m) {
     const int b = blockIdx.y;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * m; idx += gridDim.x * blockDim.x) {
         const int i = idx / m, c = idx - i * m;
-        A[(long)b * strideA + (long)i * ld + N + c] = cmake(i == cols[c] ? 1.0 : 0.0, 0.0);
+        A[(long)b * strideA + (long)i * ld + xoff + c] = cmake(i == cols[c] ? 1.0 : 0.0, 0.0);
     }
+}
+// identity on the padded diagonal [N, Np)
+__global__ void k_pad_diag(cplx* __restrict__ A, long strideA, int ld, int N, int Np) {
+    const int b = blockIdx.x, i = N + threadIdx.x;
+    if (i < Np) A[(long)b * strideA + (long)i * ld + i] = cmake(1.0, 0.0);
 }
 
 __global__ void k_init_perm(int* __restrict__ perm, int stride, int N) {
@@ -691,10 +696,14 @@ void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int l
     k_scatter_sub<<<grid, 256, 0, st>>>(A, strideA, ld, inds, nc, blk, strideBlk);
 }
 
-void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const int* cols, int m) {
+void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m) {
     if (M <= 0 || m <= 0) return;
     dim3 grid(min(cdiv_i((long)N * m, 256), 1024), M);
-    k_set_aug<<<grid, 256, 0, st>>>(A, strideA, ld, N, cols, m);
+    k_set_aug<<<grid, 256, 0, st>>>(A, strideA, ld, N, xoff, cols, m);
+}
+void gnb_launch_pad_diag(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int Np) {
+    if (M <= 0 || Np <= N) return;
+    k_pad_diag<<<M, 32, 0, st>>>(A, strideA, ld, N, Np);
 }
 
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk) {
@@ -719,6 +728,33 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
     } while (0)
     if (wt) { if (batchk) GNB_GO(true, true); else GNB_GO(true, false); }
     else { if (batchk) GNB_GO(false, true); else GNB_GO(false, false); }
+}
+
+// Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by both engines.
+long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
+                           int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
+                           int* info) {
+    int n = N - c0;
+    const int* cin = nullptr;
+    int* cout = cand0;
+    long launches = 0;
+    for (;;) {
+        const int groups = cdiv_i(n, GNB_GROUP);
+        const int fin = groups == 1;
+        dim3 grid(groups, M);
+        k_tourn<<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
+                                              perm, perm_stride, info);
+        launches++;
+        if (fin) break;
+        n = (groups - 1) * w + min(w, n - (groups - 1) * GNB_GROUP);
+        cin = cout;
+        cout = (cout == cand0) ? cand1 : cand0;
+    }
+    return launches;
+}
+void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N) {
+    dim3 grid(cdiv_i(N, 256), M);
+    k_init_perm<<<grid, 256, 0, st>>>(perm, stride, N);
 }
 
 // Block elimination of a batch of M matrices  [A | B]  (N x (N + naug), leading dimension ld).

@@ -45,10 +45,39 @@ void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, 
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E);
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,
                             const cplx* blk, long strideBlk);
-void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const int* cols, int m);
+void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m);
+void gnb_launch_pad_diag(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int Np);
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk);
 long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
                    const GnbElimWork& ws);
+
+long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
+                           int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
+                           int* info);
+void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N);
+
+// gnb_rec.cu : recursive (multi-level) elimination on a padded layout; the rank-K updates run on the
+// warp-specialised packed-operand DMMA kernel.  N and naug must be multiples of 32, ld = N + naug.
+#define RK_PPS 20                      // row stride (cplx) of a packed panel block [32 rows][16 k]
+#define RK_WPS 34                      // row stride (cplx) of a packed W block     [16 k][32 cols]
+#define RK_PBLK (32 * RK_PPS)
+#define RK_WBLK (16 * RK_WPS)
+struct GnbRecWork {
+    GnbGemmTimer* timer;
+    int* cand0; int* cand1; int cand_stride;
+    cplx* inv;                         // [N/32][M][32][32]   inverse of every pivot block
+    int* moves;                        // [N/32][M][GNB_MOVES_STRIDE]
+    int* perm; int perm_stride;        // JORDAN: running row permutation
+    cplx* Ppk; cplx* Lpk; long stridePk;   // packed panels [M][N/16][N/32][32][RK_PPS]
+    cplx* Wpk; long strideWk;          // packed pivot rows [M][N/16][ld/32][16][RK_WPS]
+    int* info;
+};
+size_t gnb_rec_pk_elems(int N);               // cplx elements per matrix of Ppk / Lpk (incl. slack)
+size_t gnb_rec_wk_elems(int N, int ld);       // cplx elements per matrix of Wpk (incl. slack)
+cudaError_t gnb_rec_init();
+void gnb_rec_set_option(const char* name, int value);
+long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
+                       const GnbRecWork& ws);
 
 // gnb_reduce.cu
 void gnb_launch_invperm(cudaStream_t st, int M, const int* perm, int* invperm, int stride, int N);

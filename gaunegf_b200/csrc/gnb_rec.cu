@@ -1,0 +1,563 @@
+// Recursive (multi-level) batched complex128 block elimination for sm_100a (B200).
+//
+// Same mathematics as gnb_elim.cu (tournament-pivoted block Gauss-Jordan / block Gaussian elimination of the
+// reference's `solve(A, I)`, utils.py:52-54, integrate.py:67-82, transport.py:150-157) but organised as a
+// binary recursion over column ranges so that the floating-point work sits in rank-K updates with K up to
+// N/2 instead of K = 32/64:  at N = 1024 more than 85 % of the update flops run at K >= 128
+// (tools/proto_recursive.py is the numpy model, kernel by kernel).
+//
+// The rank-K update  C -= P W  is a warp-specialised persistent kernel on the FP64 tensor pipe
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind):
+//   * operands are kept PACKED in global memory as ready-made shared-memory images
+//       Ppk[b][kc][rb][32][RK_PPS]   saved panel columns  (kc = 16-wide K chunk, rb = 32-row block)
+//       Wpk[b][kc][cb][16][RK_WPS]   normalised pivot rows (cb = 32-column block)
+//     so ONE producer lane feeds a 4-deep ring with two cp.async.bulk (TMA) copies per K chunk, completion
+//     on mbarriers (complete_tx); the row strides 20 / 34 make every LDS.128 fragment load conflict-free;
+//   * 8 consumer warps (4 x 2, warp tile 16 x 32) run LDS + DMMA with no CTA-wide barrier, accumulate from
+//     zero and read-modify-write C in the epilogue while the producer already streams the next tile;
+//   * optional 3M arithmetic (3 real DMMAs per complex tile product instead of 4).
+// One CTA per SM (persistent over the (matrix, row tile, column tile) space).
+#include <algorithm>
+#include <cstring>
+#include "gnb_common.cuh"
+#include "gnb_kernels.h"
+
+static inline int cdiv_i(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "RK_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RK_DONE;\n\t"
+        "bra RK_WAIT;\n\t"
+        "RK_DONE:\n\t}" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, int bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rank-K update on packed operands:  C[ilo:ihi, jlo:jhi] -= P[ilo:ihi, klo:khi] * W[klo:khi, jlo:jhi]
+// All bounds are multiples of 32.  CTA tile 64 x 64 anchored at (ilo, jlo); a trailing half tile is masked.
+// kskip != 0 (JORDAN far update): for row tiles inside [klo, khi) the panel is zero at and below the block
+// diagonal, so the K loop of such a tile starts at the chunk after the tile's first row block.
+// ------------------------------------------------------------------------------------------------
+struct RkGemmArgs {
+    cplx* C; long sC; int ldc;
+    const cplx* P; long sP; int nrb;
+    const cplx* W; long sW; int ncb;
+    int ilo, ihi, jlo, jhi, klo, khi;
+    int kskip;
+};
+
+#define RK_ST 4
+#define RK_PST (2 * RK_PBLK)
+#define RK_WST (2 * RK_WBLK)
+#define RK_STAGE (RK_PST + RK_WST)
+static const size_t kRkSmem = (size_t)RK_ST * RK_STAGE * sizeof(cplx) + 2 * RK_ST * 8;
+
+template <int M3>
+__global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int ntj, int total) {
+    constexpr int NCW = 8, WN = 2, MI = 2, NI = 4, KC = 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + RK_ST * RK_STAGE);
+    unsigned long long* empty = full + RK_ST;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_mat = nti * ntj;
+    const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < RK_ST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int kc0 = g.klo / KC, nch_all = (g.khi - g.klo) / KC;
+
+    if (warp == NCW) {
+        // ---------------- producer: one lane, two bulk copies per K chunk ----------------
+        if (lane != 0) return;
+        int q = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int b = tile / per_mat, rem = tile - b * per_mat;
+            const int ti = rem / ntj, tj = rem - ti * ntj;
+            const int i0 = g.ilo + ti * 64, j0 = g.jlo + tj * 64;
+            int ch0 = 0;
+            if (g.kskip && i0 >= g.klo && i0 + 64 <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;   // panel is zero up to the block diagonal
+            const cplx* Pb = g.P + (long)b * g.sP + ((long)kc0 * g.nrb + i0 / 32) * RK_PBLK;
+            const cplx* Wb = g.W + (long)b * g.sW + ((long)kc0 * g.ncb + j0 / 32) * RK_WBLK;
+            for (int ch = ch0; ch < nch_all; ch++, q++) {
+                const int s = q % RK_ST;
+                if (q >= RK_ST) mbar_wait(&empty[s], ((q / RK_ST) - 1) & 1);
+                cplx* Ps = sm + s * RK_STAGE;
+                mbar_expect_tx(&full[s], RK_STAGE * 16);
+                bulk_g2s(Ps, Pb + (long)ch * g.nrb * RK_PBLK, RK_PST * 16, &full[s]);
+                bulk_g2s(Ps + RK_PST, Wb + (long)ch * g.ncb * RK_WBLK, RK_WST * 16, &full[s]);
+            }
+        }
+        return;
+    }
+    // ---------------- consumers ----------------
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+    double cre[MI][NI][2], cim[MI][NI][2];
+    double c3[M3 ? MI : 1][M3 ? NI : 1][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) {
+            cre[mi][ni][0] = cre[mi][ni][1] = cim[mi][ni][0] = cim[mi][ni][1] = 0.0;
+            if (M3) c3[mi][ni][0] = c3[mi][ni][1] = 0.0;
+        }
+    int q = 0;
+    for (int it = 0; it < my_tiles; it++) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / per_mat, rem = tile - b * per_mat;
+        const int ti = rem / ntj, tj = rem - ti * ntj;
+        const int i0 = g.ilo + ti * 64, j0 = g.jlo + tj * 64;
+        int ch0 = 0;
+        if (g.kskip && i0 >= g.klo && i0 + 64 <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;
+        const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);     // warp tile inside the range
+        for (int ch = ch0; ch < nch_all; ch++, q++) {
+            const int s = q % RK_ST;
+            mbar_wait(&full[s], (q / RK_ST) & 1);
+            if (active) {
+                const cplx* Ps = sm + s * RK_STAGE + (wm * 16 + gid) * RK_PPS + tig;
+                const cplx* Ws = sm + s * RK_STAGE + RK_PST + wn * RK_WBLK + tig * RK_WPS + gid;
+#pragma unroll
+                for (int kk = 0; kk < KC; kk += 4) {
+                    cplx af[MI], bf[NI];
+#pragma unroll
+                    for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PPS + kk];
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[kk * RK_WPS + ni * 8];
+                    if (M3) {
+                        // 3M: X = ar br, Y = ai bi, Z = (ar + ai)(br + bi);  re = X - Y, im = Z - X - Y
+                        double as[MI], bs[NI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) as[mi] = af[mi].x + af[mi].y;
+#pragma unroll
+                        for (int ni = 0; ni < NI; ni++) bs[ni] = bf[ni].x + bf[ni].y;
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) {
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].y, bf[ni].y);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(c3[mi][ni][0], c3[mi][ni][1], as[mi], bs[ni]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) {
+                            const double nay = -af[mi].y;
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].x, bf[ni].y);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], nay, bf[ni].y);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi].y, bf[ni].x);
+                        }
+                    }
+                }
+            }
+            // generic-proxy reads of this stage are ordered before the producer's next async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (active && ch0 < nch_all) {
+            cplx* Cb = g.C + (long)b * g.sC + (long)(i0 + wm * 16 + gid) * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++) {
+                cplx v[NI][2];
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) {
+                    v[ni][0] = Cb[(long)(mi * 8) * g.ldc + ni * 8];
+                    v[ni][1] = Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1];
+                }
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        double re, im;
+                        if (M3) { re = cre[mi][ni][e] - cim[mi][ni][e]; im = c3[mi][ni][e] - cre[mi][ni][e] - cim[mi][ni][e]; }
+                        else { re = cre[mi][ni][e]; im = cim[mi][ni][e]; }
+                        v[ni][e].x -= re; v[ni][e].y -= im;
+                        cre[mi][ni][e] = 0.0; cim[mi][ni][e] = 0.0;
+                        if (M3) c3[mi][ni][e] = 0.0;
+                    }
+                    Cb[(long)(mi * 8) * g.ldc + ni * 8] = v[ni][0];
+                    Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1] = v[ni][1];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Panel kernels of the base step (block K = [c0, c0 + 32))
+// ------------------------------------------------------------------------------------------------
+// Phase 1: Ppk[r][K] = A[src(r)][K] for rows r in [rlo, N) (src = row move of this block), zero for the pivot
+// rows.  Reads A only and writes Ppk only, so the row moves need no separate pass over the panel.
+__global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ A, long strideA, int ld, int N, int c0,
+                                                       int rlo, const int* __restrict__ moves, cplx* __restrict__ Ppk,
+                                                       long stridePk, int nrb) {
+    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
+    __shared__ int s_nm;
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+    const int* mv = moves + (long)b * GNB_MOVES_STRIDE;
+    if (t == 0) s_nm = mv[0];
+    if (t < 2 * GNB_NB) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
+    __syncthreads();
+    const int nm = s_nm;
+    const cplx* Ab = A + (long)b * strideA;
+    cplx* Pb = Ppk + (long)b * stridePk;
+    const int kc = c0 / 16 + (lane >> 4), kk = lane & 15;
+    for (int r = rlo + blockIdx.x * 8 + wrp; r < N; r += gridDim.x * 8) {
+        int src = r;
+        for (int m = lane; m < nm; m += 32)
+            if (s_dst[m] == r) src = s_src[m];
+        src = __reduce_max_sync(0xffffffffu, src == r ? -1 : src);
+        if (src < 0) src = r;
+        const bool piv = (r >= c0 && r < c0 + GNB_NB);
+        const cplx v = piv ? cmake(0.0, 0.0) : Ab[(long)src * ld + c0 + lane];
+        Pb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk] = v;
+    }
+}
+
+// Phase 2 (JORDAN): A[r][K] = -P[r][K] inv  (rows outside the pivot block), A[K][K] = inv.
+__global__ void __launch_bounds__(256) k_rk_panel_fin(cplx* __restrict__ A, long strideA, int ld, int N, int c0,
+                                                      const cplx* __restrict__ inv, const cplx* __restrict__ Ppk,
+                                                      long stridePk, int nrb) {
+    __shared__ cplx s_inv[GNB_NB * GNB_NB];
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+    for (int i = t; i < GNB_NB * GNB_NB; i += 256) s_inv[i] = inv[(long)b * GNB_NB * GNB_NB + i];
+    __syncthreads();
+    cplx* Ab = A + (long)b * strideA;
+    const cplx* Pb = Ppk + (long)b * stridePk;
+    const int kc = c0 / 16 + (lane >> 4), kk = lane & 15;
+    for (int r = blockIdx.x * 8 + wrp; r < N; r += gridDim.x * 8) {
+        cplx out;
+        if (r >= c0 && r < c0 + GNB_NB) {
+            out = s_inv[(r - c0) * GNB_NB + lane];
+        } else {
+            const cplx p = Pb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk];
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll 8
+            for (int j = 0; j < GNB_NB; j++) {
+                const cplx pj = cmake(__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j));
+                acc = cfnma(acc, pj, s_inv[j * GNB_NB + lane]);
+            }
+            out = acc;
+        }
+        Ab[(long)r * ld + c0 + lane] = out;
+    }
+}
+
+// Row moves of blocks [blk_lo, blk_hi) applied, in order, to a 32-column tile of A.
+__global__ void __launch_bounds__(256) k_rk_moves_A(cplx* __restrict__ A, long strideA, int ld, int jlo, int jhi,
+                                                    const int* __restrict__ moves, long moves_blk_stride, int blk_lo,
+                                                    int blk_hi) {
+    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int col = jlo + blockIdx.x * 32 + (t & 31);
+    const int m0 = t >> 5;                                   // this thread handles moves m0, m0 + 8, ...
+    cplx* Ab = A + (long)b * strideA;
+    for (int blk = blk_lo; blk < blk_hi; blk++) {
+        const int* mv = moves + (long)blk * moves_blk_stride + (long)b * GNB_MOVES_STRIDE;
+        const int nm = mv[0];
+        __syncthreads();
+        if (t < nm) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
+        __syncthreads();
+        cplx v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int m = m0 + 8 * q;
+            if (m < nm && col < jhi) v[q] = Ab[(long)s_src[m] * ld + col];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int m = m0 + 8 * q;
+            if (m < nm && col < jhi) Ab[(long)s_dst[m] * ld + col] = v[q];
+        }
+    }
+}
+
+// Row moves of block `blk` applied to the saved panels (K chunks [kc_lo, kc_hi) of Ppk).  JORDAN (Lpk != null):
+// afterwards the rows of the new pivot block are moved out of Ppk into Lpk (they are the L_ab blocks of the
+// forward W solve) and cleared, which leaves Ppk strictly block-upper on pivot rows.
+__global__ void __launch_bounds__(256) k_rk_moves_P(cplx* __restrict__ Ppk, cplx* __restrict__ Lpk, long stridePk, int nrb,
+                                                    int kc_lo, int kc_hi, int c0, const int* __restrict__ moves) {
+    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int* mv = moves + (long)b * GNB_MOVES_STRIDE;
+    const int nm = mv[0];
+    if (t < nm) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
+    __syncthreads();
+    const int kk = t & 15, m0 = t >> 4;                      // 16 moves per pass
+    for (int kc = kc_lo + blockIdx.x; kc < kc_hi; kc += gridDim.x) {
+        cplx* Pc = Ppk + (long)b * stridePk + (long)kc * nrb * RK_PBLK;
+        cplx v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int m = m0 + 16 * q;
+            if (m < nm) { const int r = s_src[m]; v[q] = Pc[(long)(r >> 5) * RK_PBLK + (r & 31) * RK_PPS + kk]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int m = m0 + 16 * q;
+            if (m < nm) { const int r = s_dst[m]; Pc[(long)(r >> 5) * RK_PBLK + (r & 31) * RK_PPS + kk] = v[q]; }
+        }
+        if (Lpk) {
+            __syncthreads();
+            cplx* Lc = Lpk + (long)b * stridePk + (long)kc * nrb * RK_PBLK + (long)(c0 >> 5) * RK_PBLK;
+            cplx* Pr = Pc + (long)(c0 >> 5) * RK_PBLK;
+            for (int e = t; e < 32 * 16; e += 256) {
+                const int off = (e >> 4) * RK_PPS + (e & 15);
+                Lc[off] = Pr[off];
+                Pr[off] = cmake(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// W_b = inv_b (A[K_b, cols] - sum_{a in prev} L_ba W_a)  for a 64-column tile; written to A and to Wpk.
+// prev = the nprev (0 or 1) blocks immediately left of block b (fused pre-update of a leaf pair).
+#define WS_TC 64
+__global__ void __launch_bounds__(256) k_rk_wsolve(cplx* __restrict__ A, long strideA, int ld, int c0, int jlo, int jhi,
+                                                   const cplx* __restrict__ inv, const cplx* __restrict__ Lsrc,
+                                                   long stridePk, int nrb, int nprev, cplx* __restrict__ Wpk,
+                                                   long strideWk, int ncb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);          // [32][WS_TC]
+    cplx* sInv = tile + GNB_NB * WS_TC;                      // [32][32]
+    cplx* sL = sInv + GNB_NB * GNB_NB;                       // [32][32]
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int cs = jlo + blockIdx.x * WS_TC;
+    cplx* Ab = A + (long)b * strideA;
+    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) sInv[idx] = inv[(long)b * GNB_NB * GNB_NB + idx];
+    if (nprev) {
+        const int ca = c0 - GNB_NB;
+        const cplx* Lb = Lsrc + (long)b * stridePk;
+        for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) {
+            const int i = idx >> 5, j = idx & 31, k = ca + j;
+            sL[idx] = Lb[((long)(k >> 4) * nrb + (c0 >> 5)) * RK_PBLK + i * RK_PPS + (k & 15)];
+        }
+    }
+    for (int idx = t; idx < GNB_NB * WS_TC; idx += 256) {
+        const int i = idx / WS_TC, c = idx - i * WS_TC, col = cs + c;
+        tile[idx] = (col < jhi) ? Ab[(long)(c0 + i) * ld + col] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    const int c = t & (WS_TC - 1), rg = t >> 6, col = cs + c;
+    const bool ok = col < jhi;
+    cplx acc[8];
+    if (nprev) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = tile[(rg + 4 * q) * WS_TC + c];
+        if (ok)
+            for (int j = 0; j < GNB_NB; j++) {
+                const cplx wa = Ab[(long)(c0 - GNB_NB + j) * ld + col];
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = cfnma(acc[q], sL[(rg + 4 * q) * GNB_NB + j], wa);
+            }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; q++) tile[(rg + 4 * q) * WS_TC + c] = acc[q];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = cmake(0.0, 0.0);
+    for (int j = 0; j < GNB_NB; j++) {
+        const cplx r = tile[j * WS_TC + c];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = cfma(acc[q], sInv[(rg + 4 * q) * GNB_NB + j], r);
+    }
+    if (ok) {
+        cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = c0 + rg + 4 * q;
+            Ab[(long)k * ld + col] = acc[q];
+            Wb[(long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS] = acc[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+size_t gnb_rec_pk_elems(int N) { return (size_t)(N / 16) * (N / 32) * RK_PBLK + 2 * RK_PBLK; }
+size_t gnb_rec_wk_elems(int N, int ld) { return (size_t)(N / 16) * (ld / 32) * RK_WBLK + 2 * RK_WBLK; }
+
+static int g_rk_m3 = 0;          // 3M complex arithmetic in the rank-K update
+static int g_rk_m3_mink = 64;    // ... for K >= this
+static int g_rk_kskip = 1;
+static int g_rk_sms = 148;
+static const size_t kWsSmem = (size_t)(GNB_NB * WS_TC + 2 * GNB_NB * GNB_NB) * sizeof(cplx);
+
+cudaError_t gnb_rec_init() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_rk_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRkSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRkSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem))) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_rk_sms, cudaDevAttrMultiProcessorCount, dev);
+    return cudaSuccess;
+}
+void gnb_rec_set_option(const char* name, int value) {
+    if (!strcmp(name, "rk_m3")) g_rk_m3 = value;
+    else if (!strcmp(name, "rk_m3_mink")) g_rk_m3_mink = value;
+    else if (!strcmp(name, "rk_kskip")) g_rk_kskip = value;
+}
+
+namespace {
+struct Rec {
+    cudaStream_t st; int M, N, naug; cplx* A; long strideA; int ld; int jordan;
+    const GnbRecWork& ws; long launches;
+    int nrb, ncb;
+
+    cplx* inv(int c0) const { return ws.inv + (long)(c0 / GNB_NB) * M * GNB_NB * GNB_NB; }
+    int* mv(int c0) const { return ws.moves + (long)(c0 / GNB_NB) * M * GNB_MOVES_STRIDE; }
+
+    void gemm(int ilo, int ihi, int jlo, int jhi, int klo, int khi, const cplx* P, int kskip) {
+        if (ihi <= ilo || jhi <= jlo || khi <= klo) return;
+        RkGemmArgs g{};
+        g.C = A; g.sC = strideA; g.ldc = ld;
+        g.P = P; g.sP = ws.stridePk; g.nrb = nrb;
+        g.W = ws.Wpk; g.sW = ws.strideWk; g.ncb = ncb;
+        g.ilo = ilo; g.ihi = ihi; g.jlo = jlo; g.jhi = jhi; g.klo = klo; g.khi = khi;
+        g.kskip = (kskip && g_rk_kskip) ? 1 : 0;
+        const int nti = cdiv_i(ihi - ilo, 64), ntj = cdiv_i(jhi - jlo, 64);
+        const long total = (long)M * nti * ntj;
+        const int grid = (int)std::min<long>(total, (long)g_rk_sms);
+        double flops = 8.0 * (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M;
+        if (g.kskip)            // rows inside [klo, khi) only meet the strictly block-upper part of the panel
+            for (int i0 = ilo; i0 < ihi; i0 += 64)
+                if (i0 >= klo && i0 + 64 <= khi) flops -= 8.0 * 64.0 * (double)(jhi - jlo) * (double)(i0 + 32 - klo) * M;
+        if (ws.timer) ws.timer->begin(st);
+        if (g_rk_m3 && khi - klo >= g_rk_m3_mink) k_rk_gemm<1><<<grid, 288, kRkSmem, st>>>(g, nti, ntj, (int)total);
+        else k_rk_gemm<0><<<grid, 288, kRkSmem, st>>>(g, nti, ntj, (int)total);
+        if (ws.timer) ws.timer->end(st, flops);
+        launches++;
+    }
+
+    void base_step(int c0, int live_lo) {
+        launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
+                                          inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+        if (live_lo < c0) {
+            dim3 grid(std::min((c0 - live_lo) / 16, 64), M);
+            k_rk_moves_P<<<grid, 256, 0, st>>>(ws.Ppk, jordan ? ws.Lpk : nullptr, ws.stridePk, nrb, live_lo / 16, c0 / 16,
+                                               c0, mv(c0));
+            launches++;
+        }
+        const int rlo = jordan ? 0 : c0 + GNB_NB;
+        if (rlo < N) {
+            dim3 grid(std::min(cdiv_i(N - rlo, 8), 128), M);
+            k_rk_panel_save<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, rlo, mv(c0), ws.Ppk, ws.stridePk, nrb);
+            launches++;
+        }
+        if (jordan) {
+            dim3 grid(std::min(cdiv_i(N, 8), 128), M);
+            k_rk_panel_fin<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, inv(c0), ws.Ppk, ws.stridePk, nrb);
+            launches++;
+        }
+    }
+
+    // forward W of blocks [c0, c0 + w) on columns [jlo, jhi)  (row moves already applied)
+    void trsm(int c0, int w, int jlo, int jhi) {
+        const int nb = w / GNB_NB;
+        const cplx* Lsrc = jordan ? ws.Lpk : ws.Ppk;
+        if (nb <= 2) {
+            for (int i = 0; i < nb; i++) {
+                const int cb = c0 + i * GNB_NB;
+                dim3 grid(cdiv_i(jhi - jlo, WS_TC), M);
+                k_rk_wsolve<<<grid, 256, kWsSmem, st>>>(A, strideA, ld, cb, jlo, jhi, inv(cb), Lsrc, ws.stridePk, nrb, i,
+                                                         ws.Wpk, ws.strideWk, ncb);
+                launches++;
+            }
+            return;
+        }
+        const int h = (nb + 1) / 2 * GNB_NB;
+        trsm(c0, h, jlo, jhi);
+        gemm(c0 + h, c0 + w, jlo, jhi, c0, c0 + h, Lsrc, 0);
+        trsm(c0 + h, w - h, jlo, jhi);
+    }
+
+    void apply_far(int c0, int w, int jlo, int jhi) {
+        if (jhi <= jlo) return;
+        dim3 grid(cdiv_i(jhi - jlo, 32), M);
+        k_rk_moves_A<<<grid, 256, 0, st>>>(A, strideA, ld, jlo, jhi, ws.moves, (long)M * GNB_MOVES_STRIDE, c0 / GNB_NB,
+                                           (c0 + w) / GNB_NB);
+        launches++;
+        trsm(c0, w, jlo, jhi);
+        if (jordan) gemm(0, N, jlo, jhi, c0, c0 + w, ws.Ppk, 1);
+        else gemm(c0 + w, N, jlo, jhi, c0, c0 + w, ws.Ppk, 0);
+    }
+
+    // live: an ancestor will still apply this range's panels to other columns, so the saved panels from
+    // column live_lo on must follow the row moves of every later block of the range.
+    void factor(int c0, int w, bool live, int live_lo) {
+        if (w == GNB_NB) { base_step(c0, live ? live_lo : c0); return; }
+        const int h = (w / GNB_NB + 1) / 2 * GNB_NB;
+        factor(c0, h, true, live ? live_lo : c0);
+        const int hi = (!jordan && c0 + w == N) ? N + naug : c0 + w;     // augmented columns ride along
+        apply_far(c0, h, c0 + h, hi);
+        factor(c0 + h, w - h, jordan ? true : live, live ? live_lo : c0 + h);
+        if (jordan) apply_far(c0 + h, w - h, c0, c0 + h);
+    }
+
+    // X[c0 : c0 + w] of the unit-block-upper system; the blocks above the diagonal are the normalised rows in A
+    void backsub(int c0, int w) {
+        if (w <= GNB_NB) return;
+        const int h = (w / GNB_NB + 1) / 2 * GNB_NB;
+        backsub(c0 + h, w - h);
+        GnbGemmArgs g{};
+        g.C = A + N; g.strideC = strideA; g.ldc = ld;
+        g.P = A + c0 + h; g.strideP = strideA; g.ldp = ld;
+        g.W = A + (long)(c0 + h) * ld + N; g.strideW = strideA; g.ldw = ld;
+        g.ilo = c0; g.ihi = c0 + h; g.jlo = 0; g.jhi = naug; g.kdim = w - h;
+        g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
+        if (ws.timer) ws.timer->begin(st);
+        gnb_launch_gemm(st, g, M, false, false);
+        if (ws.timer) ws.timer->end(st, 8.0 * (double)h * (double)naug * g.kdim * M);
+        launches++;
+        backsub(c0, h);
+    }
+};
+}  // namespace
+
+long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
+                       const GnbRecWork& ws) {
+    if (M <= 0) return 0;
+    Rec e{st, M, N, naug, A, strideA, ld, jordan, ws, 0, N / 32, ld / 32};
+    if (jordan) { gnb_launch_init_perm(st, M, ws.perm, ws.perm_stride, N); e.launches++; }
+    e.factor(0, N, false, 0);
+    if (!jordan && naug > 0) {
+        e.apply_far(N - GNB_NB, GNB_NB, N, N + naug);      // the last block is nobody's left sibling
+        e.backsub(0, N);
+    }
+    return e.launches;
+}
