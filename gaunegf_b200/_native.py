@@ -101,6 +101,10 @@ class Context:
         self.h = h
         self.device = device
         self.N = 0
+        # developer A/B switches: GNB_DEV_OPTS="rk_m3=1,tourn_group=256"
+        for kv in filter(None, os.environ.get("GNB_DEV_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            self.lib.gnb_dev_set_option(k.strip().encode(), int(v))
 
     def close(self):
         if getattr(self, "h", None):

@@ -22,6 +22,8 @@ int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
+static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
+static int g_rec_streams = 1;     // independent sub-batches (streams) per chunk in the recursive engine
 
 extern "C" const char* gnb_version(void) { return "gaunegf_b200 0.1 (sm_100a)"; }
 
@@ -62,6 +64,11 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
                       &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
                       &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < GNB_MAX_SUBSTREAMS; i++) {
+        if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
+        if (c->sub_ev[i]) cudaEventDestroy(c->sub_ev[i]);
+    }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -91,10 +98,17 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "gemm_pipe")) gnb_set_gemm_pipe(value);
     else if (!strcmp(name, "gemm_bm")) gnb_set_gemm_bm(value);
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
+    else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
+    else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
+    else if (!strcmp(name, "tourn_group")) gnb_set_tourn_group(value);
     else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
     else return GNB_ERR_ARG;
     return GNB_OK;
 }
+void gnb_rec_trace_start();
+int gnb_rec_trace_dump(const char* path);
+extern "C" int gnb_dev_trace_start(void) { gnb_rec_trace_start(); return GNB_OK; }
+extern "C" int gnb_dev_trace_dump(const char* path) { return gnb_rec_trace_dump(path); }
 extern "C" int gnb_set_timing(gnb_ctx* c, int on) { if (!c) return GNB_ERR_ARG; c->timing = on != 0; return GNB_OK; }
 
 static int put(gnb_ctx* c, DevBuf& buf, const void* src, size_t bytes, int loc) {
@@ -290,6 +304,7 @@ static int run_eliminate(gnb_ctx* c, int M, int N, int naug, cplx* A, long strid
 struct Lay {
     int N, naug, Np, naugp, ld, xoff;
     bool rec, padded;
+    int back_row_lo = 0;               // FORWARD: first solution row that is needed
     size_t bytes_per_energy(bool jordan) const {
         size_t b = (size_t)Np * ld * 16 + 8 * (size_t)Np + 32768;
         if (rec) b += gnb_rec_pk_elems(Np) * 16 * (jordan ? 2 : 1) + gnb_rec_wk_elems(Np, ld) * 16 + (size_t)(Np / 32) * (16384 + 4 * GNB_MOVES_STRIDE);
@@ -313,7 +328,7 @@ static GnbRecWork rec_work(gnb_ctx* c, int M, const Lay& L, bool jordan, int* rc
     GnbRecWork w{};
     *rc = GNB_OK;
     const int Np = L.Np, nblk = Np / 32;
-    const int cand_stride = std::max(GNB_NB, (Np + 255) / 256 * GNB_NB);
+    const int cand_stride = std::max(GNB_NB, (Np + 127) / 128 * GNB_NB);
     cudaError_t e = cudaSuccess;
     auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
     need(c->cand0, (size_t)M * cand_stride * sizeof(int));
@@ -331,7 +346,8 @@ static GnbRecWork rec_work(gnb_ctx* c, int M, const Lay& L, bool jordan, int* rc
     }
     if (e != cudaSuccess) { *rc = gnb_cuda_fail(c, e, "workspace allocation"); return w; }
     w.cand0 = c->cand0.as<int>(); w.cand1 = c->cand1.as<int>(); w.cand_stride = cand_stride;
-    w.inv = c->LU.as<cplx>(); w.moves = c->moves.as<int>();
+    w.inv = c->LU.as<cplx>(); w.inv_blk_stride = (long)M * GNB_NB * GNB_NB;
+    w.moves = c->moves.as<int>(); w.moves_blk_stride = (long)M * GNB_MOVES_STRIDE;
     w.perm = c->perm.as<int>(); w.perm_stride = Np;
     w.Ppk = c->Ppk.as<cplx>(); w.Lpk = c->Lpk.as<cplx>(); w.stridePk = (long)pk;
     w.Wpk = c->Wpk.as<cplx>(); w.strideWk = (long)wk;
@@ -354,8 +370,37 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
     if (L.rec) {
         GnbRecWork w = rec_work(c, M, L, jordan != 0, &rc);
         if (rc) return rc;
+        w.back_row_lo = L.back_row_lo;
         if (c->timing) GNB_CK(cudaEventRecord(c->ev0, c->stream));
-        c->launches += gnb_eliminate_rec(c->stream, M, L.Np, L.naugp, A, strideA, L.ld, jordan, w);
+        // Independent sub-batches on separate streams: the latency-bound panel kernels of one sub-batch
+        // overlap the tensor-pipe-bound rank-K updates of the others.
+        int S = std::max(1, std::min(g_rec_streams, GNB_MAX_SUBSTREAMS));
+        S = std::min(S, std::max(1, M / 32));
+        if (S <= 1) {
+            c->launches += gnb_eliminate_rec(c->stream, M, L.Np, L.naugp, A, strideA, L.ld, jordan, w);
+        } else {
+            for (int s = 0; s < S; s++)
+                if (!c->sub[s]) {
+                    GNB_CK(cudaStreamCreateWithFlags(&c->sub[s], cudaStreamNonBlocking));
+                    GNB_CK(cudaEventCreateWithFlags(&c->sub_ev[s], cudaEventDisableTiming));
+                }
+            if (!c->fork_ev) GNB_CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+            GNB_CK(cudaEventRecord(c->fork_ev, c->stream));
+            for (int s = 0; s < S; s++) {
+                const int m0 = (int)((long)M * s / S), m1 = (int)((long)M * (s + 1) / S);
+                GnbRecWork ws = w;
+                ws.cand0 = w.cand0 + (long)m0 * w.cand_stride; ws.cand1 = w.cand1 + (long)m0 * w.cand_stride;
+                ws.inv = w.inv + (long)m0 * GNB_NB * GNB_NB; ws.moves = w.moves + (long)m0 * GNB_MOVES_STRIDE;
+                ws.perm = w.perm ? w.perm + (long)m0 * w.perm_stride : nullptr;
+                ws.Ppk = w.Ppk + (long)m0 * w.stridePk; ws.Lpk = w.Lpk ? w.Lpk + (long)m0 * w.stridePk : nullptr;
+                ws.Wpk = w.Wpk + (long)m0 * w.strideWk;
+                GNB_CK(cudaStreamWaitEvent(c->sub[s], c->fork_ev, 0));
+                c->launches += gnb_eliminate_rec(c->sub[s], m1 - m0, L.Np, L.naugp, A + (long)m0 * strideA, strideA, L.ld,
+                                                 jordan, ws);
+                GNB_CK(cudaEventRecord(c->sub_ev[s], c->sub[s]));
+                GNB_CK(cudaStreamWaitEvent(c->stream, c->sub_ev[s], 0));
+            }
+        }
         if (c->timing) {
             GNB_CK(cudaEventRecord(c->ev1, c->stream));
             GNB_CK(cudaEventSynchronize(c->ev1));
@@ -372,7 +417,9 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
 static int chunk_size(gnb_ctx* c, int M, size_t bytes_per_energy) {
     size_t m = c->ws_limit / std::max<size_t>(bytes_per_energy, 1);
     m = std::max<size_t>(1, std::min<size_t>(m, 8192));
-    return (int)std::min<size_t>(m, (size_t)M);
+    if (m >= (size_t)M) return M;
+    const size_t nchunks = ((size_t)M + m - 1) / m;            // equal-sized chunks instead of a small tail
+    return (int)(((size_t)M + nchunks - 1) / nchunks);
 }
 
 static int resolve_contact(gnb_ctx* c, int idx) {
@@ -398,15 +445,17 @@ static int prepare_sigma(gnb_ctx* c, int M, const cplx* dE, int want_gamma) {
 // A_k = E_k S - F - Sigma_tot(E_k) for the chunk, from the context's self-energy description or
 // from caller-provided dense matrices.
 static int assemble_chunk(gnb_ctx* c, int M, const cplx* dE, cplx* A, long strideA, int ld, bool use_desc,
-                          const cplx* sig_const, const cplx* sig_batch) {
+                          const cplx* sig_const, const cplx* sig_batch, const int* d_pi = nullptr,
+                          const int* d_pinv = nullptr) {
     const int N = c->N;
     const cplx* s0 = use_desc ? (c->has_sig0 ? c->dSig0.as<cplx>() : nullptr) : sig_const;
     gnb_launch_assemble(c->stream, M, A, strideA, ld, N, c->dF.as<cplx>(), c->dS.as<cplx>(), s0, sig_batch,
-                        (long)N * N, dE);
+                        (long)N * N, dE, d_pi);
     c->launches++;
     if (use_desc)
         for (auto& ct : c->contacts) {
-            gnb_launch_scatter_sub(c->stream, M, A, strideA, ld, ct.d_inds.as<int>(), ct.nc, ct.blk_ptr, ct.blk_stride);
+            gnb_launch_scatter_sub(c->stream, M, A, strideA, ld, ct.d_inds.as<int>(), ct.nc, ct.blk_ptr, ct.blk_stride,
+                                   d_pinv);
             c->launches++;
         }
     GNB_CK(cudaGetLastError());
@@ -647,8 +696,29 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
     if (rc) return rc;
     const int N = c->N;
     const int n1 = c->contacts[ca].nc, n2 = c->contacts[cb].nc;
-    const Lay L = make_layout(N, n2);
+    Lay L = make_layout(N, n2);
     const int ld = L.ld, Np = L.Np;
+    // Contacts-last ordering: with the orbitals of the two contacts moved to the end (symmetric permutation
+    // applied at assembly), G[C1, C2] only needs the last n1 + n2 rows of the solution, so the
+    // back-substitution stops there.  Needs disjoint contacts; otherwise the natural order is kept.
+    const int *d_pi = nullptr, *d_pinv = nullptr;
+    if (L.rec && g_contacts_last && ca != cb) {
+        std::vector<int> mark(N, 0), pi, pinv(N);
+        bool disjoint = true;
+        for (int i : c->contacts[ca].h_inds) { if (mark[i]) disjoint = false; mark[i] = 1; }
+        for (int i : c->contacts[cb].h_inds) { if (mark[i]) disjoint = false; mark[i] = 2; }
+        if (disjoint) {
+            pi.reserve(N);
+            for (int i = 0; i < N; i++) if (!mark[i]) pi.push_back(i);
+            pi.insert(pi.end(), c->contacts[ca].h_inds.begin(), c->contacts[ca].h_inds.end());
+            pi.insert(pi.end(), c->contacts[cb].h_inds.begin(), c->contacts[cb].h_inds.end());
+            for (int i = 0; i < N; i++) pinv[pi[i]] = i;
+            if ((rc = put(c, c->rows, pi.data(), (size_t)N * sizeof(int), GNB_HOST))) return rc;
+            if ((rc = put(c, c->cols, pinv.data(), (size_t)N * sizeof(int), GNB_HOST))) return rc;
+            d_pi = c->rows.as<int>(); d_pinv = c->cols.as<int>();
+            L.back_row_lo = N - n1 - n2;
+        }
+    }
     const size_t per = L.bytes_per_energy(false) + 3 * (size_t)n1 * n2 * 16 + 16384 +
                        2 * ((size_t)n1 * n1 + (size_t)n2 * n2) * 16 * 4;
     const int Mc = chunk_size(c, std::max(M, 1), per);
@@ -663,8 +733,8 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
         Contact& A1 = c->contacts[ca];
         Contact& A2 = c->contacts[cb];
         if ((rc = pad_chunk(c, m, L, A))) return rc;
-        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr))) return rc;
-        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, A2.d_inds.as<int>(), n2);
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr, d_pi, d_pinv))) return rc;
+        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, A2.d_inds.as<int>(), n2, d_pinv);
         c->launches++;
         if ((rc = run_eliminate(c, m, L, A, 0))) return rc;
         const long s12 = (long)n1 * n2;
@@ -672,7 +742,7 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
         GNB_CK(c->Y.ensure((size_t)m * s12 * sizeof(cplx)));
         GNB_CK(c->Z.ensure((size_t)m * s12 * sizeof(cplx)));
         GNB_CK(c->dT.ensure((size_t)m * sizeof(double)));
-        gnb_launch_gather_rows(c->stream, m, A + L.xoff, strideA, ld, A1.d_inds.as<int>(), n1, n2, c->Xr.as<cplx>(), s12);
+        gnb_launch_gather_rows(c->stream, m, A + L.xoff, strideA, ld, A1.d_inds.as<int>(), n1, n2, c->Xr.as<cplx>(), s12, d_pinv);
         GnbGemmArgs g{};
         g.skip_lo = g.skip_hi = -1; g.zero_init = 1; g.plus = 1;
         g.ilo = 0; g.ihi = n1; g.jlo = 0; g.jhi = n2;

@@ -69,11 +69,15 @@ struct EventTimer : GnbGemmTimer {
     ~EventTimer() { for (auto e : pool) cudaEventDestroy(e); }
 };
 
+#define GNB_MAX_SUBSTREAMS 8
 struct gnb_ctx {
     EventTimer gemm_timer;
+    cudaStream_t sub[GNB_MAX_SUBSTREAMS] = {};
+    cudaEvent_t sub_ev[GNB_MAX_SUBSTREAMS] = {};
+    cudaEvent_t fork_ev = nullptr;
     int device = 0;
     cudaStream_t stream = 0;
-    size_t ws_limit = (size_t)16 << 30;
+    size_t ws_limit = (size_t)48 << 30;
     std::string err;
     int64_t launches = 0;
     int N = 0;

@@ -22,16 +22,17 @@ __global__ void __launch_bounds__(256) k_assemble(cplx* __restrict__ A, long str
                                                   const cplx* __restrict__ F, const cplx* __restrict__ S,
                                                   const cplx* __restrict__ Sig0,
                                                   const cplx* __restrict__ SigB, long strideSigB,
-                                                  const cplx* __restrict__ E) {
+                                                  const cplx* __restrict__ E, const int* __restrict__ pi) {
     const int b = blockIdx.y;
     const cplx e = E[b];
     cplx* Ab = A + (long)b * strideA;
     const long total = (long)N * N;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int i = (int)(idx / N), j = (int)(idx - (long)i * N);
-        cplx v = csub(cmul(e, S[idx]), F[idx]);
-        if (Sig0) v = csub(v, Sig0[idx]);
-        if (SigB) v = csub(v, SigB[(long)b * strideSigB + idx]);
+        const long src = pi ? (long)pi[i] * N + pi[j] : idx;      // symmetric orbital reordering (contacts last)
+        cplx v = csub(cmul(e, S[src]), F[src]);
+        if (Sig0) v = csub(v, Sig0[src]);
+        if (SigB) v = csub(v, SigB[(long)b * strideSigB + src]);
         Ab[(long)i * ld + j] = v;
     }
 }
@@ -39,22 +40,25 @@ __global__ void __launch_bounds__(256) k_assemble(cplx* __restrict__ A, long str
 // A[b][inds[p]][inds[q]] -= blk[b][p][q]   (surfG1D.py:372, surfGBethe.py:527 scatter of contact blocks)
 __global__ void __launch_bounds__(256) k_scatter_sub(cplx* __restrict__ A, long strideA, int ld,
                                                      const int* __restrict__ inds, int nc,
-                                                     const cplx* __restrict__ blk, long strideBlk) {
+                                                     const cplx* __restrict__ blk, long strideBlk,
+                                                     const int* __restrict__ map) {
     const int b = blockIdx.y;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nc * nc; idx += gridDim.x * blockDim.x) {
         const int p = idx / nc, q = idx - p * nc;
-        cplx* a = A + (long)b * strideA + (long)inds[p] * ld + inds[q];
+        const int ip = map ? map[inds[p]] : inds[p], iq = map ? map[inds[q]] : inds[q];
+        cplx* a = A + (long)b * strideA + (long)ip * ld + iq;
         *a = csub(*a, blk[(long)b * strideBlk + idx]);
     }
 }
 
 // Augmented right-hand side: A[b][i][xoff + c] = (i == cols[c])
 __global__ void __launch_bounds__(256) k_set_aug(cplx* __restrict__ A, long strideA, int ld, int N, int xoff,
-                                                 const int* __restrict__ cols, int m) {
+                                                 const int* __restrict__ cols, int m, const int* __restrict__ map) {
     const int b = blockIdx.y;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * m; idx += gridDim.x * blockDim.x) {
         const int i = idx / m, c = idx - i * m;
-        A[(long)b * strideA + (long)i * ld + xoff + c] = cmake(i == cols[c] ? 1.0 : 0.0, 0.0);
+        const int r = map ? map[cols[c]] : cols[c];
+        A[(long)b * strideA + (long)i * ld + xoff + c] = cmake(i == r ? 1.0 : 0.0, 0.0);
     }
 }
 // identity on the padded diagonal [N, Np)
@@ -70,23 +74,41 @@ __global__ void k_init_perm(int* __restrict__ perm, int stride, int N) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Tournament pivoting round.  One CTA = one group of <= 256 candidate rows of one matrix; each
+// Tournament pivoting round.  One CTA = one group of <= GROUP candidate rows of one matrix; each
 // thread keeps its row of the NB-wide panel in registers and the CTA runs Gaussian elimination
-// with partial pivoting (LAPACK izamax metric |re|+|im|) WITHOUT physical swaps: a thread whose
-// row is chosen publishes it through shared memory and retires.  The w chosen rows go to the next
-// round; the final round (a single group) also emits the compact LU of the pivot block, the net
-// row moves of this step and updates the running row permutation.
+// with partial pivoting (LAPACK izamax metric |re|+|im|) WITHOUT physical swaps: the thread whose
+// row is chosen retires.  The w chosen rows go to the next round; the final round (a single group)
+// also emits the explicit inverse of the pivot block, the net row moves of this step and updates the
+// running row permutation.
+//
+// The row is ROTATED by one element per pivot step, so the pivot column is always a[0] and the loop
+// body has static register indices: the kernel is ~500 instructions instead of a 14 k-instruction
+// fully unrolled triangle that missed the instruction cache on every step.  One barrier per step:
+// every warp publishes its local winner (value, thread, row) into a double-buffered slot, all threads
+// pick the global winner after the barrier.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A, long strideA, int ld,
-                                                     int c0, int w, int r0, int n_in,
-                                                     const int* __restrict__ cand_in, int cand_in_stride,
-                                                     int* __restrict__ cand_out, int cand_out_stride,
-                                                     int final_round, cplx* __restrict__ LU,
-                                                     int* __restrict__ moves, int* __restrict__ perm,
-                                                     int perm_stride, int* __restrict__ info) {
+__device__ __forceinline__ cplx crcp_fast(cplx p) {
+    // 1 / p with a power-of-two pre-scaling (exact), one real reciprocal
+    const double s = fmax(fabs(p.x), fabs(p.y));
+    const int e = (__double2hiint(s) >> 20) & 0x7ff;
+    const double sc = __hiloint2double((2046 - e) << 20, 0);          // 2^(1023 - e): |p| * sc in [1, 2.83)
+    const double x = p.x * sc, y = p.y * sc;
+    const double r = __drcp_rn(fma(x, x, y * y)) * sc;
+    return cmake(x * r, -y * r);
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(GROUP) k_tourn(const cplx* __restrict__ A, long strideA, int ld,
+                                                 int c0, int w, int r0, int n_in,
+                                                 const int* __restrict__ cand_in, int cand_in_stride,
+                                                 int* __restrict__ cand_out, int cand_out_stride,
+                                                 int final_round, cplx* __restrict__ LU,
+                                                 int* __restrict__ moves, int* __restrict__ perm,
+                                                 int perm_stride, int* __restrict__ info) {
+    constexpr int NW = GROUP / 32;
     const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
-    const int i = g * GNB_GROUP + t;
+    const int i = g * GROUP + t;
     const bool valid = i < n_in;
     int row = -1;
     if (valid) row = cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i;
@@ -97,58 +119,51 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
 #pragma unroll
         for (int c = 0; c < GNB_NB; c++) a[c] = (valid && c < w) ? src[c] : cmake(0.0, 0.0);
     }
-    const int ngroup = min(GNB_GROUP, n_in - g * GNB_GROUP);
+    const int ngroup = min(GROUP, n_in - g * GROUP);
     const int nsel = min(w, ngroup);
 
-    __shared__ double s_wm[GNB_GROUP / 32];
-    __shared__ int s_wi[GNB_GROUP / 32];
-    __shared__ cplx s_prow[GNB_NB];
-    __shared__ cplx s_rinv;
+    __shared__ double s_cm[2][NW];
+    __shared__ int s_ci[2][NW];
+    __shared__ __align__(16) cplx s_crow[2][NW][GNB_NB];
     __shared__ int s_win[GNB_NB];
-    __shared__ cplx s_lu[GNB_NB][GNB_NB + 1];      // final round: compact LU of the pivot block
-    __shared__ cplx s_y[2][GNB_NB];
+    __shared__ __align__(16) cplx s_B[GNB_NB][GNB_NB + 1];      // final round: pivot block -> its inverse
     bool alive = valid;
 
+#pragma unroll 1
+    for (int j = 0; j < nsel; j++) {
+        const int buf = j & 1;
+        const double m = cabs1(a[0]);
+        // order-preserving integer key: 0 for retired rows, bits(m) + 1 otherwise (m >= 0)
+        const unsigned long long key = alive ? (unsigned long long)__double_as_longlong(m) + 1ull : 0ull;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+        const unsigned bal = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
+        if (lane == __ffs(bal) - 1) {                         // lowest lane on ties (izamax picks the first maximum)
+            s_cm[buf][warp] = key ? m : -1.0;
+            s_ci[buf][warp] = t;
 #pragma unroll
-    for (int j = 0; j < GNB_NB; j++) {
-        if (j < nsel) {   // block-uniform
-            double m = alive ? cabs1(a[j]) : -1.0;
-            int idx = t;
+            for (int c = 0; c < GNB_NB; c++) s_crow[buf][warp][c] = a[c];
+        }
+        __syncthreads();
+        double bm = s_cm[buf][0];
+        int bw = 0;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double m2 = __shfl_down_sync(0xffffffffu, m, off);
-                const int i2 = __shfl_down_sync(0xffffffffu, idx, off);
-                if (m2 > m || (m2 == m && i2 < idx)) { m = m2; idx = i2; }
-            }
-            if (lane == 0) { s_wm[warp] = m; s_wi[warp] = idx; }
-            __syncthreads();
-            double bm = s_wm[0];
-            int bi = s_wi[0];
+        for (int q = 1; q < NW; q++)
+            if (s_cm[buf][q] > bm) { bm = s_cm[buf][q]; bw = q; }
+        const cplx* prow = s_crow[buf][bw];
+        if (t == s_ci[buf][bw]) {
+            alive = false;
+            s_win[j] = row;
+            if (final_round && bm == 0.0) *info = 1;          // exactly singular pivot (LAPACK info > 0)
+        }
+        if (alive) {
+            // LAPACK zgetf2 scales the column by the reciprocal of the pivot
+            const cplx rinv = (bm > 0.0) ? crcp_fast(prow[0]) : cmake(0.0, 0.0);
+            const cplx l = cmul(a[0], rinv);
 #pragma unroll
-            for (int q = 1; q < GNB_GROUP / 32; q++)
-                if (s_wm[q] > bm) { bm = s_wm[q]; bi = s_wi[q]; }
-            if (t == bi) {
-                alive = false;
-#pragma unroll
-                for (int c = 0; c < GNB_NB; c++)
-                    if (c >= j) s_prow[c] = a[c];
-                s_win[j] = row;
-                // LAPACK zgetf2 scales the column by the reciprocal of the pivot
-                s_rinv = (bm > 0.0) ? cdiv(cmake(1.0, 0.0), a[j]) : cmake(0.0, 0.0);
-                if (final_round) {
-#pragma unroll
-                    for (int c = 0; c < GNB_NB; c++) s_lu[j][c] = a[c];
-                    if (bm == 0.0) *info = 1;      // exactly singular pivot (LAPACK info > 0)
-                }
-            }
-            __syncthreads();
-            if (alive) {
-                const cplx l = cmul(a[j], s_rinv);
-                a[j] = l;
-#pragma unroll
-                for (int c = 0; c < GNB_NB; c++)
-                    if (c > j) a[c] = cfnma(a[c], l, s_prow[c]);
-            }
+            for (int c = 0; c < GNB_NB - 1; c++) a[c] = cfnma(a[c + 1], l, prow[c + 1]);
+            a[GNB_NB - 1] = cmake(0.0, 0.0);
         }
     }
     __syncthreads();
@@ -156,50 +171,44 @@ __global__ void __launch_bounds__(GNB_GROUP) k_tourn(const cplx* __restrict__ A,
         if (t < nsel) cand_out[(long)b * cand_out_stride + g * w + t] = s_win[t];
         return;
     }
-    // ---- final round: explicit inverse of the pivot block, X = (L11 U11)^-1, by column-oriented
-    // substitution on all 256 threads: thread -> column c = t % 32, rows t/32 + 8 q.
+    // ---- final round: explicit inverse of the pivot block (chosen rows, pivot order) by Gauss-Jordan in
+    // shared memory without further pivoting (the row order IS the partial-pivoting order).
     {
-        const int c = t & 31, rg = t >> 5;
-        cplx x[4];
+        const cplx* Ab = A + (long)b * strideA;
+        for (int e = t; e < GNB_NB * GNB_NB; e += GROUP) {
+            const int r = e >> 5, c = e & 31;
+            cplx v = cmake(r == c ? 1.0 : 0.0, 0.0);
+            if (r < w && c < w) v = Ab[(long)s_win[r] * ld + c0 + c];
+            s_B[r][c] = v;
+        }
+        constexpr int PER = GNB_NB * GNB_NB / GROUP;
+        for (int k = 0; k < w; k++) {
+            __syncthreads();
+            const cplx piv = s_B[k][k];
+            const cplx rk = (piv.x != 0.0 || piv.y != 0.0) ? crcp_fast(piv) : cmake(0.0, 0.0);
+            cplx nv[PER];
 #pragma unroll
-        for (int q = 0; q < 4; q++) x[q] = cmake((rg + 8 * q == c) ? 1.0 : 0.0, 0.0);
-        for (int j = 0; j < w; j++) {                       // L11 y = e_c (unit lower)
-            if ((j & 7) == rg) {
-                const int jq = j >> 3;
-                s_y[j & 1][c] = jq == 0 ? x[0] : jq == 1 ? x[1] : jq == 2 ? x[2] : x[3];
+            for (int q = 0; q < PER; q++) {
+                const int e = t + q * GROUP, r = e >> 5, c = e & 31;
+                const cplx pk = cmul(s_B[k][c], rk);          // scaled pivot row
+                if (r == k) nv[q] = (c == k) ? rk : pk;
+                else {
+                    const cplx f = s_B[r][k];
+                    nv[q] = (c == k) ? cneg(cmul(f, rk)) : cfnma(s_B[r][c], f, pk);
+                }
             }
             __syncthreads();
-            const cplx yj = s_y[j & 1][c];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = rg + 8 * q;
-                if (i > j && i < w) x[q] = cfnma(x[q], s_lu[i][j], yj);
+            for (int q = 0; q < PER; q++) {
+                const int e = t + q * GROUP;
+                s_B[e >> 5][e & 31] = nv[q];
             }
         }
-        for (int j = w - 1; j >= 0; j--) {                  // U11 x = y
-            if ((j & 7) == rg) {
-                const int jq = j >> 3;
-                const cplx d = s_lu[j][j];
-                const cplx xv = jq == 0 ? x[0] : jq == 1 ? x[1] : jq == 2 ? x[2] : x[3];
-                const cplx v = (d.x != 0.0 || d.y != 0.0) ? cdiv(xv, d) : xv;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (q == jq) x[q] = v;
-                s_y[j & 1][c] = v;
-            }
-            __syncthreads();
-            const cplx xj = s_y[j & 1][c];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = rg + 8 * q;
-                if (i < j) x[q] = cfnma(x[q], s_lu[i][j], xj);
-            }
-        }
+        __syncthreads();
         cplx* inv = LU + (long)b * GNB_NB * GNB_NB;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int i = rg + 8 * q;
-            inv[i * GNB_NB + c] = (i < w && c < w) ? x[q] : cmake(0.0, 0.0);
+        for (int e = t; e < GNB_NB * GNB_NB; e += GROUP) {
+            const int r = e >> 5, c = e & 31;
+            inv[e] = (r < w && c < w) ? s_B[r][c] : cmake(0.0, 0.0);
         }
     }
     // ---- net row moves + permutation bookkeeping (warp 0) ---------------------------------------
@@ -683,23 +692,25 @@ cudaError_t gnb_kernels_init() {
 }
 
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
-                         const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E) {
+                         const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E,
+                         const int* pi) {
     if (M <= 0) return;
     dim3 grid(min(cdiv_i((long)N * N, 256 * 4), 4096), M);
-    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E);
+    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E, pi);
 }
 
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,
-                            const cplx* blk, long strideBlk) {
+                            const cplx* blk, long strideBlk, const int* map) {
     if (M <= 0 || nc <= 0) return;
     dim3 grid(min(cdiv_i((long)nc * nc, 256), 1024), M);
-    k_scatter_sub<<<grid, 256, 0, st>>>(A, strideA, ld, inds, nc, blk, strideBlk);
+    k_scatter_sub<<<grid, 256, 0, st>>>(A, strideA, ld, inds, nc, blk, strideBlk, map);
 }
 
-void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m) {
+void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m,
+                        const int* map) {
     if (M <= 0 || m <= 0) return;
     dim3 grid(min(cdiv_i((long)N * m, 256), 1024), M);
-    k_set_aug<<<grid, 256, 0, st>>>(A, strideA, ld, N, xoff, cols, m);
+    k_set_aug<<<grid, 256, 0, st>>>(A, strideA, ld, N, xoff, cols, m, map);
 }
 void gnb_launch_pad_diag(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int Np) {
     if (M <= 0 || Np <= N) return;
@@ -730,7 +741,9 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
     else { if (batchk) GNB_GO(false, true); else GNB_GO(false, false); }
 }
 
-// Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by both engines.
+static int g_tourn_group = 128;   // rows per tournament group in the recursive engine (128: CTA co-resides with the rank-K kernel)
+void gnb_set_tourn_group(int g) { g_tourn_group = (g == 256) ? 256 : 128; }
+// Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
                            int* info) {
@@ -738,15 +751,20 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
     const int* cin = nullptr;
     int* cout = cand0;
     long launches = 0;
+    const int G = g_tourn_group;
     for (;;) {
-        const int groups = cdiv_i(n, GNB_GROUP);
+        const int groups = cdiv_i(n, G);
         const int fin = groups == 1;
         dim3 grid(groups, M);
-        k_tourn<<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
-                                              perm, perm_stride, info);
+        if (G == 128)
+            k_tourn<128><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
+                                               perm, perm_stride, info);
+        else
+            k_tourn<256><<<grid, 256, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
+                                               perm, perm_stride, info);
         launches++;
         if (fin) break;
-        n = (groups - 1) * w + min(w, n - (groups - 1) * GNB_GROUP);
+        n = (groups - 1) * w + min(w, n - (groups - 1) * G);
         cin = cout;
         cout = (cout == cand0) ? cand1 : cand0;
     }
@@ -783,7 +801,7 @@ struct Elim {
             const int groups = cdiv_i(n, GNB_GROUP);
             const int fin = groups == 1;
             dim3 grid(groups, M);
-            k_tourn<<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, ws.cand_stride, cout, ws.cand_stride,
+            k_tourn<GNB_GROUP><<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, ws.cand_stride, cout, ws.cand_stride,
                                                   fin, lu(slot), mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride,
                                                   ws.info);
             launches++;

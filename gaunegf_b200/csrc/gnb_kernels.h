@@ -41,11 +41,14 @@ cudaError_t gnb_kernels_init();
 void gnb_set_gemm_bm(int bm);
 void gnb_set_gemm_pipe(int on);
 void gnb_set_two_level(int on);
+void gnb_set_tourn_group(int g);
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
-                         const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E);
+                         const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E,
+                         const int* pi = nullptr);
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,
-                            const cplx* blk, long strideBlk);
-void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m);
+                            const cplx* blk, long strideBlk, const int* map = nullptr);
+void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m,
+                        const int* map = nullptr);
 void gnb_launch_pad_diag(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int Np);
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk);
 long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
@@ -65,12 +68,13 @@ void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N);
 struct GnbRecWork {
     GnbGemmTimer* timer;
     int* cand0; int* cand1; int cand_stride;
-    cplx* inv;                         // [N/32][M][32][32]   inverse of every pivot block
-    int* moves;                        // [N/32][M][GNB_MOVES_STRIDE]
+    cplx* inv; long inv_blk_stride;    // [N/32][Mtot][32][32] inverse of every pivot block (block stride in cplx)
+    int* moves; long moves_blk_stride; // [N/32][Mtot][GNB_MOVES_STRIDE]                (block stride in ints)
     int* perm; int perm_stride;        // JORDAN: running row permutation
     cplx* Ppk; cplx* Lpk; long stridePk;   // packed panels [M][N/16][N/32][32][RK_PPS]
     cplx* Wpk; long strideWk;          // packed pivot rows [M][N/16][ld/32][16][RK_WPS]
     int* info;
+    int back_row_lo;                   // FORWARD: only rows >= back_row_lo of the solution are needed
 };
 size_t gnb_rec_pk_elems(int N);               // cplx elements per matrix of Ppk / Lpk (incl. slack)
 size_t gnb_rec_wk_elems(int N, int ld);       // cplx elements per matrix of Wpk (incl. slack)
@@ -88,7 +92,7 @@ void gnb_launch_unpermute(cudaStream_t st, int M, int N, const cplx* A, long str
 void gnb_launch_dos(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld,
                     const int* invperm, int pstride, double* tot, double* per_site);
 void gnb_launch_gather_rows(cudaStream_t st, int M, const cplx* X, long strideX, int ldx, const int* rows,
-                            int nr, int ncols, cplx* out, long strideOut);
+                            int nr, int ncols, cplx* out, long strideOut, const int* map = nullptr);
 void gnb_launch_trace_dot(cudaStream_t st, int M, const cplx* Z, const cplx* X, long stride, int n, double* T);
 void gnb_launch_gamma_from_sigma(cudaStream_t st, int M, const cplx* sig, long stride, int n, cplx* gam);
 void gnb_launch_scale_cols(cudaStream_t st, int M, cplx* X, long stride, int n, const cplx* w);

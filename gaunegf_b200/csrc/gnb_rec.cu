@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) k_rk_wsolve(cplx* __restrict__ A, long st
 size_t gnb_rec_pk_elems(int N) { return (size_t)(N / 16) * (N / 32) * RK_PBLK + 2 * RK_PBLK; }
 size_t gnb_rec_wk_elems(int N, int ld) { return (size_t)(N / 16) * (ld / 32) * RK_WBLK + 2 * RK_WBLK; }
 
-static int g_rk_m3 = 0;          // 3M complex arithmetic in the rank-K update
+static int g_rk_m3 = 1;          // 3M complex arithmetic in the rank-K update (3 real DMMAs per complex tile product)
 static int g_rk_m3_mink = 64;    // ... for K >= this
 static int g_rk_kskip = 1;
 static int g_rk_sms = 148;
@@ -433,14 +433,58 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_kskip")) g_rk_kskip = value;
 }
 
+// Developer trace: CUDA events around every launch of the engine, per stream (tools/trace_elim.py).
+#include <vector>
+#include <cstdio>
+namespace {
+struct TraceRec { const char* name; cudaStream_t st; cudaEvent_t e0, e1; int M; };
+std::vector<TraceRec> g_trace;
+cudaEvent_t g_trace_base = nullptr;
+int g_trace_on = 0;
+struct TraceScope {
+    size_t idx = (size_t)-1;
+    TraceScope(const char* name, cudaStream_t st, int M) {
+        if (!g_trace_on) return;
+        TraceRec r{name, st, nullptr, nullptr, M};
+        cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        idx = g_trace.size();
+        g_trace.push_back(r);
+    }
+    ~TraceScope() { if (idx != (size_t)-1) cudaEventRecord(g_trace[idx].e1, g_trace[idx].st); }
+};
+}  // namespace
+void gnb_rec_trace_start() {
+    g_trace.clear();
+    g_trace_on = 1;
+    if (!g_trace_base) cudaEventCreate(&g_trace_base);
+    cudaEventRecord(g_trace_base, 0);
+}
+int gnb_rec_trace_dump(const char* path) {
+    g_trace_on = 0;
+    cudaDeviceSynchronize();
+    FILE* f = fopen(path, "w");
+    if (!f) return 1;
+    for (auto& r : g_trace) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, g_trace_base, r.e0);
+        cudaEventElapsedTime(&t1, g_trace_base, r.e1);
+        fprintf(f, "%s %p %d %.4f %.4f\n", r.name, (void*)r.st, r.M, t0, t1);
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    fclose(f);
+    g_trace.clear();
+    return 0;
+}
+
 namespace {
 struct Rec {
     cudaStream_t st; int M, N, naug; cplx* A; long strideA; int ld; int jordan;
     const GnbRecWork& ws; long launches;
     int nrb, ncb;
 
-    cplx* inv(int c0) const { return ws.inv + (long)(c0 / GNB_NB) * M * GNB_NB * GNB_NB; }
-    int* mv(int c0) const { return ws.moves + (long)(c0 / GNB_NB) * M * GNB_MOVES_STRIDE; }
+    cplx* inv(int c0) const { return ws.inv + (long)(c0 / GNB_NB) * ws.inv_blk_stride; }
+    int* mv(int c0) const { return ws.moves + (long)(c0 / GNB_NB) * ws.moves_blk_stride; }
 
     void gemm(int ilo, int ihi, int jlo, int jhi, int klo, int khi, const cplx* P, int kskip) {
         if (ihi <= ilo || jhi <= jlo || khi <= klo) return;
@@ -457,6 +501,7 @@ struct Rec {
         if (g.kskip)            // rows inside [klo, khi) only meet the strictly block-upper part of the panel
             for (int i0 = ilo; i0 < ihi; i0 += 64)
                 if (i0 >= klo && i0 + 64 <= khi) flops -= 8.0 * 64.0 * (double)(jhi - jlo) * (double)(i0 + 32 - klo) * M;
+        TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
         if (ws.timer) ws.timer->begin(st);
         if (g_rk_m3 && khi - klo >= g_rk_m3_mink) k_rk_gemm<1><<<grid, 288, kRkSmem, st>>>(g, nti, ntj, (int)total);
         else k_rk_gemm<0><<<grid, 288, kRkSmem, st>>>(g, nti, ntj, (int)total);
@@ -465,8 +510,12 @@ struct Rec {
     }
 
     void base_step(int c0, int live_lo) {
-        launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
-                                          inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+        {
+            TraceScope ts("tourn", st, M);
+            launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
+                                              inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+        }
+        TraceScope ts2("panel", st, M);
         if (live_lo < c0) {
             dim3 grid(std::min((c0 - live_lo) / 16, 64), M);
             k_rk_moves_P<<<grid, 256, 0, st>>>(ws.Ppk, jordan ? ws.Lpk : nullptr, ws.stridePk, nrb, live_lo / 16, c0 / 16,
@@ -491,6 +540,7 @@ struct Rec {
         const int nb = w / GNB_NB;
         const cplx* Lsrc = jordan ? ws.Lpk : ws.Ppk;
         if (nb <= 2) {
+            TraceScope ts("wsolve", st, M);
             for (int i = 0; i < nb; i++) {
                 const int cb = c0 + i * GNB_NB;
                 dim3 grid(cdiv_i(jhi - jlo, WS_TC), M);
@@ -509,7 +559,8 @@ struct Rec {
     void apply_far(int c0, int w, int jlo, int jhi) {
         if (jhi <= jlo) return;
         dim3 grid(cdiv_i(jhi - jlo, 32), M);
-        k_rk_moves_A<<<grid, 256, 0, st>>>(A, strideA, ld, jlo, jhi, ws.moves, (long)M * GNB_MOVES_STRIDE, c0 / GNB_NB,
+        TraceScope ts("movesA", st, M);
+        k_rk_moves_A<<<grid, 256, 0, st>>>(A, strideA, ld, jlo, jhi, ws.moves, ws.moves_blk_stride, c0 / GNB_NB,
                                            (c0 + w) / GNB_NB);
         launches++;
         trsm(c0, w, jlo, jhi);
@@ -529,22 +580,28 @@ struct Rec {
         if (jordan) apply_far(c0 + h, w - h, c0, c0 + h);
     }
 
-    // X[c0 : c0 + w] of the unit-block-upper system; the blocks above the diagonal are the normalised rows in A
-    void backsub(int c0, int w) {
+    // X[c0 : c0 + w] of the unit-block-upper system; the blocks above the diagonal are the normalised rows in A.
+    // Only rows >= row_lo of the solution are produced (contacts-last ordering of the transmission path).
+    void backsub(int c0, int w, int row_lo) {
         if (w <= GNB_NB) return;
         const int h = (w / GNB_NB + 1) / 2 * GNB_NB;
-        backsub(c0 + h, w - h);
+        backsub(c0 + h, w - h, row_lo);
+        const int ilo = std::max(c0, row_lo);
+        if (ilo >= c0 + h) return;
         GnbGemmArgs g{};
         g.C = A + N; g.strideC = strideA; g.ldc = ld;
         g.P = A + c0 + h; g.strideP = strideA; g.ldp = ld;
         g.W = A + (long)(c0 + h) * ld + N; g.strideW = strideA; g.ldw = ld;
-        g.ilo = c0; g.ihi = c0 + h; g.jlo = 0; g.jhi = naug; g.kdim = w - h;
+        g.ilo = ilo; g.ihi = c0 + h; g.jlo = 0; g.jhi = naug; g.kdim = w - h;
         g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
-        if (ws.timer) ws.timer->begin(st);
-        gnb_launch_gemm(st, g, M, false, false);
-        if (ws.timer) ws.timer->end(st, 8.0 * (double)h * (double)naug * g.kdim * M);
-        launches++;
-        backsub(c0, h);
+        {
+            TraceScope ts("backsub", st, M);
+            if (ws.timer) ws.timer->begin(st);
+            gnb_launch_gemm(st, g, M, false, false);
+            if (ws.timer) ws.timer->end(st, 8.0 * (double)(c0 + h - ilo) * (double)naug * g.kdim * M);
+            launches++;
+        }
+        backsub(c0, h, row_lo);
     }
 };
 }  // namespace
@@ -557,7 +614,7 @@ long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long st
     e.factor(0, N, false, 0);
     if (!jordan && naug > 0) {
         e.apply_far(N - GNB_NB, GNB_NB, N, N + naug);      // the last block is nobody's left sibling
-        e.backsub(0, N);
+        e.backsub(0, N, std::max(0, ws.back_row_lo) / GNB_NB * GNB_NB);
     }
     return e.launches;
 }

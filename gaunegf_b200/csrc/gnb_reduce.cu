@@ -66,11 +66,13 @@ __global__ void __launch_bounds__(256) k_dos(int N, const cplx* __restrict__ A, 
 
 __global__ void __launch_bounds__(256) k_gather_rows(const cplx* __restrict__ X, long strideX, int ldx,
                                                      const int* __restrict__ rows, int nr, int ncols,
-                                                     cplx* __restrict__ out, long strideOut) {
+                                                     cplx* __restrict__ out, long strideOut,
+                                                     const int* __restrict__ map) {
     const int b = blockIdx.y;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nr * ncols; idx += gridDim.x * blockDim.x) {
         const int r = idx / ncols, c = idx - r * ncols;
-        out[(long)b * strideOut + idx] = X[(long)b * strideX + (long)rows[r] * ldx + c];
+        const int row = map ? map[rows[r]] : rows[r];
+        out[(long)b * strideOut + idx] = X[(long)b * strideX + (long)row * ldx + c];
     }
 }
 
@@ -147,10 +149,10 @@ void gnb_launch_dos(cudaStream_t st, int M, int N, const cplx* A, long strideA, 
     k_dos<<<M, 256, 0, st>>>(N, A, strideA, ld, invperm, pstride, tot, per_site);
 }
 void gnb_launch_gather_rows(cudaStream_t st, int M, const cplx* X, long strideX, int ldx, const int* rows,
-                            int nr, int ncols, cplx* out, long strideOut) {
+                            int nr, int ncols, cplx* out, long strideOut, const int* map) {
     if (M <= 0 || nr <= 0 || ncols <= 0) return;
     dim3 grid(min(cdiv_i((long)nr * ncols, 256), 1024), M);
-    k_gather_rows<<<grid, 256, 0, st>>>(X, strideX, ldx, rows, nr, ncols, out, strideOut);
+    k_gather_rows<<<grid, 256, 0, st>>>(X, strideX, ldx, rows, nr, ncols, out, strideOut, map);
 }
 void gnb_launch_trace_dot(cudaStream_t st, int M, const cplx* Z, const cplx* X, long stride, int n, double* T) {
     if (M <= 0) return;
