@@ -180,7 +180,6 @@ def run_ours(args):
     ctx.sigma_clear()
     ctx.sigma_add_const_block(np.arange(nc), np.diag(s1[:nc]))
     ctx.sigma_add_const_block(np.arange(N_ORB - nc, N_ORB), np.diag(s2[N_ORB - nc:]))
-    ctx.set_timing(True)
     T_last = [None]
 
     def step_dev():
@@ -188,17 +187,22 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_dev()
-    ctx.gemm_stats(reset=True)
     l0 = ctx.launches
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(step_dev, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - l0
+    value = M_total * args.steps / (ms * 1e-3)
+    # roofline leg: the same steps again with a CUDA-event pair around every launch of the rank-K update kernel
+    # (on the stream the kernel is launched on); kept out of `value` because the per-launch events cost time.
+    ctx.set_timing(True)
+    ctx.gemm_stats(reset=True)
+    roof_steps = max(1, min(args.steps, 3))
+    ms_roof = timed(step_dev, roof_steps)
     gemm_ms, gemm_flops, gemm_n = ctx.gemm_stats(reset=True)
     ctx.set_timing(False)
-    value = M_total * args.steps / (ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end leg: public API, host buffers, H2D + D2H inside the timed region ---------
     Fp = torch.from_numpy(F.astype(np.complex128)).pin_memory().numpy()
@@ -246,7 +250,7 @@ def run_ours(args):
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_ncu_summary.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_rk_gemm_ncu.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -258,10 +262,15 @@ def run_ours(args):
                     "api": "gaunegf_b200.transport.calculate_transmission (pinned numpy in, numpy out)",
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "k_gemm<false,false> (complex rank-32 update, DMMA.8x8x4)",
+            "roofline": {"bound": "tensor",
+                         "kernel": "k_rk_gemm (complex128 rank-K update C -= P W, K = 32..512, packed operands, DMMA.8x8x4; "
+                                   "3M arithmetic for K >= 64: 3 real DMMAs per complex tile product, so the algorithmic "
+                                   "rate may exceed the 4-multiplication pipe ceiling)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "launches_timed": int(gemm_n),
-                         "kernel_share_of_step": gemm_ms / ms if ms > 0 else None,
+                         "algorithmic_flops_per_launch_avg": gemm_flops / gemm_n if gemm_n else None,
+                         "kernel_share_of_step": gemm_ms / ms_roof if ms_roof > 0 else None,
+                         "roofline_leg_ms_per_step": ms_roof / roof_steps,
                          "step_algorithmic_tflops": (8 / 3 * N_ORB ** 3 + 8 * N_ORB ** 2 * nc) * E_loc.size * args.steps
                                                     / (ms * 1e-3) / 1e12},
             "secondary": {"what": f"integrate.GrInt contour integration N={N_ORB}: full G(E) per point + on-device weighted "
