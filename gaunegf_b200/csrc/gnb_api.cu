@@ -239,7 +239,7 @@ extern "C" int gnb_sigma_add_bethe(gnb_ctx* c, int natoms, const int32_t* inds, 
 GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc) {
     GnbElimWork w{};
     *rc = GNB_OK;
-    const int cand_stride = std::max(GNB_NB, (N + 255) / 256 * GNB_NB);
+    const int cand_stride = std::max(GNB_NB, (N + 127) / 128 * GNB_NB);
     cudaError_t e = cudaSuccess;
     auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
     need(c->cand0, (size_t)M * cand_stride * sizeof(int));

@@ -97,74 +97,134 @@ __device__ __forceinline__ cplx crcp_fast(cplx p) {
     return cmake(x * r, -y * r);
 }
 
+// Thread tiling: GROUP rows x 32 columns as 4-row x 8-column register tiles; warp w owns column group w
+// (columns 8w .. 8w+7) of all rows, lane l owns rows 4l .. 4l+3.  The warp that owns the pivot column finds
+// the pivot with two REDUX operations (no cross-warp reduction), publishes the column (for the multipliers)
+// and the winner; every warp takes its 8 elements of the pivot row from the lane of its own that holds them.
+// One CTA barrier per pivot step, ~30 shared-memory instructions per warp-step (a row-per-thread layout needs
+// 65 and is bound by the shared-memory pipe).  Inside the owning warp the tile is rotated by one column per
+// step so that the pivot column is always local column 0 (static register indices, small code).
 template <int GROUP>
-__global__ void __launch_bounds__(GROUP) k_tourn(const cplx* __restrict__ A, long strideA, int ld,
-                                                 int c0, int w, int r0, int n_in,
-                                                 const int* __restrict__ cand_in, int cand_in_stride,
-                                                 int* __restrict__ cand_out, int cand_out_stride,
-                                                 int final_round, cplx* __restrict__ LU,
-                                                 int* __restrict__ moves, int* __restrict__ perm,
-                                                 int perm_stride, int* __restrict__ info) {
-    constexpr int NW = GROUP / 32;
+__global__ void __launch_bounds__(GROUP, 3) k_tourn(const cplx* __restrict__ A, long strideA, int ld,
+                                                    int c0, int w, int r0, int n_in,
+                                                    const int* __restrict__ cand_in, int cand_in_stride,
+                                                    int* __restrict__ cand_out, int cand_out_stride,
+                                                    int final_round, cplx* __restrict__ LU,
+                                                    int* __restrict__ moves, int* __restrict__ perm,
+                                                    int perm_stride, int* __restrict__ info) {
+    static_assert(GROUP == 128, "tile mapping: 4 warps = 4 column groups, 32 lanes x 4 rows");
     const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
-    const int lane = t & 31, warp = t >> 5;
-    const int i = g * GROUP + t;
-    const bool valid = i < n_in;
-    int row = -1;
-    if (valid) row = cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i;
-
-    cplx a[GNB_NB];
-    {
-        const cplx* src = A + (long)b * strideA + (long)(valid ? row : 0) * ld + c0;
+    const int lane = t & 31, tc = t >> 5;                  // tc = column group of this warp
+    int rows[4];
+    cplx a[4][8];
+    const cplx* Ab = A + (long)b * strideA;
 #pragma unroll
-        for (int c = 0; c < GNB_NB; c++) a[c] = (valid && c < w) ? src[c] : cmake(0.0, 0.0);
+    for (int rr = 0; rr < 4; rr++) {
+        const int i = g * GROUP + 4 * lane + rr;
+        const bool valid = i < n_in;
+        rows[rr] = valid ? (cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i) : -1;
+        const cplx* src = Ab + (long)(valid ? rows[rr] : 0) * ld + c0 + 8 * tc;
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? src[k] : cmake(0.0, 0.0);
     }
     const int ngroup = min(GROUP, n_in - g * GROUP);
     const int nsel = min(w, ngroup);
 
-    __shared__ double s_cm[2][NW];
-    __shared__ int s_ci[2][NW];
-    __shared__ __align__(16) cplx s_crow[2][NW][GNB_NB];
+    __shared__ __align__(16) cplx s_col[2][GROUP];          // pivot column of every row (before scaling), [rr][lane]
+    __shared__ int s_widx[2];                               // winner: rr * 32 + lane
+    __shared__ double s_wmax[2];
+    __shared__ __align__(16) cplx s_prow[4][8];             // per warp: its 8 elements of the pivot row
     __shared__ int s_win[GNB_NB];
-    __shared__ __align__(16) cplx s_B[GNB_NB][GNB_NB + 1];      // final round: pivot block -> its inverse
-    bool alive = valid;
+    __shared__ __align__(16) cplx s_B[GNB_NB][GNB_NB + 1];  // final round: pivot block -> its inverse
+    unsigned alive = 0;                                     // bit rr: row 4*lane + rr still a candidate
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) alive |= (rows[rr] >= 0 ? 1u : 0u) << rr;
 
-#pragma unroll 1
-    for (int j = 0; j < nsel; j++) {
-        const int buf = j & 1;
-        const double m = cabs1(a[0]);
-        // order-preserving integer key: 0 for retired rows, bits(m) + 1 otherwise (m >= 0)
-        const unsigned long long key = alive ? (unsigned long long)__double_as_longlong(m) + 1ull : 0ull;
+    // pivot search of step jn on local column 0 of the owning warp; results go to buffer jn & 1
+    auto search = [&](int jn) {
+        const int nb_ = jn & 1;
+        unsigned long long key = 0ull;
+        int krr = 0;
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            s_col[nb_][rr * 32 + lane] = a[rr][0];
+            const unsigned long long kq = ((alive >> rr) & 1u)
+                ? (unsigned long long)__double_as_longlong(cabs1(a[rr][0])) + 1ull : 0ull;
+            if (kq > key) { key = kq; krr = rr; }            // first maximum wins (izamax)
+        }
         const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
         const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
         const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
         const unsigned bal = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
-        if (lane == __ffs(bal) - 1) {                         // lowest lane on ties (izamax picks the first maximum)
-            s_cm[buf][warp] = key ? m : -1.0;
-            s_ci[buf][warp] = t;
-#pragma unroll
-            for (int c = 0; c < GNB_NB; c++) s_crow[buf][warp][c] = a[c];
+        if (lane == __ffs(bal) - 1) {
+            s_widx[nb_] = krr * 32 + lane;
+            s_wmax[nb_] = key ? __longlong_as_double((long long)(key - 1ull)) : -1.0;
+            s_win[jn] = krr == 0 ? rows[0] : krr == 1 ? rows[1] : krr == 2 ? rows[2] : rows[3];
         }
+    };
+    if (tc == 0 && nsel > 0) search(0);
+
+#pragma unroll 1
+    for (int j = 0; j < nsel; j++) {
+        const int buf = j & 1, jc = j >> 3;
         __syncthreads();
-        double bm = s_cm[buf][0];
-        int bw = 0;
+        const int wi = s_widx[buf];
+        const double bm = s_wmax[buf];
+        if (final_round && bm == 0.0 && t == 0) *info = 1;     // exactly singular pivot (LAPACK info > 0)
+        if (lane == (wi & 31)) {
+            const int wr = wi >> 5;
+            alive &= ~(1u << wr);
+            if (tc >= jc) {                                   // this lane holds the pivot row: publish this warp's 8 elements
 #pragma unroll
-        for (int q = 1; q < NW; q++)
-            if (s_cm[buf][q] > bm) { bm = s_cm[buf][q]; bw = q; }
-        const cplx* prow = s_crow[buf][bw];
-        if (t == s_ci[buf][bw]) {
-            alive = false;
-            s_win[j] = row;
-            if (final_round && bm == 0.0) *info = 1;          // exactly singular pivot (LAPACK info > 0)
+                for (int k = 0; k < 8; k++) {
+                    cplx v = a[0][k];
+                    if (wr == 1) v = a[1][k];
+                    if (wr == 2) v = a[2][k];
+                    if (wr == 3) v = a[3][k];
+                    s_prow[tc][k] = v;
+                }
+            }
         }
-        if (alive) {
-            // LAPACK zgetf2 scales the column by the reciprocal of the pivot
-            const cplx rinv = (bm > 0.0) ? crcp_fast(prow[0]) : cmake(0.0, 0.0);
-            const cplx l = cmul(a[0], rinv);
+        if (tc < jc) continue;                                // all columns of this warp are eliminated (warp-uniform)
+        __syncwarp();
+        // LAPACK zgetf2 scales the column by the reciprocal of the pivot
+        const cplx rinv = (bm > 0.0) ? crcp_fast(s_col[buf][wi]) : cmake(0.0, 0.0);
+        cplx l[4];
 #pragma unroll
-            for (int c = 0; c < GNB_NB - 1; c++) a[c] = cfnma(a[c + 1], l, prow[c + 1]);
-            a[GNB_NB - 1] = cmake(0.0, 0.0);
+        for (int rr = 0; rr < 4; rr++) l[rr] = cmul(s_col[buf][rr * 32 + lane], rinv);
+        // look-ahead: the warp that owns the next pivot column updates that column first, searches the next
+        // pivot and publishes it, and only then finishes its update -- the search overlaps the other warps' work
+        const bool next_owner = (j + 1 < nsel) && (tc == ((j + 1) >> 3));
+        if (tc == jc) {                                       // owning warp: update and rotate left by one column
+            {
+                const cplx p = s_prow[tc][1];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) a[rr][0] = cfnma(a[rr][1], l[rr], p);
+            }
+            if (next_owner) search(j + 1);
+#pragma unroll
+            for (int k = 1; k < 7; k++) {
+                const cplx p = s_prow[tc][k + 1];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) a[rr][k] = cfnma(a[rr][k + 1], l[rr], p);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) a[rr][7] = cmake(0.0, 0.0);
+        } else {
+            {
+                const cplx p = s_prow[tc][0];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) a[rr][0] = cfnma(a[rr][0], l[rr], p);
+            }
+            if (next_owner) search(j + 1);
+#pragma unroll
+            for (int k = 1; k < 8; k++) {
+                const cplx p = s_prow[tc][k];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) a[rr][k] = cfnma(a[rr][k], l[rr], p);
+            }
         }
+        __syncwarp();                                         // s_prow[tc] is rewritten in the next step
     }
     __syncthreads();
     if (!final_round) {
@@ -751,17 +811,13 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
     const int* cin = nullptr;
     int* cout = cand0;
     long launches = 0;
-    const int G = g_tourn_group;
+    const int G = 128;
     for (;;) {
         const int groups = cdiv_i(n, G);
         const int fin = groups == 1;
         dim3 grid(groups, M);
-        if (G == 128)
-            k_tourn<128><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
-                                               perm, perm_stride, info);
-        else
-            k_tourn<256><<<grid, 256, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
-                                               perm, perm_stride, info);
+        k_tourn<128><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
+                                           perm, perm_stride, info);
         launches++;
         if (fin) break;
         n = (groups - 1) * w + min(w, n - (groups - 1) * G);
@@ -782,6 +838,9 @@ void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N) 
 // only the 64 "near" columns of an outer step are updated block by block; every other ("far")
 // column receives ONE rank-64 update per outer step, which halves the C traffic of the dominant
 // kernel (tools/proto_blockgj.py: two_level_jordan / two_level_forward are the numpy models).
+long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
+                           int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
+                           int* info);
 static int g_two_level = 1;
 void gnb_set_two_level(int on) { g_two_level = on; }
 
@@ -794,22 +853,8 @@ struct Elim {
     int* mv(int slot) const { return ws.moves + (long)slot * M * GNB_MOVES_STRIDE; }
 
     void tournament(int c0, int w, int slot) {
-        int n = N - c0;
-        const int* cin = nullptr;
-        int* cout = ws.cand0;
-        for (;;) {
-            const int groups = cdiv_i(n, GNB_GROUP);
-            const int fin = groups == 1;
-            dim3 grid(groups, M);
-            k_tourn<GNB_GROUP><<<grid, GNB_GROUP, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, ws.cand_stride, cout, ws.cand_stride,
-                                                  fin, lu(slot), mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride,
-                                                  ws.info);
-            launches++;
-            if (fin) break;
-            n = (groups - 1) * w + min(w, n - (groups - 1) * GNB_GROUP);
-            cin = cout;
-            cout = (cout == ws.cand0) ? ws.cand1 : ws.cand0;
-        }
+        launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, w, ws.cand0, ws.cand1, ws.cand_stride, lu(slot),
+                                          mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
     }
     void permute_solve(cplx* buf, long stride, int bld, int c0, int w, int lo, int hi, int slot, int mode,
                        const cplx* preL = nullptr, long strideL = 0, int ldL = 0, int pre_row = 0, int pre_k = 0) {

@@ -342,65 +342,96 @@ __global__ void __launch_bounds__(256) k_rk_moves_P(cplx* __restrict__ Ppk, cplx
     }
 }
 
-// W_b = inv_b (A[K_b, cols] - sum_{a in prev} L_ba W_a)  for a 64-column tile; written to A and to Wpk.
-// prev = the nprev (0 or 1) blocks immediately left of block b (fused pre-update of a leaf pair).
+// Forward W of a leaf of nb (1 or 2) adjacent pivot blocks on columns [jlo, jhi):
+//     W_a = inv_a A[K_a, cols];   W_b = inv_b (A[K_b, cols] - L_ba W_a)
+// written to A and to Wpk.  One CTA walks several 64-column tiles of one matrix, so the pivot-block inverses and
+// L_ba are staged in shared memory once, and W_a never makes a round trip through global memory.
 #define WS_TC 64
-__global__ void __launch_bounds__(256) k_rk_wsolve(cplx* __restrict__ A, long strideA, int ld, int c0, int jlo, int jhi,
-                                                   const cplx* __restrict__ inv, const cplx* __restrict__ Lsrc,
-                                                   long stridePk, int nrb, int nprev, cplx* __restrict__ Wpk,
-                                                   long strideWk, int ncb) {
+__global__ void __launch_bounds__(256, 2) k_rk_wsolve(cplx* __restrict__ A, long strideA, int ld, int c0, int nb, int jlo,
+                                                      int jhi, int tiles_per_cta, const cplx* __restrict__ inv_a,
+                                                      const cplx* __restrict__ inv_b, const cplx* __restrict__ Lsrc,
+                                                      long stridePk, int nrb, cplx* __restrict__ Wpk, long strideWk,
+                                                      int ncb) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    cplx* tile = reinterpret_cast<cplx*>(smem_raw);          // [32][WS_TC]
-    cplx* sInv = tile + GNB_NB * WS_TC;                      // [32][32]
-    cplx* sL = sInv + GNB_NB * GNB_NB;                       // [32][32]
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);          // [64][WS_TC]: rows of block a, then rows of block b
+    cplx* sInv = tile + 2 * GNB_NB * WS_TC;                  // [2][32][32]
+    cplx* sL = sInv + 2 * GNB_NB * GNB_NB;                   // [32][32]  L_ba
     const int b = blockIdx.y, t = threadIdx.x;
-    const int cs = jlo + blockIdx.x * WS_TC;
     cplx* Ab = A + (long)b * strideA;
-    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) sInv[idx] = inv[(long)b * GNB_NB * GNB_NB + idx];
-    if (nprev) {
-        const int ca = c0 - GNB_NB;
+    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) sInv[idx] = inv_a[(long)b * GNB_NB * GNB_NB + idx];
+    if (nb == 2) {
+        const int cb = c0 + GNB_NB;
         const cplx* Lb = Lsrc + (long)b * stridePk;
         for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) {
-            const int i = idx >> 5, j = idx & 31, k = ca + j;
-            sL[idx] = Lb[((long)(k >> 4) * nrb + (c0 >> 5)) * RK_PBLK + i * RK_PPS + (k & 15)];
+            sInv[GNB_NB * GNB_NB + idx] = inv_b[(long)b * GNB_NB * GNB_NB + idx];
+            const int i = idx >> 5, j = idx & 31, k = c0 + j;
+            sL[idx] = Lb[((long)(k >> 4) * nrb + (cb >> 5)) * RK_PBLK + i * RK_PPS + (k & 15)];
         }
     }
-    for (int idx = t; idx < GNB_NB * WS_TC; idx += 256) {
-        const int i = idx / WS_TC, c = idx - i * WS_TC, col = cs + c;
-        tile[idx] = (col < jhi) ? Ab[(long)(c0 + i) * ld + col] : cmake(0.0, 0.0);
-    }
-    __syncthreads();
-    const int c = t & (WS_TC - 1), rg = t >> 6, col = cs + c;
-    const bool ok = col < jhi;
-    cplx acc[8];
-    if (nprev) {
+    const int nrows = nb * GNB_NB;
+    const int c = t & (WS_TC - 1), rg = t >> 6;
+    for (int tt = 0; tt < tiles_per_cta; tt++) {
+        const int cs = jlo + (blockIdx.x * tiles_per_cta + tt) * WS_TC;
+        if (cs >= jhi) break;                                 // block-uniform
+        __syncthreads();                                      // previous tile fully consumed (and sInv/sL staged)
+        for (int idx = t; idx < nrows * WS_TC; idx += 256) {
+            const int i = idx / WS_TC, cc = idx - i * WS_TC, col = cs + cc;
+            tile[idx] = (col < jhi) ? Ab[(long)(c0 + i) * ld + col] : cmake(0.0, 0.0);
+        }
+        __syncthreads();
+        const int col = cs + c;
+        const bool ok = col < jhi;
+        cplx acc[8];
+        // ---- W_a = inv_a R_a
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = tile[(rg + 4 * q) * WS_TC + c];
-        if (ok)
+        for (int q = 0; q < 8; q++) acc[q] = cmake(0.0, 0.0);
+        for (int j = 0; j < GNB_NB; j++) {
+            const cplx r = tile[j * WS_TC + c];
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[q] = cfma(acc[q], sInv[(rg + 4 * q) * GNB_NB + j], r);
+        }
+        cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
+        if (ok) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int k = c0 + rg + 4 * q;
+                Ab[(long)k * ld + col] = acc[q];
+                Wb[(long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS] = acc[q];
+            }
+        }
+        if (nb == 2) {
+            __syncthreads();                                  // every thread is done reading R_a
+#pragma unroll
+            for (int q = 0; q < 8; q++) tile[(rg + 4 * q) * WS_TC + c] = acc[q];      // W_a replaces R_a
+            __syncthreads();
+            // ---- R_b -= L_ba W_a
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[q] = tile[(GNB_NB + rg + 4 * q) * WS_TC + c];
             for (int j = 0; j < GNB_NB; j++) {
-                const cplx wa = Ab[(long)(c0 - GNB_NB + j) * ld + col];
+                const cplx wa = tile[j * WS_TC + c];
 #pragma unroll
                 for (int q = 0; q < 8; q++) acc[q] = cfnma(acc[q], sL[(rg + 4 * q) * GNB_NB + j], wa);
             }
-        __syncthreads();
+            __syncthreads();                                  // R_b rows are private per (row, col) but read by all below
 #pragma unroll
-        for (int q = 0; q < 8; q++) tile[(rg + 4 * q) * WS_TC + c] = acc[q];
-        __syncthreads();
-    }
+            for (int q = 0; q < 8; q++) tile[(GNB_NB + rg + 4 * q) * WS_TC + c] = acc[q];
+            __syncthreads();
+            // ---- W_b = inv_b R_b
 #pragma unroll
-    for (int q = 0; q < 8; q++) acc[q] = cmake(0.0, 0.0);
-    for (int j = 0; j < GNB_NB; j++) {
-        const cplx r = tile[j * WS_TC + c];
+            for (int q = 0; q < 8; q++) acc[q] = cmake(0.0, 0.0);
+            for (int j = 0; j < GNB_NB; j++) {
+                const cplx r = tile[(GNB_NB + j) * WS_TC + c];
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = cfma(acc[q], sInv[(rg + 4 * q) * GNB_NB + j], r);
-    }
-    if (ok) {
-        cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
+                for (int q = 0; q < 8; q++) acc[q] = cfma(acc[q], sInv[GNB_NB * GNB_NB + (rg + 4 * q) * GNB_NB + j], r);
+            }
+            if (ok) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int k = c0 + rg + 4 * q;
-            Ab[(long)k * ld + col] = acc[q];
-            Wb[(long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS] = acc[q];
+                for (int q = 0; q < 8; q++) {
+                    const int k = c0 + GNB_NB + rg + 4 * q;
+                    Ab[(long)k * ld + col] = acc[q];
+                    Wb[(long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS] = acc[q];
+                }
+            }
         }
     }
 }
@@ -415,7 +446,7 @@ static int g_rk_m3 = 1;          // 3M complex arithmetic in the rank-K update (
 static int g_rk_m3_mink = 64;    // ... for K >= this
 static int g_rk_kskip = 1;
 static int g_rk_sms = 148;
-static const size_t kWsSmem = (size_t)(GNB_NB * WS_TC + 2 * GNB_NB * GNB_NB) * sizeof(cplx);
+static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_rec_init() {
     cudaError_t e;
@@ -541,13 +572,14 @@ struct Rec {
         const cplx* Lsrc = jordan ? ws.Lpk : ws.Ppk;
         if (nb <= 2) {
             TraceScope ts("wsolve", st, M);
-            for (int i = 0; i < nb; i++) {
-                const int cb = c0 + i * GNB_NB;
-                dim3 grid(cdiv_i(jhi - jlo, WS_TC), M);
-                k_rk_wsolve<<<grid, 256, kWsSmem, st>>>(A, strideA, ld, cb, jlo, jhi, inv(cb), Lsrc, ws.stridePk, nrb, i,
-                                                         ws.Wpk, ws.strideWk, ncb);
-                launches++;
-            }
+            const int ntile = cdiv_i(jhi - jlo, WS_TC);
+            const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
+            const int per = cdiv_i(ntile, split);
+            dim3 grid(cdiv_i(ntile, per), M);
+            k_rk_wsolve<<<grid, 256, kWsSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
+                                                     nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb, ws.Wpk,
+                                                     ws.strideWk, ncb);
+            launches++;
             return;
         }
         const int h = (nb + 1) / 2 * GNB_NB;
