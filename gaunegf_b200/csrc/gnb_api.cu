@@ -100,7 +100,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
-    else if (!strcmp(name, "tourn_group")) gnb_set_tourn_group(value);
+    else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
     else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
     else return GNB_ERR_ARG;
     return GNB_OK;

@@ -97,26 +97,60 @@ __device__ __forceinline__ cplx crcp_fast(cplx p) {
     return cmake(x * r, -y * r);
 }
 
+// Scalar traits of the tournament: the NOMINATING rounds run in single precision (half the registers, twice the
+// resident groups, no FP64-pipe use); they only pick which rows go on.  The FINAL round, which fixes the pivot
+// order, and the pivot-block inverse are always double precision on the original matrix entries.
+template <typename R> struct TT;
+template <> struct TT<double> {
+    typedef double2 C;
+    static __device__ __forceinline__ C ld(cplx v) { return v; }
+    static __device__ __forceinline__ C zero() { return make_double2(0.0, 0.0); }
+    static __device__ __forceinline__ C mul(C a, C b) { return cmul(a, b); }
+    static __device__ __forceinline__ C fnma(C a, C b, C c) { return cfnma(a, b, c); }
+    static __device__ __forceinline__ C rcp(C p) { return crcp_fast(p); }
+    static __device__ __forceinline__ unsigned long long key(C v) {          // order-preserving, > 0
+        return (unsigned long long)__double_as_longlong(fabs(v.x) + fabs(v.y)) + 1ull;
+    }
+};
+template <> struct TT<float> {
+    typedef float2 C;
+    static __device__ __forceinline__ C ld(cplx v) { return make_float2((float)v.x, (float)v.y); }
+    static __device__ __forceinline__ C zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ C mul(C a, C b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+    static __device__ __forceinline__ C fnma(C a, C b, C c) {
+        return make_float2(fmaf(b.y, c.y, fmaf(-b.x, c.x, a.x)), fmaf(-b.y, c.x, fmaf(-b.x, c.y, a.y)));
+    }
+    static __device__ __forceinline__ C rcp(C p) {
+        const float s = fmaxf(fabsf(p.x), fabsf(p.y));
+        const float sc = 1.0f / s;
+        const float x = p.x * sc, y = p.y * sc;
+        const float r = sc / fmaf(x, x, y * y);
+        return make_float2(x * r, -y * r);
+    }
+    static __device__ __forceinline__ unsigned long long key(C v) {
+        return (unsigned long long)__float_as_uint(fabsf(v.x) + fabsf(v.y)) + 1ull;
+    }
+};
+
 // Thread tiling: GROUP rows x 32 columns as 4-row x 8-column register tiles; warp w owns column group w
 // (columns 8w .. 8w+7) of all rows, lane l owns rows 4l .. 4l+3.  The warp that owns the pivot column finds
-// the pivot with two REDUX operations (no cross-warp reduction), publishes the column (for the multipliers)
+// the pivot with REDUX operations (no cross-warp reduction), publishes the column (for the multipliers)
 // and the winner; every warp takes its 8 elements of the pivot row from the lane of its own that holds them.
-// One CTA barrier per pivot step, ~30 shared-memory instructions per warp-step (a row-per-thread layout needs
-// 65 and is bound by the shared-memory pipe).  Inside the owning warp the tile is rotated by one column per
-// step so that the pivot column is always local column 0 (static register indices, small code).
-template <int GROUP>
-__global__ void __launch_bounds__(GROUP, 3) k_tourn(const cplx* __restrict__ A, long strideA, int ld,
-                                                    int c0, int w, int r0, int n_in,
-                                                    const int* __restrict__ cand_in, int cand_in_stride,
-                                                    int* __restrict__ cand_out, int cand_out_stride,
-                                                    int final_round, cplx* __restrict__ LU,
-                                                    int* __restrict__ moves, int* __restrict__ perm,
-                                                    int perm_stride, int* __restrict__ info) {
+// One CTA barrier per pivot step; the owning warp searches the NEXT pivot (look-ahead) before it finishes its
+// own update.  Inside the owning warp the tile is rotated by one column per step so that the pivot column is
+// always local column 0 (static register indices, small code).
+template <int GROUP, typename R>
+__global__ void __launch_bounds__(GROUP, sizeof(R) == 4 ? 5 : 3)
+k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0, int n_in,
+        const int* __restrict__ cand_in, int cand_in_stride, int* __restrict__ cand_out, int cand_out_stride,
+        int final_round, cplx* __restrict__ LU, int* __restrict__ moves, int* __restrict__ perm, int perm_stride,
+        int* __restrict__ info) {
     static_assert(GROUP == 128, "tile mapping: 4 warps = 4 column groups, 32 lanes x 4 rows");
+    typedef typename TT<R>::C C;
     const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
     const int lane = t & 31, tc = t >> 5;                  // tc = column group of this warp
     int rows[4];
-    cplx a[4][8];
+    C a[4][8];
     const cplx* Ab = A + (long)b * strideA;
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) {
@@ -125,17 +159,17 @@ __global__ void __launch_bounds__(GROUP, 3) k_tourn(const cplx* __restrict__ A, 
         rows[rr] = valid ? (cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i) : -1;
         const cplx* src = Ab + (long)(valid ? rows[rr] : 0) * ld + c0 + 8 * tc;
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? src[k] : cmake(0.0, 0.0);
+        for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? TT<R>::ld(src[k]) : TT<R>::zero();
     }
     const int ngroup = min(GROUP, n_in - g * GROUP);
     const int nsel = min(w, ngroup);
 
-    __shared__ __align__(16) cplx s_col[2][GROUP];          // pivot column of every row (before scaling), [rr][lane]
+    __shared__ __align__(16) C s_col[2][GROUP];             // pivot column of every row (before scaling), [rr][lane]
     __shared__ int s_widx[2];                               // winner: rr * 32 + lane
-    __shared__ double s_wmax[2];
-    __shared__ __align__(16) cplx s_prow[4][8];             // per warp: its 8 elements of the pivot row
+    __shared__ int s_wnz[2];                                // winner magnitude: -1 none, 0 exactly zero, 1 positive
+    __shared__ __align__(16) C s_prow[4][8];                // per warp: its 8 elements of the pivot row
     __shared__ int s_win[GNB_NB];
-    __shared__ __align__(16) cplx s_B[GNB_NB][GNB_NB + 1];  // final round: pivot block -> its inverse
+    __shared__ __align__(16) cplx s_B[sizeof(R) == 8 ? GNB_NB : 1][GNB_NB + 1];  // final round: pivot block -> inverse
     unsigned alive = 0;                                     // bit rr: row 4*lane + rr still a candidate
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) alive |= (rows[rr] >= 0 ? 1u : 0u) << rr;
@@ -148,17 +182,23 @@ __global__ void __launch_bounds__(GROUP, 3) k_tourn(const cplx* __restrict__ A, 
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             s_col[nb_][rr * 32 + lane] = a[rr][0];
-            const unsigned long long kq = ((alive >> rr) & 1u)
-                ? (unsigned long long)__double_as_longlong(cabs1(a[rr][0])) + 1ull : 0ull;
+            const unsigned long long kq = ((alive >> rr) & 1u) ? TT<R>::key(a[rr][0]) : 0ull;
             if (kq > key) { key = kq; krr = rr; }            // first maximum wins (izamax)
         }
-        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-        const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
-        const unsigned bal = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
+        unsigned bal;
+        if (sizeof(R) == 4) {
+            const unsigned k32 = (unsigned)key;
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, k32);
+            bal = __ballot_sync(0xffffffffu, k32 == kmax);
+        } else {
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+            bal = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
+        }
         if (lane == __ffs(bal) - 1) {
             s_widx[nb_] = krr * 32 + lane;
-            s_wmax[nb_] = key ? __longlong_as_double((long long)(key - 1ull)) : -1.0;
+            s_wnz[nb_] = key == 0ull ? -1 : (key == TT<R>::key(TT<R>::zero()) ? 0 : 1);
             s_win[jn] = krr == 0 ? rows[0] : krr == 1 ? rows[1] : krr == 2 ? rows[2] : rows[3];
         }
     };
@@ -169,15 +209,15 @@ __global__ void __launch_bounds__(GROUP, 3) k_tourn(const cplx* __restrict__ A, 
         const int buf = j & 1, jc = j >> 3;
         __syncthreads();
         const int wi = s_widx[buf];
-        const double bm = s_wmax[buf];
-        if (final_round && bm == 0.0 && t == 0) *info = 1;     // exactly singular pivot (LAPACK info > 0)
+        const int nz = s_wnz[buf];
+        if (final_round && nz == 0 && t == 0) *info = 1;      // exactly singular pivot (LAPACK info > 0)
         if (lane == (wi & 31)) {
             const int wr = wi >> 5;
             alive &= ~(1u << wr);
             if (tc >= jc) {                                   // this lane holds the pivot row: publish this warp's 8 elements
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    cplx v = a[0][k];
+                    C v = a[0][k];
                     if (wr == 1) v = a[1][k];
                     if (wr == 2) v = a[2][k];
                     if (wr == 3) v = a[3][k];
@@ -188,46 +228,46 @@ __global__ void __launch_bounds__(GROUP, 3) k_tourn(const cplx* __restrict__ A, 
         if (tc < jc) continue;                                // all columns of this warp are eliminated (warp-uniform)
         __syncwarp();
         // LAPACK zgetf2 scales the column by the reciprocal of the pivot
-        const cplx rinv = (bm > 0.0) ? crcp_fast(s_col[buf][wi]) : cmake(0.0, 0.0);
-        cplx l[4];
+        const C rinv = (nz > 0) ? TT<R>::rcp(s_col[buf][wi]) : TT<R>::zero();
+        C l[4];
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) l[rr] = cmul(s_col[buf][rr * 32 + lane], rinv);
+        for (int rr = 0; rr < 4; rr++) l[rr] = TT<R>::mul(s_col[buf][rr * 32 + lane], rinv);
         // look-ahead: the warp that owns the next pivot column updates that column first, searches the next
         // pivot and publishes it, and only then finishes its update -- the search overlaps the other warps' work
         const bool next_owner = (j + 1 < nsel) && (tc == ((j + 1) >> 3));
         if (tc == jc) {                                       // owning warp: update and rotate left by one column
             {
-                const cplx p = s_prow[tc][1];
+                const C p = s_prow[tc][1];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][0] = cfnma(a[rr][1], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][0] = TT<R>::fnma(a[rr][1], l[rr], p);
             }
             if (next_owner) search(j + 1);
 #pragma unroll
             for (int k = 1; k < 7; k++) {
-                const cplx p = s_prow[tc][k + 1];
+                const C p = s_prow[tc][k + 1];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][k] = cfnma(a[rr][k + 1], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][k] = TT<R>::fnma(a[rr][k + 1], l[rr], p);
             }
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) a[rr][7] = cmake(0.0, 0.0);
+            for (int rr = 0; rr < 4; rr++) a[rr][7] = TT<R>::zero();
         } else {
             {
-                const cplx p = s_prow[tc][0];
+                const C p = s_prow[tc][0];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][0] = cfnma(a[rr][0], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][0] = TT<R>::fnma(a[rr][0], l[rr], p);
             }
             if (next_owner) search(j + 1);
 #pragma unroll
             for (int k = 1; k < 8; k++) {
-                const cplx p = s_prow[tc][k];
+                const C p = s_prow[tc][k];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][k] = cfnma(a[rr][k], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][k] = TT<R>::fnma(a[rr][k], l[rr], p);
             }
         }
         __syncwarp();                                         // s_prow[tc] is rewritten in the next step
     }
     __syncthreads();
-    if (!final_round) {
+    if (!final_round || sizeof(R) == 4) {
         if (t < nsel) cand_out[(long)b * cand_out_stride + g * w + t] = s_win[t];
         return;
     }
@@ -801,8 +841,8 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
     else { if (batchk) GNB_GO(false, true); else GNB_GO(false, false); }
 }
 
-static int g_tourn_group = 128;   // rows per tournament group in the recursive engine (128: CTA co-resides with the rank-K kernel)
-void gnb_set_tourn_group(int g) { g_tourn_group = (g == 256) ? 256 : 128; }
+static int g_tourn_fp32 = 1;      // nominating (non-final) tournament rounds in single precision
+void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
@@ -816,8 +856,12 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         const int groups = cdiv_i(n, G);
         const int fin = groups == 1;
         dim3 grid(groups, M);
-        k_tourn<128><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin, LU, moves,
-                                           perm, perm_stride, info);
+        if (!fin && g_tourn_fp32)
+            k_tourn<128, float><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, 0, LU,
+                                                      moves, perm, perm_stride, info);
+        else
+            k_tourn<128, double><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin,
+                                                       LU, moves, perm, perm_stride, info);
         launches++;
         if (fin) break;
         n = (groups - 1) * w + min(w, n - (groups - 1) * G);

@@ -15,7 +15,7 @@ def ev(f, n=2):
 
 ctx = Context(0)
 import ctypes, os
-for opt in ("two_level", "gemm_pipe", "engine_rec", "rec_streams", "tourn_group", "rk_m3", "rk_m3_mink", "rk_kskip"):
+for opt in ("two_level", "gemm_pipe", "engine_rec", "rec_streams", "tourn_fp32", "rk_m3", "rk_m3_mink", "rk_kskip"):
     if opt.upper() in os.environ:
         ctx.lib.gnb_dev_set_option(opt.encode(), int(os.environ[opt.upper()]))
 ctx.set_timing(True)

@@ -9,7 +9,7 @@ streams = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 nc = 64 if N >= 1024 else max(N // 16, 2)
 ctx = Context(0)
 ctx.lib.gnb_dev_set_option(b"rec_streams", streams)
-for opt in ("rk_m3", "tourn_group"):
+for opt in ("rk_m3", "tourn_fp32"):
     if opt.upper() in os.environ:
         ctx.lib.gnb_dev_set_option(opt.encode(), int(os.environ[opt.upper()]))
 F, S = sy.hermitian_pair(N, seed=1)
