@@ -185,3 +185,87 @@ def test_bethe_sigma(ctx, golden):
     Eg = mid * (x + 1) + mu - 0.25
     out = ctx.gless_int(Eg, mid * w * 1.0, 1) / (2 * np.pi)
     assert relerr(out, G["PgB"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# Recursive multi-level engine (gnb_rec.cu): A/B against the two-level engine and its own switches
+# ---------------------------------------------------------------------------------------------------
+def _set(ctx, **opts):
+    for k, v in opts.items():
+        assert ctx.lib.gnb_dev_set_option(k.encode(), int(v)) == 0
+
+
+DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=1)
+
+
+@pytest.mark.parametrize("N,nc", [(96, 8), (100, 7), (256, 16), (416, 33), (600, 40)])
+def test_recursive_engine_matches_two_level_engine_and_numpy(ctx, N, nc):
+    """padded sizes (N, naug not multiples of 32), both elimination modes, against numpy and the other engine"""
+    F, S, inds, sig = const_system(ctx, N, nc, seed=N + 1)
+    st = sig[0] + sig[1]
+    E = np.array([0.13 + 0j, -0.8 + 0.5j, 0.41 + 1e-6j])
+    Er = np.linspace(-0.7, 0.9, 5)
+    z, w = sy.contour_points(6, -5.0, 0.0)
+    out = {}
+    try:
+        for eng in (1, 0):
+            _set(ctx, engine_rec=eng)
+            out[eng] = (ctx.green(E), ctx.transmission(Er, 0, -1), ctx.gr_int(z, w), ctx.gless_int(Er, np.ones(5) * 0.2, -1))
+    finally:
+        _set(ctx, **DEFAULTS)
+    Gref = np.array([O.gr_matrix(st, e, F, S) for e in E])
+    for k in range(len(E)):
+        assert relerr(out[1][0][k], Gref[k]) < TOL
+    for a, b in zip(out[1], out[0]):
+        assert relerr(a, b) < TOL
+    g1 = 1j * (sig[0] - sig[0].conj().T)
+    g2 = 1j * (sig[1] - sig[1].conj().T)
+    Tref = np.array([O.transmission_restricted(e, F, S, st, g1, g2) for e in Er])
+    assert np.allclose(out[1][1], Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
+
+
+@pytest.mark.parametrize("opt", ["rk_m3", "rk_kskip", "contacts_last", "tourn_fp32", "rec_streams"])
+def test_recursive_engine_switches_do_not_change_results(ctx, opt):
+    """3M arithmetic, block-upper K skipping, contacts-last ordering, FP32 nominating rounds and sub-batch streams
+    are performance switches: results must stay within the parity tolerance of the plain path."""
+    N, nc = 320, 32
+    F, S, inds, sig = const_system(ctx, N, nc, seed=7)
+    E = np.concatenate([np.linspace(-1, 1, 70), [0.2 + 0.3j]])
+    Er = np.linspace(-1, 1, 70)
+    res = {}
+    try:
+        for v in ((1, 0) if opt != "rec_streams" else (1, 2)):
+            _set(ctx, **{opt: v})
+            res[v] = (ctx.green(E[-2:]), ctx.transmission(Er, 0, -1), ctx.dos(E)[0])
+    finally:
+        _set(ctx, **DEFAULTS)
+    a, b = list(res.values())
+    for x, y in zip(a, b):
+        assert relerr(x, y) < TOL
+
+
+def test_full_size_properties_n1024(ctx):
+    """BASELINE size (N = 1024, 64-orbital contacts): size-independent properties instead of a CPU comparison of
+    every point -- G A = I, T from the contact-column solve == T from the full inverse, reciprocity T12 == T21,
+    0 <= T <= min(n1, n2); plus one energy against numpy."""
+    N, nc = 1024, 64
+    F, S = sy.hermitian_pair(N, seed=1)
+    s1, s2 = sy.block_sigma_vectors(N, nc, 0.1)
+    ctx.set_system(F, S)
+    ctx.sigma_clear()
+    ctx.sigma_add_const_block(np.arange(nc), np.diag(s1[:nc]))
+    ctx.sigma_add_const_block(np.arange(N - nc, N), np.diag(s2[N - nc:]))
+    E = np.linspace(-0.5, 0.5, 40)
+    T12 = ctx.transmission(E, 0, -1)
+    T21 = ctx.transmission(E, -1, 0)
+    assert np.all(T12 > -1e-12) and np.all(T12 < nc + 1e-9)
+    assert np.allclose(T12, T21, rtol=1e-9, atol=1e-12)
+    G = ctx.green(E[:3])
+    sig = np.diag(s1 + s2)
+    g1, g2 = np.diag(-2 * s1.imag), np.diag(-2 * s2.imag)
+    for k in range(3):
+        A = E[k] * S - F - sig
+        assert np.abs(G[k] @ A - np.eye(N)).max() < 1e-9
+        Tfull = np.trace(g1 @ G[k] @ g2 @ G[k].conj().T).real
+        assert abs(Tfull - T12[k]) < 1e-9 * max(1.0, abs(Tfull))
+    assert relerr(G[0], np.linalg.inv(E[0] * S - F - sig)) < TOL
