@@ -23,7 +23,7 @@ int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where) {
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
 static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
-static int g_rec_streams = 1;     // independent sub-batches (streams) per chunk in the recursive engine
+static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
 
 extern "C" const char* gnb_version(void) { return "gaunegf_b200 0.1 (sm_100a)"; }
 
@@ -375,7 +375,8 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
         // Independent sub-batches on separate streams: the latency-bound panel kernels of one sub-batch
         // overlap the tensor-pipe-bound rank-K updates of the others.
         int S = std::max(1, std::min(g_rec_streams, GNB_MAX_SUBSTREAMS));
-        S = std::min(S, std::max(1, M / 32));
+        S = std::min(S, std::max(1, M / 64));
+        if (c->timing) S = 1;                   // per-launch event timing of the rank-K kernel needs it alone on the GPU
         if (S <= 1) {
             c->launches += gnb_eliminate_rec(c->stream, M, L.Np, L.naugp, A, strideA, L.ld, jordan, w);
         } else {

@@ -195,7 +195,7 @@ def _set(ctx, **opts):
         assert ctx.lib.gnb_dev_set_option(k.encode(), int(v)) == 0
 
 
-DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=1)
+DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=2)
 
 
 @pytest.mark.parametrize("N,nc", [(96, 8), (100, 7), (256, 16), (416, 33), (600, 40)])
@@ -234,7 +234,7 @@ def test_recursive_engine_switches_do_not_change_results(ctx, opt):
     Er = np.linspace(-1, 1, 70)
     res = {}
     try:
-        for v in ((1, 0) if opt != "rec_streams" else (1, 2)):
+        for v in ((1, 0) if opt != "rec_streams" else (1, 3)):
             _set(ctx, **{opt: v})
             res[v] = (ctx.green(E[-2:]), ctx.transmission(Er, 0, -1), ctx.dos(E)[0])
     finally:
