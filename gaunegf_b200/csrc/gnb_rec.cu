@@ -66,14 +66,17 @@ struct RkGemmArgs {
 };
 
 #define RK_ST 4
-#define RK_PST (2 * RK_PBLK)
-#define RK_WST (2 * RK_WBLK)
-#define RK_STAGE (RK_PST + RK_WST)
-static const size_t kRkSmem = (size_t)RK_ST * RK_STAGE * sizeof(cplx) + 2 * RK_ST * 8;
+template <int RB, int CB> constexpr size_t rk_smem() {
+    return (size_t)RK_ST * (RB * RK_PBLK + CB * RK_WBLK) * sizeof(cplx) + 2 * RK_ST * 8;
+}
 
-template <int M3>
+// CTA tile = (32 RB) x (32 CB), RB * CB = 4: 64 x 64 for the general case, 128 x 32 for 32-column strips.
+template <int M3, int RB, int CB>
 __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int ntj, int total) {
-    constexpr int NCW = 8, WN = 2, MI = 2, NI = 4, KC = 16;
+    static_assert(RB * CB == 4, "8 consumer warps of 16 x 32");
+    constexpr int NCW = 8, WN = CB, MI = 2, NI = 4, KC = 16;
+    constexpr int TM = 32 * RB, TN = 32 * CB;
+    constexpr int RK_PST = RB * RK_PBLK, RK_WST = CB * RK_WBLK, RK_STAGE = RK_PST + RK_WST;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(smem_raw);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + RK_ST * RK_STAGE);
@@ -96,9 +99,9 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
             const int tile = blockIdx.x + it * gridDim.x;
             const int b = tile / per_mat, rem = tile - b * per_mat;
             const int ti = rem / ntj, tj = rem - ti * ntj;
-            const int i0 = g.ilo + ti * 64, j0 = g.jlo + tj * 64;
+            const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
             int ch0 = 0;
-            if (g.kskip && i0 >= g.klo && i0 + 64 <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;   // panel is zero up to the block diagonal
+            if (g.kskip && i0 >= g.klo && i0 + TM <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;   // panel is zero up to the block diagonal
             const cplx* Pb = g.P + (long)b * g.sP + ((long)kc0 * g.nrb + i0 / 32) * RK_PBLK;
             const cplx* Wb = g.W + (long)b * g.sW + ((long)kc0 * g.ncb + j0 / 32) * RK_WBLK;
             for (int ch = ch0; ch < nch_all; ch++, q++) {
@@ -129,9 +132,9 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
         const int tile = blockIdx.x + it * gridDim.x;
         const int b = tile / per_mat, rem = tile - b * per_mat;
         const int ti = rem / ntj, tj = rem - ti * ntj;
-        const int i0 = g.ilo + ti * 64, j0 = g.jlo + tj * 64;
+        const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
         int ch0 = 0;
-        if (g.kskip && i0 >= g.klo && i0 + 64 <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;
+        if (g.kskip && i0 >= g.klo && i0 + TM <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;
         const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);     // warp tile inside the range
         for (int ch = ch0; ch < nch_all; ch++, q++) {
             const int s = q % RK_ST;
@@ -439,19 +442,22 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve(cplx* __restrict__ A, long
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-size_t gnb_rec_pk_elems(int N) { return (size_t)(N / 16) * (N / 32) * RK_PBLK + 2 * RK_PBLK; }
-size_t gnb_rec_wk_elems(int N, int ld) { return (size_t)(N / 16) * (ld / 32) * RK_WBLK + 2 * RK_WBLK; }
+size_t gnb_rec_pk_elems(int N) { return (size_t)(N / 16) * (N / 32) * RK_PBLK + 4 * RK_PBLK; }
+size_t gnb_rec_wk_elems(int N, int ld) { return (size_t)(N / 16) * (ld / 32) * RK_WBLK + 4 * RK_WBLK; }
 
 static int g_rk_m3 = 1;          // 3M complex arithmetic in the rank-K update (3 real DMMAs per complex tile product)
 static int g_rk_m3_mink = 64;    // ... for K >= this
 static int g_rk_kskip = 1;
+static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_rec_init() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_rk_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRkSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_rk_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRkSmem))) return e;
+#define RK_ATTR(M3_, RB_, CB_)                                                                                  \
+    if ((e = cudaFuncSetAttribute(k_rk_gemm<M3_, RB_, CB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                  (int)rk_smem<RB_, CB_>()))) return e;
+    RK_ATTR(0, 2, 2) RK_ATTR(1, 2, 2) RK_ATTR(0, 4, 1) RK_ATTR(1, 4, 1)
     if ((e = cudaFuncSetAttribute(k_rk_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem))) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -462,6 +468,7 @@ void gnb_rec_set_option(const char* name, int value) {
     if (!strcmp(name, "rk_m3")) g_rk_m3 = value;
     else if (!strcmp(name, "rk_m3_mink")) g_rk_m3_mink = value;
     else if (!strcmp(name, "rk_kskip")) g_rk_kskip = value;
+    else if (!strcmp(name, "rk_strip")) g_rk_strip = value;
 }
 
 // Developer trace: CUDA events around every launch of the engine, per stream (tools/trace_elim.py).
@@ -525,17 +532,25 @@ struct Rec {
         g.W = ws.Wpk; g.sW = ws.strideWk; g.ncb = ncb;
         g.ilo = ilo; g.ihi = ihi; g.jlo = jlo; g.jhi = jhi; g.klo = klo; g.khi = khi;
         g.kskip = (kskip && g_rk_kskip) ? 1 : 0;
-        const int nti = cdiv_i(ihi - ilo, 64), ntj = cdiv_i(jhi - jlo, 64);
+        const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);     // 128 x 32 tiles for 32-column strips
+        const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
+        const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
         const long total = (long)M * nti * ntj;
         const int grid = (int)std::min<long>(total, (long)g_rk_sms);
         double flops = 8.0 * (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M;
         if (g.kskip)            // rows inside [klo, khi) only meet the strictly block-upper part of the panel
-            for (int i0 = ilo; i0 < ihi; i0 += 64)
-                if (i0 >= klo && i0 + 64 <= khi) flops -= 8.0 * 64.0 * (double)(jhi - jlo) * (double)(i0 + 32 - klo) * M;
+            for (int i0 = ilo; i0 < ihi; i0 += tm)
+                if (i0 >= klo && i0 + tm <= khi) flops -= 8.0 * tm * (double)(jhi - jlo) * (double)(i0 + 32 - klo) * M;
         TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
         if (ws.timer) ws.timer->begin(st);
-        if (g_rk_m3 && khi - klo >= g_rk_m3_mink) k_rk_gemm<1><<<grid, 288, kRkSmem, st>>>(g, nti, ntj, (int)total);
-        else k_rk_gemm<0><<<grid, 288, kRkSmem, st>>>(g, nti, ntj, (int)total);
+        const bool m3 = g_rk_m3 && khi - klo >= g_rk_m3_mink;
+        if (strip) {
+            if (m3) k_rk_gemm<1, 4, 1><<<grid, 288, rk_smem<4, 1>(), st>>>(g, nti, ntj, (int)total);
+            else k_rk_gemm<0, 4, 1><<<grid, 288, rk_smem<4, 1>(), st>>>(g, nti, ntj, (int)total);
+        } else {
+            if (m3) k_rk_gemm<1, 2, 2><<<grid, 288, rk_smem<2, 2>(), st>>>(g, nti, ntj, (int)total);
+            else k_rk_gemm<0, 2, 2><<<grid, 288, rk_smem<2, 2>(), st>>>(g, nti, ntj, (int)total);
+        }
         if (ws.timer) ws.timer->end(st, flops);
         launches++;
     }
