@@ -247,31 +247,54 @@ __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ 
 }
 
 // Phase 2 (JORDAN): A[r][K] = -P[r][K] inv  (rows outside the pivot block), A[K][K] = inv.
-__global__ void __launch_bounds__(256) k_rk_panel_fin(cplx* __restrict__ A, long strideA, int ld, int N, int c0,
+// One CTA = 64 rows; P rows and the inverse are staged in shared memory, every thread forms a 4 x 4 block of
+// the product (8 LDS.128 per 16 complex FMAs, FP64-FMA bound).
+#define PF_ROWS 64
+#define PF_PS 33
+__global__ void __launch_bounds__(128) k_rk_panel_fin(cplx* __restrict__ A, long strideA, int ld, int N, int c0,
                                                       const cplx* __restrict__ inv, const cplx* __restrict__ Ppk,
                                                       long stridePk, int nrb) {
-    __shared__ cplx s_inv[GNB_NB * GNB_NB];
-    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, wrp = t >> 5;
-    for (int i = t; i < GNB_NB * GNB_NB; i += 256) s_inv[i] = inv[(long)b * GNB_NB * GNB_NB + i];
-    __syncthreads();
-    cplx* Ab = A + (long)b * strideA;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* s_inv = reinterpret_cast<cplx*>(smem_raw);         // [32][32]
+    cplx* s_P = s_inv + GNB_NB * GNB_NB;                     // [PF_ROWS][PF_PS]
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int r0 = blockIdx.x * PF_ROWS;
+    for (int i = t; i < GNB_NB * GNB_NB; i += 128) s_inv[i] = inv[(long)b * GNB_NB * GNB_NB + i];
     const cplx* Pb = Ppk + (long)b * stridePk;
-    const int kc = c0 / 16 + (lane >> 4), kk = lane & 15;
-    for (int r = blockIdx.x * 8 + wrp; r < N; r += gridDim.x * 8) {
-        cplx out;
-        if (r >= c0 && r < c0 + GNB_NB) {
-            out = s_inv[(r - c0) * GNB_NB + lane];
-        } else {
-            const cplx p = Pb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk];
-            cplx acc = cmake(0.0, 0.0);
-#pragma unroll 8
-            for (int j = 0; j < GNB_NB; j++) {
-                const cplx pj = cmake(__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j));
-                acc = cfnma(acc, pj, s_inv[j * GNB_NB + lane]);
-            }
-            out = acc;
-        }
-        Ab[(long)r * ld + c0 + lane] = out;
+    for (int e = t; e < PF_ROWS * GNB_NB; e += 128) {
+        const int rr = e >> 5, k = e & 31, r = r0 + rr;
+        cplx v = cmake(0.0, 0.0);
+        if (r < N) v = Pb[((long)(c0 / 16 + (k >> 4)) * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + (k & 15)];
+        s_P[rr * PF_PS + k] = v;
+    }
+    __syncthreads();
+    const int tr = t >> 3, tq = t & 7;                      // rows 4 tr .. 4 tr + 3, columns 4 tq .. 4 tq + 3
+    cplx acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[i][c] = cmake(0.0, 0.0);
+#pragma unroll 4
+    for (int j = 0; j < GNB_NB; j++) {
+        cplx p[4], v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = s_P[(4 * tr + i) * PF_PS + j];
+#pragma unroll
+        for (int c = 0; c < 4; c++) v[c] = s_inv[j * GNB_NB + 4 * tq + c];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][c] = cfnma(acc[i][c], p[i], v[c]);
+    }
+    cplx* Ab = A + (long)b * strideA;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = r0 + 4 * tr + i;
+        if (r >= N) continue;
+        const bool piv = (r >= c0 && r < c0 + GNB_NB);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            Ab[(long)r * ld + c0 + 4 * tq + c] = piv ? s_inv[(r - c0) * GNB_NB + 4 * tq + c] : acc[i][c];
     }
 }
 
@@ -450,6 +473,7 @@ static int g_rk_m3_mink = 64;    // ... for K >= this
 static int g_rk_kskip = 1;
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
+static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
 static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_rec_init() {
@@ -459,6 +483,7 @@ cudaError_t gnb_rec_init() {
                                   (int)rk_smem<RB_, CB_>()))) return e;
     RK_ATTR(0, 2, 2) RK_ATTR(1, 2, 2) RK_ATTR(0, 4, 1) RK_ATTR(1, 4, 1)
     if ((e = cudaFuncSetAttribute(k_rk_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_panel_fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmem))) return e;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_rk_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -575,8 +600,8 @@ struct Rec {
             launches++;
         }
         if (jordan) {
-            dim3 grid(std::min(cdiv_i(N, 8), 128), M);
-            k_rk_panel_fin<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, inv(c0), ws.Ppk, ws.stridePk, nrb);
+            dim3 grid(cdiv_i(N, PF_ROWS), M);
+            k_rk_panel_fin<<<grid, 128, kPfSmem, st>>>(A, strideA, ld, N, c0, inv(c0), ws.Ppk, ws.stridePk, nrb);
             launches++;
         }
     }
