@@ -462,6 +462,115 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve(cplx* __restrict__ A, long
     }
 }
 
+// DMMA version of the leaf forward-W kernel (same contract as k_rk_wsolve; columns in 32-wide tiles):
+// the three 32 x 32 x 32 products of a leaf pair run on the FP64 tensor pipe.  8 warps = 2 (rows) x 4 (columns),
+// warp tile 16 x 8; A operands (inv_a, L_ba, inv_b) with row stride 36, the R / W tile with row stride 34
+// (conflict-free LDS.128 fragment loads, as in k_rk_gemm).
+#define WM_TC 32
+#define WM_AS 36
+#define WM_BS 34
+__device__ __forceinline__ void ws_mma_product(double (&cre)[2][2], double (&cim)[2][2], const cplx* __restrict__ sAm,
+                                               const cplx* __restrict__ sBk, int wm, int wn, int gid, int tig, bool neg) {
+#pragma unroll
+    for (int kk = 0; kk < GNB_NB; kk += 4) {
+        cplx a[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) a[mi] = sAm[(wm * 16 + mi * 8 + gid) * WM_AS + kk + tig];
+        const cplx bq = sBk[(kk + tig) * WM_BS + wn * 8 + gid];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const double ax = neg ? -a[mi].x : a[mi].x, ay = neg ? -a[mi].y : a[mi].y;
+            dmma884(cre[mi][0], cre[mi][1], ax, bq.x);
+            dmma884(cim[mi][0], cim[mi][1], ax, bq.y);
+            dmma884(cre[mi][0], cre[mi][1], -ay, bq.y);
+            dmma884(cim[mi][0], cim[mi][1], ay, bq.x);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, long strideA, int ld, int c0, int nb,
+                                                          int jlo, int jhi, int tiles_per_cta,
+                                                          const cplx* __restrict__ inv_a, const cplx* __restrict__ inv_b,
+                                                          const cplx* __restrict__ Lsrc, long stridePk, int nrb,
+                                                          cplx* __restrict__ Wpk, long strideWk, int ncb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* sA = reinterpret_cast<cplx*>(smem_raw);            // [3][32][WM_AS]: inv_a, L_ba, inv_b
+    cplx* sB = sA + 3 * GNB_NB * WM_AS;                      // [64][WM_BS]: R_a / W_a rows, then R_b rows
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int gid = lane >> 2, tig = lane & 3, wm = warp >> 2, wn = warp & 3;
+    cplx* Ab = A + (long)b * strideA;
+    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) {
+        const int i = idx >> 5, j = idx & 31;
+        sA[i * WM_AS + j] = inv_a[(long)b * GNB_NB * GNB_NB + idx];
+        if (nb == 2) {
+            const int cb = c0 + GNB_NB, k = c0 + j;
+            sA[(2 * GNB_NB + i) * WM_AS + j] = inv_b[(long)b * GNB_NB * GNB_NB + idx];
+            sA[(GNB_NB + i) * WM_AS + j] =
+                Lsrc[(long)b * stridePk + ((long)(k >> 4) * nrb + (cb >> 5)) * RK_PBLK + i * RK_PPS + (k & 15)];
+        }
+    }
+    const int nrows = nb * GNB_NB;
+    for (int tt = 0; tt < tiles_per_cta; tt++) {
+        const int cs = jlo + (blockIdx.x * tiles_per_cta + tt) * WM_TC;
+        if (cs >= jhi) break;                                 // block-uniform
+        __syncthreads();                                      // previous tile consumed; operands staged
+        for (int idx = t; idx < nrows * WM_TC; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            sB[i * WM_BS + cc] = Ab[(long)(c0 + i) * ld + cs + cc];
+        }
+        __syncthreads();
+        double cre[2][2], cim[2][2];
+        const int col = cs + wn * 8 + tig * 2;                // this thread's two adjacent output columns
+        cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
+        // ---- W_a = inv_a R_a
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
+        ws_mma_product(cre, cim, sA, sB, wm, wn, gid, tig, false);
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int k = c0 + wm * 16 + mi * 8 + gid;
+            const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
+            Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1;
+            cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
+            wq[0] = v0; wq[1] = v1;
+        }
+        if (nb == 2) {
+            __syncthreads();                                  // every warp is done reading R_a
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm * 16 + mi * 8 + gid, cc = wn * 8 + tig * 2;
+                sB[r * WM_BS + cc] = cmake(cre[mi][0], cim[mi][0]);          // W_a replaces R_a
+                sB[r * WM_BS + cc + 1] = cmake(cre[mi][1], cim[mi][1]);
+                const cplx r0 = sB[(GNB_NB + r) * WM_BS + cc], r1 = sB[(GNB_NB + r) * WM_BS + cc + 1];
+                cre[mi][0] = r0.x; cim[mi][0] = r0.y; cre[mi][1] = r1.x; cim[mi][1] = r1.y;   // accumulators <- R_b
+            }
+            __syncthreads();
+            // ---- R_b -= L_ba W_a
+            ws_mma_product(cre, cim, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, true);
+            // R_b of this warp's rows x columns is read only through B fragments of the next product
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm * 16 + mi * 8 + gid, cc = wn * 8 + tig * 2;
+                sB[(GNB_NB + r) * WM_BS + cc] = cmake(cre[mi][0], cim[mi][0]);
+                sB[(GNB_NB + r) * WM_BS + cc + 1] = cmake(cre[mi][1], cim[mi][1]);
+            }
+            __syncthreads();
+            // ---- W_b = inv_b R_b
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
+            ws_mma_product(cre, cim, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WM_BS, wm, wn, gid, tig, false);
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int k = c0 + GNB_NB + wm * 16 + mi * 8 + gid;
+                const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
+                Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1;
+                cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
+                wq[0] = v0; wq[1] = v1;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -474,6 +583,8 @@ static int g_rk_kskip = 1;
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
+static const size_t kWmSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WM_BS) * sizeof(cplx);
+static int g_rk_wsolve_mma = 1;  // leaf forward-W products on the FP64 tensor pipe
 static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_rec_init() {
@@ -483,6 +594,7 @@ cudaError_t gnb_rec_init() {
                                   (int)rk_smem<RB_, CB_>()))) return e;
     RK_ATTR(0, 2, 2) RK_ATTR(1, 2, 2) RK_ATTR(0, 4, 1) RK_ATTR(1, 4, 1)
     if ((e = cudaFuncSetAttribute(k_rk_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_wsolve_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWmSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_rk_panel_fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmem))) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -494,6 +606,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_m3_mink")) g_rk_m3_mink = value;
     else if (!strcmp(name, "rk_kskip")) g_rk_kskip = value;
     else if (!strcmp(name, "rk_strip")) g_rk_strip = value;
+    else if (!strcmp(name, "rk_wsolve_mma")) g_rk_wsolve_mma = value;
 }
 
 // Developer trace: CUDA events around every launch of the engine, per stream (tools/trace_elim.py).
@@ -612,13 +725,23 @@ struct Rec {
         const cplx* Lsrc = jordan ? ws.Lpk : ws.Ppk;
         if (nb <= 2) {
             TraceScope ts("wsolve", st, M);
-            const int ntile = cdiv_i(jhi - jlo, WS_TC);
-            const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
-            const int per = cdiv_i(ntile, split);
-            dim3 grid(cdiv_i(ntile, per), M);
-            k_rk_wsolve<<<grid, 256, kWsSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
-                                                     nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb, ws.Wpk,
-                                                     ws.strideWk, ncb);
+            if (g_rk_wsolve_mma) {
+                const int ntile = (jhi - jlo) / WM_TC;
+                const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
+                const int per = cdiv_i(ntile, split);
+                dim3 grid(cdiv_i(ntile, per), M);
+                k_rk_wsolve_mma<<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
+                                                            nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
+                                                            ws.Wpk, ws.strideWk, ncb);
+            } else {
+                const int ntile = cdiv_i(jhi - jlo, WS_TC);
+                const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
+                const int per = cdiv_i(ntile, split);
+                dim3 grid(cdiv_i(ntile, per), M);
+                k_rk_wsolve<<<grid, 256, kWsSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
+                                                         nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb, ws.Wpk,
+                                                         ws.strideWk, ncb);
+            }
             launches++;
             return;
         }
