@@ -324,10 +324,10 @@ static Lay make_layout(int N, int naug) {
     return L;
 }
 
-static GnbRecWork rec_work(gnb_ctx* c, int M, const Lay& L, bool jordan, int* rc) {
+GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc) {
     GnbRecWork w{};
     *rc = GNB_OK;
-    const int Np = L.Np, nblk = Np / 32;
+    const int nblk = Np / 32;
     const int cand_stride = std::max(GNB_NB, (Np + 127) / 128 * GNB_NB);
     cudaError_t e = cudaSuccess;
     auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
@@ -336,7 +336,7 @@ static GnbRecWork rec_work(gnb_ctx* c, int M, const Lay& L, bool jordan, int* rc
     need(c->LU, (size_t)nblk * M * GNB_NB * GNB_NB * sizeof(cplx));
     need(c->moves, (size_t)nblk * M * GNB_MOVES_STRIDE * sizeof(int));
     need(c->info, sizeof(int) * 4);
-    const size_t pk = gnb_rec_pk_elems(Np), wk = gnb_rec_wk_elems(Np, L.ld);
+    const size_t pk = gnb_rec_pk_elems(Np), wk = gnb_rec_wk_elems(Np, ld);
     need(c->Ppk, (size_t)M * pk * sizeof(cplx));
     need(c->Wpk, (size_t)M * wk * sizeof(cplx));
     if (jordan) {
@@ -368,7 +368,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
     int rc;
     const long strideA = (long)L.Np * L.ld;
     if (L.rec) {
-        GnbRecWork w = rec_work(c, M, L, jordan != 0, &rc);
+        GnbRecWork w = gnb_rec_work(c, M, L.Np, L.ld, jordan != 0, &rc);
         if (rc) return rc;
         w.back_row_lo = L.back_row_lo;
         if (c->timing) GNB_CK(cudaEventRecord(c->ev0, c->stream));

@@ -99,6 +99,7 @@ int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_ga
 int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE);     // leaves g in c->cg
 int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cplx* d_out);
 GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc);
+GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc);
 int gnb_fail(gnb_ctx* c, int code, const std::string& msg);
 int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where);
 

@@ -25,22 +25,36 @@ class ArrayPlan:
 
     def __init__(self, sigs, N):
         self.N = N
-        self.full = []
-        for s in sigs:
-            s = np.asarray(s)
-            self.full.append(np.diag(s).astype(complex) if s.ndim == 1 else s.astype(complex))
-        for f in self.full:
-            if f.shape != (N, N):
-                raise ValueError(f"self-energy of shape {f.shape} does not match a {N}x{N} system")
-        self.inds = [support(f) for f in self.full]
+        self._src = [np.asarray(s) for s in sigs]
+        self._full = None
+        self.inds, self.blocks = [], []
+        for s in self._src:
+            if s.ndim == 1:                      # vector -> diagonal: never materialise the N x N matrix
+                if s.shape != (N,):
+                    raise ValueError(f"self-energy of shape {(s.shape[0], s.shape[0])} does not match a {N}x{N} system")
+                i = np.nonzero(s)[0]
+                self.inds.append(i)
+                self.blocks.append(np.diag(s[i]).astype(complex))
+            else:
+                if s.shape != (N, N):
+                    raise ValueError(f"self-energy of shape {s.shape} does not match a {N}x{N} system")
+                i = support(s)
+                self.inds.append(i)
+                self.blocks.append(s[np.ix_(i, i)].astype(complex))
         # compact (low-rank) path when every contact touches at most half of the orbitals
         self.kind = DESC if all(0 < len(i) <= max(1, N // 2) for i in self.inds) else DENSE_CONST
+
+    @property
+    def full(self):
+        if self._full is None:
+            self._full = [np.diag(s).astype(complex) if s.ndim == 1 else s.astype(complex) for s in self._src]
+        return self._full
 
     def install(self, ctx):
         ctx.sigma_clear()
         if self.kind == DESC:
-            for f, i in zip(self.full, self.inds):
-                ctx.sigma_add_const_block(i, f[np.ix_(i, i)])
+            for b, i in zip(self.blocks, self.inds):
+                ctx.sigma_add_const_block(i, b)
 
     def sigma_total(self, E=None):
         return sum(self.full)
