@@ -263,16 +263,22 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor",
-                         "kernel": "k_rk_gemm (complex128 rank-K update C -= P W, K = 32..512, packed operands, DMMA.8x8x4; "
-                                   "3M arithmetic for K >= 64: 3 real DMMAs per complex tile product, so the algorithmic "
-                                   "rate may exceed the 4-multiplication pipe ceiling)",
+                         "kernel": "k_rk_gemm (complex128 rank-K update C -= P W, K = 32..512, packed operands, DMMA.8x8x4). "
+                                   "achieved counts EXECUTED arithmetic in 4-multiplication-equivalent flops: 8 per complex "
+                                   "MAC, 4 where the panel is real, 2 where panel and pivot rows are real (real F, S, E with "
+                                   "the contact orbitals ordered last keep every column left of the contacts exactly real); "
+                                   "complex tiles with K >= 64 use 3M arithmetic (3 DMMAs for an 8-flop MAC), so the rate can "
+                                   "exceed the DMMA ceiling",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "launches_timed": int(gemm_n),
                          "algorithmic_flops_per_launch_avg": gemm_flops / gemm_n if gemm_n else None,
                          "kernel_share_of_step": gemm_ms / ms_roof if ms_roof > 0 else None,
                          "roofline_leg_ms_per_step": ms_roof / roof_steps,
                          "step_algorithmic_tflops": (8 / 3 * N_ORB ** 3 + 8 * N_ORB ** 2 * nc) * E_loc.size * args.steps
-                                                    / (ms * 1e-3) / 1e12},
+                                                    / (ms * 1e-3) / 1e12,
+                         "step_algorithmic_note": "complex128 flop count of the contact-column algorithm (SURVEY 8d: 8/3 N^3 "
+                                                  "+ 8 N^2 n2 per energy); the executed count is lower because real columns "
+                                                  "are updated with real arithmetic"},
             "secondary": {"what": f"integrate.GrInt contour integration N={N_ORB}: full G(E) per point + on-device weighted "
                                   f"reduction + one NCCL all-reduce per call, {Mg} points per GPU per call (public API, host buffers)",
                           "value": grint_val, "unit": UNIT,

@@ -129,6 +129,12 @@ extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* 
     c->N = N;
     const size_t bytes = (size_t)N * N * sizeof(cplx);
     int rc;
+    c->real_FS = false;
+    if (loc == GNB_HOST) {                // real F and S (restricted-spin Gaussian output): A = E S - F is real off the contacts
+        bool re = true;
+        for (size_t i = 0; i < (size_t)N * N && re; i++) re = (F[2 * i + 1] == 0.0) && (S[2 * i + 1] == 0.0);
+        c->real_FS = re;
+    }
     if ((rc = put(c, c->dF, F, bytes, loc))) return rc;
     if ((rc = put(c, c->dS, S, bytes, loc))) return rc;
     GNB_CK(cudaStreamSynchronize(c->stream));
@@ -305,6 +311,7 @@ struct Lay {
     int N, naug, Np, naugp, ld, xoff;
     bool rec, padded;
     int back_row_lo = 0;               // FORWARD: first solution row that is needed
+    int nreal = 0;                     // FORWARD: leading real columns (real F, S, E; contact orbitals last)
     size_t bytes_per_energy(bool jordan) const {
         size_t b = (size_t)Np * ld * 16 + 8 * (size_t)Np + 32768;
         if (rec) b += gnb_rec_pk_elems(Np) * 16 * (jordan ? 2 : 1) + gnb_rec_wk_elems(Np, ld) * 16 + (size_t)(Np / 32) * (16384 + 4 * GNB_MOVES_STRIDE);
@@ -371,6 +378,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
         GnbRecWork w = gnb_rec_work(c, M, L.Np, L.ld, jordan != 0, &rc);
         if (rc) return rc;
         w.back_row_lo = L.back_row_lo;
+        w.nreal = jordan ? 0 : L.nreal;
         if (c->timing) GNB_CK(cudaEventRecord(c->ev0, c->stream));
         // Independent sub-batches on separate streams: the latency-bound panel kernels of one sub-batch
         // overlap the tensor-pipe-bound rank-K updates of the others.
@@ -718,6 +726,11 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
             if ((rc = put(c, c->cols, pinv.data(), (size_t)N * sizeof(int), GNB_HOST))) return rc;
             d_pi = c->rows.as<int>(); d_pinv = c->cols.as<int>();
             L.back_row_lo = N - n1 - n2;
+            // real F, S, real energies, no dense Sigma0 and no third contact: every column left of the contact
+            // orbitals stays exactly real through the elimination -> the rank-K kernel skips the imaginary DMMAs
+            bool ereal = c->real_FS && !c->has_sig0 && c->contacts.size() == 2;
+            for (int k = 0; k < M && ereal; k++) ereal = (E[2 * (size_t)k + 1] == 0.0);
+            if (ereal) L.nreal = N - n1 - n2;
         }
     }
     const size_t per = L.bytes_per_energy(false) + 3 * (size_t)n1 * n2 * 16 + 16384 +

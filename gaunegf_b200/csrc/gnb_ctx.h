@@ -83,6 +83,7 @@ struct gnb_ctx {
     int N = 0;
     DevBuf dF, dS, dSig0;
     bool has_sig0 = false;
+    bool real_FS = false;          // F and S given with zero imaginary parts (host arrays only)
     std::vector<Contact> contacts;
     // workspaces
     DevBuf A, Pws, LU, moves, cand0, cand1, perm, invperm, info, dE, dW, G, Y, Z, Xr, out, dT, dDosT, dDosP,

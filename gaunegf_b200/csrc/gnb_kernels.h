@@ -75,6 +75,7 @@ struct GnbRecWork {
     cplx* Wpk; long strideWk;          // packed pivot rows [M][N/16][ld/32][16][RK_WPS]
     int* info;
     int back_row_lo;                   // FORWARD: only rows >= back_row_lo of the solution are needed
+    int nreal;                         // FORWARD: columns [0, nreal) of the matrices are real (0 = unknown / complex)
 };
 size_t gnb_rec_pk_elems(int N);               // cplx elements per matrix of Ppk / Lpk (incl. slack)
 size_t gnb_rec_wk_elems(int N, int ld);       // cplx elements per matrix of Wpk (incl. slack)

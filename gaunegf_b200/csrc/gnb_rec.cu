@@ -63,6 +63,8 @@ struct RkGemmArgs {
     const cplx* W; long sW; int ncb;
     int ilo, ihi, jlo, jhi, klo, khi;
     int kskip;
+    int preal;      // the panel operand P is real (imaginary parts exactly zero)
+    int nreal;      // columns [0, nreal) of C / W are real (real F, S, E with the contact orbitals ordered last)
 };
 
 #define RK_ST 4
@@ -136,12 +138,46 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
         int ch0 = 0;
         if (g.kskip && i0 >= g.klo && i0 + TM <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;
         const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);     // warp tile inside the range
+        const int mode = !g.preal ? 3 : (j0 + TN <= g.nreal ? 1 : 2);              // 1: real x real, 2: real x complex
         for (int ch = ch0; ch < nch_all; ch++, q++) {
             const int s = q % RK_ST;
             mbar_wait(&full[s], (q / RK_ST) & 1);
             if (active) {
                 const cplx* Ps = sm + s * RK_STAGE + (wm * 16 + gid) * RK_PPS + tig;
                 const cplx* Ws = sm + s * RK_STAGE + RK_PST + wn * RK_WBLK + tig * RK_WPS + gid;
+                if (mode == 1) {
+                    // real P, real W: one real DMMA per tile product, the imaginary part of C stays exactly zero
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        double af[MI], bf[NI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PPS + kk].x;
+#pragma unroll
+                        for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[kk * RK_WPS + ni * 8].x;
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi], bf[ni]);
+                    }
+                } else if (mode == 2) {
+                    // real P, complex W: re += ar br, im += ar bi
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        double af[MI];
+                        cplx bf[NI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PPS + kk].x;
+#pragma unroll
+                        for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[kk * RK_WPS + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) {
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi], bf[ni].x);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cim[mi][ni][0], cim[mi][ni][1], af[mi], bf[ni].y);
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int kk = 0; kk < KC; kk += 4) {
                     cplx af[MI], bf[NI];
@@ -180,6 +216,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
                         }
                     }
                 }
+                }
             }
             // generic-proxy reads of this stage are ordered before the producer's next async-proxy write
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -201,7 +238,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         double re, im;
-                        if (M3) { re = cre[mi][ni][e] - cim[mi][ni][e]; im = c3[mi][ni][e] - cre[mi][ni][e] - cim[mi][ni][e]; }
+                        if (M3 && mode == 3) { re = cre[mi][ni][e] - cim[mi][ni][e]; im = c3[mi][ni][e] - cre[mi][ni][e] - cim[mi][ni][e]; }
                         else { re = cre[mi][ni][e]; im = cim[mi][ni][e]; }
                         v[ni][e].x -= re; v[ni][e].y -= im;
                         cre[mi][ni][e] = 0.0; cim[mi][ni][e] = 0.0;
@@ -469,8 +506,10 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve(cplx* __restrict__ A, long
 #define WM_TC 32
 #define WM_AS 36
 #define WM_BS 34
+// mode 1: A and B real (one DMMA per tile product), 2: A real, B complex (two), 3: both complex (four)
 __device__ __forceinline__ void ws_mma_product(double (&cre)[2][2], double (&cim)[2][2], const cplx* __restrict__ sAm,
-                                               const cplx* __restrict__ sBk, int wm, int wn, int gid, int tig, bool neg) {
+                                               const cplx* __restrict__ sBk, int wm, int wn, int gid, int tig, bool neg,
+                                               int mode) {
 #pragma unroll
     for (int kk = 0; kk < GNB_NB; kk += 4) {
         cplx a[2];
@@ -481,9 +520,11 @@ __device__ __forceinline__ void ws_mma_product(double (&cre)[2][2], double (&cim
         for (int mi = 0; mi < 2; mi++) {
             const double ax = neg ? -a[mi].x : a[mi].x, ay = neg ? -a[mi].y : a[mi].y;
             dmma884(cre[mi][0], cre[mi][1], ax, bq.x);
-            dmma884(cim[mi][0], cim[mi][1], ax, bq.y);
-            dmma884(cre[mi][0], cre[mi][1], -ay, bq.y);
-            dmma884(cim[mi][0], cim[mi][1], ay, bq.x);
+            if (mode >= 2) dmma884(cim[mi][0], cim[mi][1], ax, bq.y);
+            if (mode == 3) {
+                dmma884(cre[mi][0], cre[mi][1], -ay, bq.y);
+                dmma884(cim[mi][0], cim[mi][1], ay, bq.x);
+            }
         }
     }
 }
@@ -492,7 +533,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
                                                           int jlo, int jhi, int tiles_per_cta,
                                                           const cplx* __restrict__ inv_a, const cplx* __restrict__ inv_b,
                                                           const cplx* __restrict__ Lsrc, long stridePk, int nrb,
-                                                          cplx* __restrict__ Wpk, long strideWk, int ncb) {
+                                                          cplx* __restrict__ Wpk, long strideWk, int ncb, int nreal) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);            // [3][32][WM_AS]: inv_a, L_ba, inv_b
     cplx* sB = sA + 3 * GNB_NB * WM_AS;                      // [64][WM_BS]: R_a / W_a rows, then R_b rows
@@ -520,12 +561,14 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
         }
         __syncthreads();
         double cre[2][2], cim[2][2];
+        // pivot blocks left of nreal are real; so are the columns left of nreal (see RkGemmArgs::nreal)
+        const int mode = (c0 + nrows <= nreal) ? (cs + WM_TC <= nreal ? 1 : 2) : 3;
         const int col = cs + wn * 8 + tig * 2;                // this thread's two adjacent output columns
         cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
         // ---- W_a = inv_a R_a
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
-        ws_mma_product(cre, cim, sA, sB, wm, wn, gid, tig, false);
+        ws_mma_product(cre, cim, sA, sB, wm, wn, gid, tig, false, mode);
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
             const int k = c0 + wm * 16 + mi * 8 + gid;
@@ -546,7 +589,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
             }
             __syncthreads();
             // ---- R_b -= L_ba W_a
-            ws_mma_product(cre, cim, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, true);
+            ws_mma_product(cre, cim, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, true, mode);
             // R_b of this warp's rows x columns is read only through B fragments of the next product
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
@@ -558,7 +601,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
             // ---- W_b = inv_b R_b
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
-            ws_mma_product(cre, cim, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WM_BS, wm, wn, gid, tig, false);
+            ws_mma_product(cre, cim, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WM_BS, wm, wn, gid, tig, false, mode);
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
                 const int k = c0 + GNB_NB + wm * 16 + mi * 8 + gid;
@@ -580,6 +623,7 @@ size_t gnb_rec_wk_elems(int N, int ld) { return (size_t)(N / 16) * (ld / 32) * R
 static int g_rk_m3 = 1;          // 3M complex arithmetic in the rank-K update (3 real DMMAs per complex tile product)
 static int g_rk_m3_mink = 64;    // ... for K >= this
 static int g_rk_kskip = 1;
+static int g_rk_real = 1;        // skip the imaginary DMMAs where the operands are known to be real
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
@@ -606,6 +650,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_m3_mink")) g_rk_m3_mink = value;
     else if (!strcmp(name, "rk_kskip")) g_rk_kskip = value;
     else if (!strcmp(name, "rk_strip")) g_rk_strip = value;
+    else if (!strcmp(name, "rk_real")) g_rk_real = value;
     else if (!strcmp(name, "rk_wsolve_mma")) g_rk_wsolve_mma = value;
 }
 
@@ -670,15 +715,22 @@ struct Rec {
         g.W = ws.Wpk; g.sW = ws.strideWk; g.ncb = ncb;
         g.ilo = ilo; g.ihi = ihi; g.jlo = jlo; g.jhi = jhi; g.klo = klo; g.khi = khi;
         g.kskip = (kskip && g_rk_kskip) ? 1 : 0;
+        g.nreal = g_rk_real ? ws.nreal : 0;
+        g.preal = (g.nreal > 0 && khi <= g.nreal) ? 1 : 0;
         const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);     // 128 x 32 tiles for 32-column strips
         const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
         const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
         const long total = (long)M * nti * ntj;
         const int grid = (int)std::min<long>(total, (long)g_rk_sms);
-        double flops = 8.0 * (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M;
+        // executed arithmetic in 4-multiplication-equivalent real flops: 8 per complex MAC, 4 where P is real and W
+        // complex, 2 where both are real (tiles entirely left of nreal)
+        int ncol1 = 0;
+        if (g.preal) ncol1 = std::max(0, (std::min(jhi, g.nreal) - jlo) / tn * tn);
+        const double colw = 2.0 * ncol1 + (g.preal ? 4.0 : 8.0) * (double)(jhi - jlo - ncol1);
+        double flops = (double)(ihi - ilo) * colw * (double)(khi - klo) * M;
         if (g.kskip)            // rows inside [klo, khi) only meet the strictly block-upper part of the panel
             for (int i0 = ilo; i0 < ihi; i0 += tm)
-                if (i0 >= klo && i0 + tm <= khi) flops -= 8.0 * tm * (double)(jhi - jlo) * (double)(i0 + 32 - klo) * M;
+                if (i0 >= klo && i0 + tm <= khi) flops -= tm * colw * (double)(i0 + 32 - klo) * M;
         TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
         if (ws.timer) ws.timer->begin(st);
         const bool m3 = g_rk_m3 && khi - klo >= g_rk_m3_mink;
@@ -732,7 +784,7 @@ struct Rec {
                 dim3 grid(cdiv_i(ntile, per), M);
                 k_rk_wsolve_mma<<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
                                                             nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
-                                                            ws.Wpk, ws.strideWk, ncb);
+                                                            ws.Wpk, ws.strideWk, ncb, g_rk_real ? ws.nreal : 0);
             } else {
                 const int ntile = cdiv_i(jhi - jlo, WS_TC);
                 const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix

@@ -269,3 +269,31 @@ def test_full_size_properties_n1024(ctx):
         Tfull = np.trace(g1 @ G[k] @ g2 @ G[k].conj().T).real
         assert abs(Tfull - T12[k]) < 1e-9 * max(1.0, abs(Tfull))
     assert relerr(G[0], np.linalg.inv(E[0] * S - F - sig)) < TOL
+
+
+def test_real_structure_shortcut_matches_complex_path(ctx):
+    """real F, S and real energies: with the contact orbitals ordered last every column left of them stays exactly
+    real, and the rank-K / forward-W kernels skip the imaginary DMMAs there (rk_real).  Same results as the full
+    complex arithmetic, and as a system whose F carries an imaginary part that disables the shortcut."""
+    N, nc = 352, 40
+    F, S, inds, sig = const_system(ctx, N, nc, seed=11)
+    Er = np.linspace(-0.9, 0.9, 33)
+    st = sig[0] + sig[1]
+    g1 = 1j * (sig[0] - sig[0].conj().T)
+    g2 = 1j * (sig[1] - sig[1].conj().T)
+    try:
+        T1 = ctx.transmission(Er, 0, -1)
+        _set(ctx, rk_real=0)
+        T0 = ctx.transmission(Er, 0, -1)
+    finally:
+        _set(ctx, **DEFAULTS, rk_real=1)
+    assert relerr(T1, T0) < TOL
+    Tref = np.array([O.transmission_restricted(e, F, S, st, g1, g2) for e in Er[::4]])
+    assert np.allclose(T1[::4], Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
+    # complex energies must not take the shortcut (A is complex everywhere) -- compared through GrLessInt-free T path
+    Fc, Sc, indsc, sigc = const_system(ctx, N, nc, seed=11, complex_F=True)
+    Tc = ctx.transmission(Er[:5], 0, -1)
+    stc = sigc[0] + sigc[1]
+    Tcref = np.array([O.transmission_restricted(e, Fc, Sc, stc, 1j * (sigc[0] - sigc[0].conj().T),
+                                                1j * (sigc[1] - sigc[1].conj().T)) for e in Er[:5]])
+    assert np.allclose(Tc, Tcref, rtol=1e-9, atol=1e-12 * np.abs(Tcref).max())
