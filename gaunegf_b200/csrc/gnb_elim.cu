@@ -132,6 +132,29 @@ template <> struct TT<float> {
     }
 };
 
+// Real panels (real F, S, E; columns left of the contact orbitals): the same tournament on the real parts only.
+template <typename R> struct TTR;
+template <> struct TTR<double> {
+    typedef double C;
+    static __device__ __forceinline__ C ld(cplx v) { return v.x; }
+    static __device__ __forceinline__ C zero() { return 0.0; }
+    static __device__ __forceinline__ C mul(C a, C b) { return a * b; }
+    static __device__ __forceinline__ C fnma(C a, C b, C c) { return fma(-b, c, a); }
+    static __device__ __forceinline__ C rcp(C p) { return 1.0 / p; }
+    static __device__ __forceinline__ unsigned long long key(C v) {
+        return (unsigned long long)__double_as_longlong(fabs(v)) + 1ull;
+    }
+};
+template <> struct TTR<float> {
+    typedef float C;
+    static __device__ __forceinline__ C ld(cplx v) { return (float)v.x; }
+    static __device__ __forceinline__ C zero() { return 0.f; }
+    static __device__ __forceinline__ C mul(C a, C b) { return a * b; }
+    static __device__ __forceinline__ C fnma(C a, C b, C c) { return fmaf(-b, c, a); }
+    static __device__ __forceinline__ C rcp(C p) { return 1.0f / p; }
+    static __device__ __forceinline__ unsigned long long key(C v) { return (unsigned long long)__float_as_uint(fabsf(v)) + 1ull; }
+};
+
 // Thread tiling: GROUP rows x 32 columns as 4-row x 8-column register tiles; warp w owns column group w
 // (columns 8w .. 8w+7) of all rows, lane l owns rows 4l .. 4l+3.  The warp that owns the pivot column finds
 // the pivot with REDUX operations (no cross-warp reduction), publishes the column (for the multipliers)
@@ -139,14 +162,14 @@ template <> struct TT<float> {
 // One CTA barrier per pivot step; the owning warp searches the NEXT pivot (look-ahead) before it finishes its
 // own update.  Inside the owning warp the tile is rotated by one column per step so that the pivot column is
 // always local column 0 (static register indices, small code).
-template <int GROUP, typename R>
-__global__ void __launch_bounds__(GROUP, sizeof(R) == 4 ? 5 : 3)
+template <int GROUP, typename T, bool F64, int MINB>
+__global__ void __launch_bounds__(GROUP, MINB)
 k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0, int n_in,
         const int* __restrict__ cand_in, int cand_in_stride, int* __restrict__ cand_out, int cand_out_stride,
         int final_round, cplx* __restrict__ LU, int* __restrict__ moves, int* __restrict__ perm, int perm_stride,
         int* __restrict__ info) {
     static_assert(GROUP == 128, "tile mapping: 4 warps = 4 column groups, 32 lanes x 4 rows");
-    typedef typename TT<R>::C C;
+    typedef typename T::C C;
     const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
     const int lane = t & 31, tc = t >> 5;                  // tc = column group of this warp
     int rows[4];
@@ -159,7 +182,7 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
         rows[rr] = valid ? (cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i) : -1;
         const cplx* src = Ab + (long)(valid ? rows[rr] : 0) * ld + c0 + 8 * tc;
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? TT<R>::ld(src[k]) : TT<R>::zero();
+        for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? T::ld(src[k]) : T::zero();
     }
     const int ngroup = min(GROUP, n_in - g * GROUP);
     const int nsel = min(w, ngroup);
@@ -169,7 +192,7 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
     __shared__ int s_wnz[2];                                // winner magnitude: -1 none, 0 exactly zero, 1 positive
     __shared__ __align__(16) C s_prow[4][8];                // per warp: its 8 elements of the pivot row
     __shared__ int s_win[GNB_NB];
-    __shared__ __align__(16) cplx s_B[sizeof(R) == 8 ? GNB_NB : 1][GNB_NB + 1];  // final round: pivot block -> inverse
+    __shared__ __align__(16) cplx s_B[F64 ? GNB_NB : 1][GNB_NB + 1];  // final round: pivot block -> inverse
     unsigned alive = 0;                                     // bit rr: row 4*lane + rr still a candidate
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) alive |= (rows[rr] >= 0 ? 1u : 0u) << rr;
@@ -182,11 +205,11 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             s_col[nb_][rr * 32 + lane] = a[rr][0];
-            const unsigned long long kq = ((alive >> rr) & 1u) ? TT<R>::key(a[rr][0]) : 0ull;
+            const unsigned long long kq = ((alive >> rr) & 1u) ? T::key(a[rr][0]) : 0ull;
             if (kq > key) { key = kq; krr = rr; }            // first maximum wins (izamax)
         }
         unsigned bal;
-        if (sizeof(R) == 4) {
+        if (!F64) {
             const unsigned k32 = (unsigned)key;
             const unsigned kmax = __reduce_max_sync(0xffffffffu, k32);
             bal = __ballot_sync(0xffffffffu, k32 == kmax);
@@ -198,7 +221,7 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
         }
         if (lane == __ffs(bal) - 1) {
             s_widx[nb_] = krr * 32 + lane;
-            s_wnz[nb_] = key == 0ull ? -1 : (key == TT<R>::key(TT<R>::zero()) ? 0 : 1);
+            s_wnz[nb_] = key == 0ull ? -1 : (key == T::key(T::zero()) ? 0 : 1);
             s_win[jn] = krr == 0 ? rows[0] : krr == 1 ? rows[1] : krr == 2 ? rows[2] : rows[3];
         }
     };
@@ -228,10 +251,10 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
         if (tc < jc) continue;                                // all columns of this warp are eliminated (warp-uniform)
         __syncwarp();
         // LAPACK zgetf2 scales the column by the reciprocal of the pivot
-        const C rinv = (nz > 0) ? TT<R>::rcp(s_col[buf][wi]) : TT<R>::zero();
+        const C rinv = (nz > 0) ? T::rcp(s_col[buf][wi]) : T::zero();
         C l[4];
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) l[rr] = TT<R>::mul(s_col[buf][rr * 32 + lane], rinv);
+        for (int rr = 0; rr < 4; rr++) l[rr] = T::mul(s_col[buf][rr * 32 + lane], rinv);
         // look-ahead: the warp that owns the next pivot column updates that column first, searches the next
         // pivot and publishes it, and only then finishes its update -- the search overlaps the other warps' work
         const bool next_owner = (j + 1 < nsel) && (tc == ((j + 1) >> 3));
@@ -239,35 +262,35 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
             {
                 const C p = s_prow[tc][1];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][0] = TT<R>::fnma(a[rr][1], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][0] = T::fnma(a[rr][1], l[rr], p);
             }
             if (next_owner) search(j + 1);
 #pragma unroll
             for (int k = 1; k < 7; k++) {
                 const C p = s_prow[tc][k + 1];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][k] = TT<R>::fnma(a[rr][k + 1], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][k] = T::fnma(a[rr][k + 1], l[rr], p);
             }
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) a[rr][7] = TT<R>::zero();
+            for (int rr = 0; rr < 4; rr++) a[rr][7] = T::zero();
         } else {
             {
                 const C p = s_prow[tc][0];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][0] = TT<R>::fnma(a[rr][0], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][0] = T::fnma(a[rr][0], l[rr], p);
             }
             if (next_owner) search(j + 1);
 #pragma unroll
             for (int k = 1; k < 8; k++) {
                 const C p = s_prow[tc][k];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) a[rr][k] = TT<R>::fnma(a[rr][k], l[rr], p);
+                for (int rr = 0; rr < 4; rr++) a[rr][k] = T::fnma(a[rr][k], l[rr], p);
             }
         }
         __syncwarp();                                         // s_prow[tc] is rewritten in the next step
     }
     __syncthreads();
-    if (!final_round || sizeof(R) == 4) {
+    if (!final_round || !F64) {
         if (t < nsel) cand_out[(long)b * cand_out_stride + g * w + t] = s_win[t];
         return;
     }
@@ -846,7 +869,7 @@ void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
-                           int* info) {
+                           int* info, int real_panel) {
     int n = N - c0;
     const int* cin = nullptr;
     int* cout = cand0;
@@ -856,12 +879,17 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         const int groups = cdiv_i(n, G);
         const int fin = groups == 1;
         dim3 grid(groups, M);
-        if (!fin && g_tourn_fp32)
-            k_tourn<128, float><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, 0, LU,
-                                                      moves, perm, perm_stride, info);
-        else
-            k_tourn<128, double><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, fin,
-                                                       LU, moves, perm, perm_stride, info);
+#define GNB_TOURN(T_, F64_, MINB_, FIN_)                                                                             \
+    k_tourn<128, T_, F64_, MINB_><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, \
+                                                        FIN_, LU, moves, perm, perm_stride, info)
+        if (!fin && g_tourn_fp32) {
+            if (real_panel) GNB_TOURN(TTR<float>, false, 8, 0);
+            else GNB_TOURN(TT<float>, false, 5, 0);
+        } else {
+            if (real_panel) GNB_TOURN(TTR<double>, true, 5, fin);
+            else GNB_TOURN(TT<double>, true, 3, fin);
+        }
+#undef GNB_TOURN
         launches++;
         if (fin) break;
         n = (groups - 1) * w + min(w, n - (groups - 1) * G);
@@ -884,7 +912,7 @@ void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N) 
 // kernel (tools/proto_blockgj.py: two_level_jordan / two_level_forward are the numpy models).
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
-                           int* info);
+                           int* info, int real_panel);
 static int g_two_level = 1;
 void gnb_set_two_level(int on) { g_two_level = on; }
 
@@ -898,7 +926,7 @@ struct Elim {
 
     void tournament(int c0, int w, int slot) {
         launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, w, ws.cand0, ws.cand1, ws.cand_stride, lu(slot),
-                                          mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+                                          mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info, 0);
     }
     void permute_solve(cplx* buf, long stride, int bld, int c0, int w, int lo, int hi, int slot, int mode,
                        const cplx* preL = nullptr, long strideL = 0, int ldL = 0, int pre_row = 0, int pre_k = 0) {

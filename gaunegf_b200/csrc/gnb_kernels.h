@@ -56,7 +56,7 @@ long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long stride
 
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
-                           int* info);
+                           int* info, int real_panel = 0);
 void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N);
 
 // gnb_rec.cu : recursive (multi-level) elimination on a padded layout; the rank-K updates run on the

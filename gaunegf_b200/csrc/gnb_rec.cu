@@ -749,7 +749,8 @@ struct Rec {
         {
             TraceScope ts("tourn", st, M);
             launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
-                                              inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info);
+                                              inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info,
+                                              (g_rk_real && c0 + GNB_NB <= ws.nreal) ? 1 : 0);
         }
         TraceScope ts2("panel", st, M);
         if (live_lo < c0) {
