@@ -798,11 +798,35 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         nmax = std::max(nmax, c->contacts[ci].nc);
     }
     const int naug = (int)cols.size();
-    const Lay L = make_layout(N, naug);
+    Lay L = make_layout(N, naug);
     const int ld = L.ld, Np = L.Np;
     if ((rc = put(c, c->cols, cols.data(), cols.size() * sizeof(int), GNB_HOST))) return rc;
+    // All-contacts-last ordering (as in gnb_transmission): with real F, S and real energies every column left of
+    // the contact orbitals stays real through the elimination.  The result is formed in the permuted order and
+    // un-permuted once at the end.
+    const int *d_pi = nullptr, *d_pinv = nullptr;
+    if (L.rec && g_contacts_last && c->real_FS && !c->has_sig0) {
+        bool ereal = true;
+        for (int k = 0; k < M && ereal; k++) ereal = (E[2 * (size_t)k + 1] == 0.0);
+        std::vector<int> mark(N, 0), pi, pinv(N);
+        int ncall = 0;
+        for (auto& ct : c->contacts)
+            for (int i : ct.h_inds) { if (mark[i]) ereal = false; mark[i] = 1; ncall++; }
+        if (ereal && ncall < N) {
+            pi.reserve(N);
+            for (int i = 0; i < N; i++) if (!mark[i]) pi.push_back(i);
+            for (auto& ct : c->contacts) pi.insert(pi.end(), ct.h_inds.begin(), ct.h_inds.end());
+            for (int i = 0; i < N; i++) pinv[pi[i]] = i;
+            if ((rc = put(c, c->rows, pi.data(), (size_t)N * sizeof(int), GNB_HOST))) return rc;
+            if ((rc = put(c, c->in_stage, pinv.data(), (size_t)N * sizeof(int), GNB_HOST))) return rc;
+            d_pi = c->rows.as<int>(); d_pinv = c->in_stage.as<int>();
+            L.nreal = N - ncall;
+        }
+    }
     cplx* d_out = nullptr;
     if ((rc = get_out(c, out, loc, &d_out))) return rc;
+    cplx* d_acc = d_out;                         // accumulation target (permuted order when d_pi is set)
+    if (d_pi) { GNB_CK(c->Z.ensure((size_t)N * N * sizeof(cplx))); d_acc = c->Z.as<cplx>(); }
     if (M == 0) GNB_CK(cudaMemsetAsync(d_out, 0, (size_t)N * N * sizeof(cplx), c->stream));
     const size_t per = L.bytes_per_energy(false) + (size_t)N * nmax * 16 + 16384 + 8 * (size_t)naug * nmax * 16;
     const int Mc = chunk_size(c, std::max(M, 1), per);
@@ -816,8 +840,8 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         const long strideA = (long)Np * ld;
         if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
         if ((rc = pad_chunk(c, m, L, A))) return rc;
-        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr))) return rc;
-        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, c->cols.as<int>(), naug);
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr, d_pi, d_pinv))) return rc;
+        gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, c->cols.as<int>(), naug, d_pinv);
         c->launches++;
         if ((rc = run_eliminate(c, m, L, A, 0))) return rc;
         GNB_CK(c->Y.ensure((size_t)m * N * nmax * sizeof(cplx)));
@@ -832,7 +856,7 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
             g.P = X; g.strideP = strideA; g.ldp = ld;
             g.W = ct.gam_ptr; g.strideW = ct.gam_stride; g.ldw = nc;
             gnb_launch_gemm(c->stream, g, m, false, false);
-            g.C = d_out; g.strideC = 0; g.ldc = N;                          // out += sum_b w_b Y_b G[:,C]^H
+            g.C = d_acc; g.strideC = 0; g.ldc = N;                          // out += sum_b w_b Y_b G[:,C]^H
             g.jhi = N;
             g.P = c->Y.as<cplx>(); g.strideP = (long)N * nc; g.ldp = nc;
             g.W = X; g.strideW = strideA; g.ldw = ld;
@@ -843,6 +867,10 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         }
         GNB_CK(cudaGetLastError());
         if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));
+    }
+    if (d_pi && M > 0) {                          // out[pi[i]][pi[j]] = acc[i][j]
+        gnb_launch_unpermute_sym(c->stream, N, d_acc, d_pi, d_out);
+        c->launches++;
     }
     if (loc == GNB_HOST)
         GNB_CK(cudaMemcpyAsync(out, d_out, (size_t)N * N * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));

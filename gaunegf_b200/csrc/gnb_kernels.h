@@ -96,6 +96,7 @@ void gnb_launch_gather_rows(cudaStream_t st, int M, const cplx* X, long strideX,
                             int nr, int ncols, cplx* out, long strideOut, const int* map = nullptr);
 void gnb_launch_trace_dot(cudaStream_t st, int M, const cplx* Z, const cplx* X, long stride, int n, double* T);
 void gnb_launch_gamma_from_sigma(cudaStream_t st, int M, const cplx* sig, long stride, int n, cplx* gam);
+void gnb_launch_unpermute_sym(cudaStream_t st, int N, const cplx* in, const int* pi, cplx* out);
 void gnb_launch_scale_cols(cudaStream_t st, int M, cplx* X, long stride, int n, const cplx* w);
 void gnb_launch_trace_dot_strided(cudaStream_t st, int M, const cplx* Z, long strideZ, int ldz, const cplx* X,
                                   long strideX, int ldx, int nr, int ncols, double* T, int tstride, int toff);

@@ -168,3 +168,16 @@ void gnb_launch_trace_dot_strided(cudaStream_t st, int M, const cplx* Z, long st
     if (M <= 0) return;
     k_trace_dot_strided<<<M, 256, 0, st>>>(Z, strideZ, ldz, X, strideX, ldx, nr, ncols, T, tstride, toff);
 }
+
+// out[pi[i]][pi[j]] = in[i][j]  (undo the symmetric contacts-last reordering of a result matrix)
+__global__ void __launch_bounds__(256) k_unpermute_sym(int N, const cplx* __restrict__ in, const int* __restrict__ pi,
+                                                       cplx* __restrict__ out) {
+    const long total = (long)N * N;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / N), j = (int)(idx - (long)i * N);
+        out[(long)pi[i] * N + pi[j]] = in[idx];
+    }
+}
+void gnb_launch_unpermute_sym(cudaStream_t st, int N, const cplx* in, const int* pi, cplx* out) {
+    k_unpermute_sym<<<min(cdiv_i((long)N * N, 256), 4096), 256, 0, st>>>(N, in, pi, out);
+}
