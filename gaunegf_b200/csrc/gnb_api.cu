@@ -22,6 +22,7 @@ int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
+static int g_mixed_layout = 1;    // transmission: store the real columns as doubles (mixed layout, gnb_rec.cu)
 static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
 static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
 
@@ -100,6 +101,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
+    else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
     else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
     else return GNB_ERR_ARG;
@@ -312,9 +314,17 @@ struct Lay {
     bool rec, padded;
     int back_row_lo = 0;               // FORWARD: first solution row that is needed
     int nreal = 0;                     // FORWARD: leading real columns (real F, S, E; contact orbitals last)
+    int mixr = 0;                      // mixed layout: the first mixr (== nreal) columns are stored as real doubles
+    int ldl() const { return Np + naugp; }        // logical number of columns
+    void use_mixed_layout() {          // storage row stride in complex units: mixr/2 for the real part + the complex rest
+        mixr = nreal / 32 * 32; nreal = mixr;
+        ld = mixr / 2 + (ldl() - mixr);
+    }
+    // logical complex base of a chunk stored at `base` (see gnb_rec.cu: A[row * ld + col] valid for col >= mixr)
+    cplx* logical(void* base) const { return reinterpret_cast<cplx*>(reinterpret_cast<char*>(base) - (size_t)mixr * 8); }
     size_t bytes_per_energy(bool jordan) const {
         size_t b = (size_t)Np * ld * 16 + 8 * (size_t)Np + 32768;
-        if (rec) b += gnb_rec_pk_elems(Np) * 16 * (jordan ? 2 : 1) + gnb_rec_wk_elems(Np, ld) * 16 + (size_t)(Np / 32) * (16384 + 4 * GNB_MOVES_STRIDE);
+        if (rec) b += gnb_rec_pk_elems(Np) * 16 * (jordan ? 2 : 1) + gnb_rec_wk_elems(Np, ldl()) * 16 + (size_t)(Np / 32) * (16384 + 4 * GNB_MOVES_STRIDE);
         else if (jordan) b += (size_t)N * 2 * GNB_NB * 16;
         return b;
     }
@@ -366,7 +376,7 @@ GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc)
 // padded rows/columns of a chunk: everything zero, identity on the padded diagonal (call BEFORE assembly)
 static int pad_chunk(gnb_ctx* c, int M, const Lay& L, cplx* A) {
     if (!L.padded) return GNB_OK;
-    GNB_CK(cudaMemsetAsync(A, 0, (size_t)M * L.Np * L.ld * sizeof(cplx), c->stream));
+    GNB_CK(cudaMemsetAsync(reinterpret_cast<char*>(A) + (size_t)L.mixr * 8, 0, (size_t)M * L.Np * L.ld * sizeof(cplx), c->stream));
     if (L.Np != L.N) { gnb_launch_pad_diag(c->stream, M, A, (long)L.Np * L.ld, L.ld, L.N, L.Np); c->launches++; }
     return GNB_OK;
 }
@@ -375,10 +385,11 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
     int rc;
     const long strideA = (long)L.Np * L.ld;
     if (L.rec) {
-        GnbRecWork w = gnb_rec_work(c, M, L.Np, L.ld, jordan != 0, &rc);
+        GnbRecWork w = gnb_rec_work(c, M, L.Np, L.ldl(), jordan != 0, &rc);
         if (rc) return rc;
         w.back_row_lo = L.back_row_lo;
         w.nreal = jordan ? 0 : L.nreal;
+        w.mixr = jordan ? 0 : L.mixr;
         if (c->timing) GNB_CK(cudaEventRecord(c->ev0, c->stream));
         // Independent sub-batches on separate streams: the latency-bound panel kernels of one sub-batch
         // overlap the tensor-pipe-bound rank-K updates of the others.
@@ -455,11 +466,11 @@ static int prepare_sigma(gnb_ctx* c, int M, const cplx* dE, int want_gamma) {
 // from caller-provided dense matrices.
 static int assemble_chunk(gnb_ctx* c, int M, const cplx* dE, cplx* A, long strideA, int ld, bool use_desc,
                           const cplx* sig_const, const cplx* sig_batch, const int* d_pi = nullptr,
-                          const int* d_pinv = nullptr) {
+                          const int* d_pinv = nullptr, int mixr = 0) {
     const int N = c->N;
     const cplx* s0 = use_desc ? (c->has_sig0 ? c->dSig0.as<cplx>() : nullptr) : sig_const;
     gnb_launch_assemble(c->stream, M, A, strideA, ld, N, c->dF.as<cplx>(), c->dS.as<cplx>(), s0, sig_batch,
-                        (long)N * N, dE, d_pi);
+                        (long)N * N, dE, d_pi, mixr);
     c->launches++;
     if (use_desc)
         for (auto& ct : c->contacts) {
@@ -706,7 +717,7 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
     const int N = c->N;
     const int n1 = c->contacts[ca].nc, n2 = c->contacts[cb].nc;
     Lay L = make_layout(N, n2);
-    const int ld = L.ld, Np = L.Np;
+    const int Np = L.Np;
     // Contacts-last ordering: with the orbitals of the two contacts moved to the end (symmetric permutation
     // applied at assembly), G[C1, C2] only needs the last n1 + n2 rows of the solution, so the
     // back-substitution stops there.  Needs disjoint contacts; otherwise the natural order is kept.
@@ -728,11 +739,15 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
             L.back_row_lo = N - n1 - n2;
             // real F, S, real energies, no dense Sigma0 and no third contact: every column left of the contact
             // orbitals stays exactly real through the elimination -> the rank-K kernel skips the imaginary DMMAs
-            bool ereal = c->real_FS && !c->has_sig0 && c->contacts.size() == 2;
+            bool ereal = gnb_rec_real_enabled() && c->real_FS && !c->has_sig0 && c->contacts.size() == 2;
             for (int k = 0; k < M && ereal; k++) ereal = (E[2 * (size_t)k + 1] == 0.0);
-            if (ereal) L.nreal = N - n1 - n2;
+            if (ereal) {
+                L.nreal = N - n1 - n2;
+                if (g_mixed_layout && L.nreal >= 64) L.use_mixed_layout();   // real columns stored as doubles
+            }
         }
     }
+    const int ld = L.ld;
     const size_t per = L.bytes_per_energy(false) + 3 * (size_t)n1 * n2 * 16 + 16384 +
                        2 * ((size_t)n1 * n1 + (size_t)n2 * n2) * 16 * 4;
     const int Mc = chunk_size(c, std::max(M, 1), per);
@@ -741,13 +756,13 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
         if ((rc = put_chunk_scalars(c, E, nullptr, k0, m))) return rc;
         const cplx* dE = c->dE.as<cplx>();
         GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
-        cplx* A = c->A.as<cplx>();
+        cplx* A = L.logical(c->A.p);
         const long strideA = (long)Np * ld;
         if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
         Contact& A1 = c->contacts[ca];
         Contact& A2 = c->contacts[cb];
         if ((rc = pad_chunk(c, m, L, A))) return rc;
-        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr, d_pi, d_pinv))) return rc;
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr, d_pi, d_pinv, L.mixr))) return rc;
         gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, A2.d_inds.as<int>(), n2, d_pinv);
         c->launches++;
         if ((rc = run_eliminate(c, m, L, A, 0))) return rc;
@@ -805,7 +820,7 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
     // the contact orbitals stays real through the elimination.  The result is formed in the permuted order and
     // un-permuted once at the end.
     const int *d_pi = nullptr, *d_pinv = nullptr;
-    if (L.rec && g_contacts_last && c->real_FS && !c->has_sig0) {
+    if (L.rec && g_contacts_last && gnb_rec_real_enabled() && c->real_FS && !c->has_sig0) {
         bool ereal = true;
         for (int k = 0; k < M && ereal; k++) ereal = (E[2 * (size_t)k + 1] == 0.0);
         std::vector<int> mark(N, 0), pi, pinv(N);

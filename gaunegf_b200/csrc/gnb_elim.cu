@@ -18,14 +18,25 @@
 // Assembly  A_k = E_k * S - F - Sigma0 - SigmaB_k   (integrate.py:70,77; transport.py:153,186)
 // HBM-bound: 16 N^2 B written per energy, F/S/Sigma0 stay L2-resident.
 // ------------------------------------------------------------------------------------------
+// mixr > 0 (mixed layout of the transmission path): the first mixr columns of every row are stored as real
+// doubles, the rest as complex128; A is the LOGICAL complex base (A[row * ld + col] is valid for col >= mixr),
+// the real view starts mixr * 8 bytes later with a row stride of 2 * ld doubles (see gnb_rec.cu).
+__device__ __forceinline__ double* gnb_real_view(cplx* A, int mixr) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(A) + (size_t)mixr * 8);
+}
+__device__ __forceinline__ const double* gnb_real_view(const cplx* A, int mixr) {
+    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(A) + (size_t)mixr * 8);
+}
+
 __global__ void __launch_bounds__(256) k_assemble(cplx* __restrict__ A, long strideA, int ld, int N,
                                                   const cplx* __restrict__ F, const cplx* __restrict__ S,
                                                   const cplx* __restrict__ Sig0,
                                                   const cplx* __restrict__ SigB, long strideSigB,
-                                                  const cplx* __restrict__ E, const int* __restrict__ pi) {
+                                                  const cplx* __restrict__ E, const int* __restrict__ pi, int mixr) {
     const int b = blockIdx.y;
     const cplx e = E[b];
     cplx* Ab = A + (long)b * strideA;
+    double* Ar = gnb_real_view(A, mixr) + (long)b * 2 * strideA;
     const long total = (long)N * N;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int i = (int)(idx / N), j = (int)(idx - (long)i * N);
@@ -33,7 +44,8 @@ __global__ void __launch_bounds__(256) k_assemble(cplx* __restrict__ A, long str
         cplx v = csub(cmul(e, S[src]), F[src]);
         if (Sig0) v = csub(v, Sig0[src]);
         if (SigB) v = csub(v, SigB[(long)b * strideSigB + src]);
-        Ab[(long)i * ld + j] = v;
+        if (j < mixr) Ar[(long)i * 2 * ld + j] = v.x;
+        else Ab[(long)i * ld + j] = v;
     }
 }
 
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(GROUP, MINB)
 k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0, int n_in,
         const int* __restrict__ cand_in, int cand_in_stride, int* __restrict__ cand_out, int cand_out_stride,
         int final_round, cplx* __restrict__ LU, int* __restrict__ moves, int* __restrict__ perm, int perm_stride,
-        int* __restrict__ info) {
+        int* __restrict__ info, int mixr) {
     static_assert(GROUP == 128, "tile mapping: 4 warps = 4 column groups, 32 lanes x 4 rows");
     typedef typename T::C C;
     const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
@@ -180,9 +192,15 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
         const int i = g * GROUP + 4 * lane + rr;
         const bool valid = i < n_in;
         rows[rr] = valid ? (cand_in ? cand_in[(long)b * cand_in_stride + i] : r0 + i) : -1;
-        const cplx* src = Ab + (long)(valid ? rows[rr] : 0) * ld + c0 + 8 * tc;
+        if (c0 < mixr) {                                     // panel stored as real doubles (mixed layout)
+            const double* srcr = gnb_real_view(Ab, mixr) + (long)(valid ? rows[rr] : 0) * 2 * ld + c0 + 8 * tc;
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? T::ld(src[k]) : T::zero();
+            for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? T::ld(cmake(srcr[k], 0.0)) : T::zero();
+        } else {
+            const cplx* src = Ab + (long)(valid ? rows[rr] : 0) * ld + c0 + 8 * tc;
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[rr][k] = (valid && 8 * tc + k < w) ? T::ld(src[k]) : T::zero();
+        }
     }
     const int ngroup = min(GROUP, n_in - g * GROUP);
     const int nsel = min(w, ngroup);
@@ -301,7 +319,9 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
         for (int e = t; e < GNB_NB * GNB_NB; e += GROUP) {
             const int r = e >> 5, c = e & 31;
             cplx v = cmake(r == c ? 1.0 : 0.0, 0.0);
-            if (r < w && c < w) v = Ab[(long)s_win[r] * ld + c0 + c];
+            if (r < w && c < w)
+                v = (c0 < mixr) ? cmake(gnb_real_view(Ab, mixr)[(long)s_win[r] * 2 * ld + c0 + c], 0.0)
+                                : Ab[(long)s_win[r] * ld + c0 + c];
             s_B[r][c] = v;
         }
         constexpr int PER = GNB_NB * GNB_NB / GROUP;
@@ -816,10 +836,10 @@ cudaError_t gnb_kernels_init() {
 
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E,
-                         const int* pi) {
+                         const int* pi, int mixr) {
     if (M <= 0) return;
     dim3 grid(min(cdiv_i((long)N * N, 256 * 4), 4096), M);
-    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E, pi);
+    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E, pi, mixr);
 }
 
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,
@@ -869,7 +889,7 @@ void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
-                           int* info, int real_panel) {
+                           int* info, int real_panel, int mixr) {
     int n = N - c0;
     const int* cin = nullptr;
     int* cout = cand0;
@@ -881,7 +901,7 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         dim3 grid(groups, M);
 #define GNB_TOURN(T_, F64_, MINB_, FIN_)                                                                             \
     k_tourn<128, T_, F64_, MINB_><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, \
-                                                        FIN_, LU, moves, perm, perm_stride, info)
+                                                        FIN_, LU, moves, perm, perm_stride, info, mixr)
         if (!fin && g_tourn_fp32) {
             if (real_panel) GNB_TOURN(TTR<float>, false, 8, 0);
             else GNB_TOURN(TT<float>, false, 5, 0);
@@ -912,7 +932,7 @@ void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N) 
 // kernel (tools/proto_blockgj.py: two_level_jordan / two_level_forward are the numpy models).
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
-                           int* info, int real_panel);
+                           int* info, int real_panel, int mixr);
 static int g_two_level = 1;
 void gnb_set_two_level(int on) { g_two_level = on; }
 
@@ -926,7 +946,7 @@ struct Elim {
 
     void tournament(int c0, int w, int slot) {
         launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, w, ws.cand0, ws.cand1, ws.cand_stride, lu(slot),
-                                          mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info, 0);
+                                          mv(slot), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info, 0, 0);
     }
     void permute_solve(cplx* buf, long stride, int bld, int c0, int w, int lo, int hi, int slot, int mode,
                        const cplx* preL = nullptr, long strideL = 0, int ldL = 0, int pre_row = 0, int pre_k = 0) {

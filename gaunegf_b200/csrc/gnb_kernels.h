@@ -44,7 +44,7 @@ void gnb_set_two_level(int on);
 void gnb_set_tourn_group(int g);
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E,
-                         const int* pi = nullptr);
+                         const int* pi = nullptr, int mixr = 0);
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,
                             const cplx* blk, long strideBlk, const int* map = nullptr);
 void gnb_launch_set_aug(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, int xoff, const int* cols, int m,
@@ -56,7 +56,7 @@ long gnb_eliminate(cudaStream_t st, int M, int N, int naug, cplx* A, long stride
 
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
-                           int* info, int real_panel = 0);
+                           int* info, int real_panel = 0, int mixr = 0);
 void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N);
 
 // gnb_rec.cu : recursive (multi-level) elimination on a padded layout; the rank-K updates run on the
@@ -76,11 +76,13 @@ struct GnbRecWork {
     int* info;
     int back_row_lo;                   // FORWARD: only rows >= back_row_lo of the solution are needed
     int nreal;                         // FORWARD: columns [0, nreal) of the matrices are real (0 = unknown / complex)
+    int mixr;                          // mixed layout: columns [0, mixr) stored as real doubles (0 or == nreal)
 };
 size_t gnb_rec_pk_elems(int N);               // cplx elements per matrix of Ppk / Lpk (incl. slack)
 size_t gnb_rec_wk_elems(int N, int ld);       // cplx elements per matrix of Wpk (incl. slack)
 cudaError_t gnb_rec_init();
 void gnb_rec_set_option(const char* name, int value);
+int gnb_rec_real_enabled();
 long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
                        const GnbRecWork& ws);
 

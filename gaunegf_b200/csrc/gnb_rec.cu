@@ -24,6 +24,17 @@
 
 static inline int cdiv_i(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Mixed layout (transmission path with the real-structure shortcut): the first mixr columns of every row are
+// stored as real doubles, the others as complex128.  `A` is always the LOGICAL complex base, i.e.
+// A[row * ld + col] is the element for col >= mixr; the real view of the same rows starts mixr * 8 bytes later
+// and has a row stride of 2 * ld doubles.  mixr is a multiple of 32, so 32-column tiles never straddle.
+__device__ __forceinline__ double* rk_real_view(cplx* A, int mixr) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(A) + (size_t)mixr * 8);
+}
+__device__ __forceinline__ const double* rk_real_view(const cplx* A, int mixr) {
+    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(A) + (size_t)mixr * 8);
+}
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy helpers
 // ------------------------------------------------------------------------------------------------
@@ -65,6 +76,7 @@ struct RkGemmArgs {
     int kskip;
     int preal;      // the panel operand P is real (imaginary parts exactly zero)
     int nreal;      // columns [0, nreal) of C / W are real (real F, S, E with the contact orbitals ordered last)
+    int mixr;       // columns [0, mixr) of C are STORED as real doubles (launches never straddle mixr)
 };
 
 #define RK_ST 4
@@ -224,6 +236,22 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         if (active && ch0 < nch_all) {
+            if (j0 < g.mixr) {
+                // real-stored C (mode 1 by construction): 16-byte read-modify-write of two adjacent doubles
+                double* Cr = rk_real_view(g.C + (long)b * g.sC, g.mixr) + (long)(i0 + wm * 16 + gid) * 2 * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) {
+                    double2 v[NI];
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) v[ni] = *reinterpret_cast<const double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8);
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) {
+                        v[ni].x -= cre[mi][ni][0]; v[ni].y -= cre[mi][ni][1];
+                        cre[mi][ni][0] = cre[mi][ni][1] = 0.0;
+                        *reinterpret_cast<double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8) = v[ni];
+                    }
+                }
+            } else {
             cplx* Cb = g.C + (long)b * g.sC + (long)(i0 + wm * 16 + gid) * g.ldc + j0 + wn * 32 + tig * 2;
 #pragma unroll
             for (int mi = 0; mi < MI; mi++) {
@@ -248,6 +276,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
                     Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1] = v[ni][1];
                 }
             }
+            }
         }
     }
 }
@@ -259,7 +288,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
 // rows.  Reads A only and writes Ppk only, so the row moves need no separate pass over the panel.
 __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ A, long strideA, int ld, int N, int c0,
                                                        int rlo, const int* __restrict__ moves, cplx* __restrict__ Ppk,
-                                                       long stridePk, int nrb) {
+                                                       long stridePk, int nrb, int mixr) {
     __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
     __shared__ int s_nm;
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, wrp = t >> 5;
@@ -278,7 +307,8 @@ __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ 
         src = __reduce_max_sync(0xffffffffu, src == r ? -1 : src);
         if (src < 0) src = r;
         const bool piv = (r >= c0 && r < c0 + GNB_NB);
-        const cplx v = piv ? cmake(0.0, 0.0) : Ab[(long)src * ld + c0 + lane];
+        cplx v = cmake(0.0, 0.0);
+        if (!piv) v = (c0 < mixr) ? cmake(rk_real_view(Ab, mixr)[(long)src * 2 * ld + c0 + lane], 0.0) : Ab[(long)src * ld + c0 + lane];
         Pb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk] = v;
     }
 }
@@ -336,33 +366,41 @@ __global__ void __launch_bounds__(128) k_rk_panel_fin(cplx* __restrict__ A, long
 }
 
 // Row moves of blocks [blk_lo, blk_hi) applied, in order, to a 32-column tile of A.
-__global__ void __launch_bounds__(256) k_rk_moves_A(cplx* __restrict__ A, long strideA, int ld, int jlo, int jhi,
-                                                    const int* __restrict__ moves, long moves_blk_stride, int blk_lo,
-                                                    int blk_hi) {
-    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
-    const int b = blockIdx.y, t = threadIdx.x;
-    const int col = jlo + blockIdx.x * 32 + (t & 31);
-    const int m0 = t >> 5;                                   // this thread handles moves m0, m0 + 8, ...
-    cplx* Ab = A + (long)b * strideA;
+template <typename ET>
+__device__ __forceinline__ void rk_moves_tile(ET* __restrict__ Xb, long ldx, int col, bool colok, const int* __restrict__ moves,
+                                              long moves_blk_stride, int b, int blk_lo, int blk_hi, int* s_dst, int* s_src) {
+    const int t = threadIdx.x, m0 = t >> 5;                  // this thread handles moves m0, m0 + 8, ...
     for (int blk = blk_lo; blk < blk_hi; blk++) {
         const int* mv = moves + (long)blk * moves_blk_stride + (long)b * GNB_MOVES_STRIDE;
         const int nm = mv[0];
         __syncthreads();
         if (t < nm) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
         __syncthreads();
-        cplx v[8];
+        ET v[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int m = m0 + 8 * q;
-            if (m < nm && col < jhi) v[q] = Ab[(long)s_src[m] * ld + col];
+            if (m < nm && colok) v[q] = Xb[(long)s_src[m] * ldx + col];
         }
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int m = m0 + 8 * q;
-            if (m < nm && col < jhi) Ab[(long)s_dst[m] * ld + col] = v[q];
+            if (m < nm && colok) Xb[(long)s_dst[m] * ldx + col] = v[q];
         }
     }
+}
+__global__ void __launch_bounds__(256) k_rk_moves_A(cplx* __restrict__ A, long strideA, int ld, int jlo, int jhi,
+                                                    const int* __restrict__ moves, long moves_blk_stride, int blk_lo,
+                                                    int blk_hi, int mixr) {
+    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
+    const int b = blockIdx.y;
+    const int col = jlo + blockIdx.x * 32 + (threadIdx.x & 31);
+    cplx* Ab = A + (long)b * strideA;
+    if (jlo + (int)blockIdx.x * 32 < mixr)                   // block-uniform: this tile lives in the real-stored columns
+        rk_moves_tile<double>(rk_real_view(Ab, mixr), 2L * ld, col, col < jhi, moves, moves_blk_stride, b, blk_lo, blk_hi, s_dst, s_src);
+    else
+        rk_moves_tile<cplx>(Ab, ld, col, col < jhi, moves, moves_blk_stride, b, blk_lo, blk_hi, s_dst, s_src);
 }
 
 // Row moves of block `blk` applied to the saved panels (K chunks [kc_lo, kc_hi) of Ppk).  JORDAN (Lpk != null):
@@ -533,7 +571,8 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
                                                           int jlo, int jhi, int tiles_per_cta,
                                                           const cplx* __restrict__ inv_a, const cplx* __restrict__ inv_b,
                                                           const cplx* __restrict__ Lsrc, long stridePk, int nrb,
-                                                          cplx* __restrict__ Wpk, long strideWk, int ncb, int nreal) {
+                                                          cplx* __restrict__ Wpk, long strideWk, int ncb, int nreal,
+                                                          int mixr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);            // [3][32][WM_AS]: inv_a, L_ba, inv_b
     cplx* sB = sA + 3 * GNB_NB * WM_AS;                      // [64][WM_BS]: R_a / W_a rows, then R_b rows
@@ -555,9 +594,11 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
         const int cs = jlo + (blockIdx.x * tiles_per_cta + tt) * WM_TC;
         if (cs >= jhi) break;                                 // block-uniform
         __syncthreads();                                      // previous tile consumed; operands staged
+        const bool rstore = cs < mixr;                       // tile stored as real doubles (mixed layout)
+        double* Abr = rk_real_view(Ab, mixr);
         for (int idx = t; idx < nrows * WM_TC; idx += 256) {
             const int i = idx >> 5, cc = idx & 31;
-            sB[i * WM_BS + cc] = Ab[(long)(c0 + i) * ld + cs + cc];
+            sB[i * WM_BS + cc] = rstore ? cmake(Abr[(long)(c0 + i) * 2 * ld + cs + cc], 0.0) : Ab[(long)(c0 + i) * ld + cs + cc];
         }
         __syncthreads();
         double cre[2][2], cim[2][2];
@@ -573,7 +614,8 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
         for (int mi = 0; mi < 2; mi++) {
             const int k = c0 + wm * 16 + mi * 8 + gid;
             const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
-            Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1;
+            if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
+            else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
             cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
             wq[0] = v0; wq[1] = v1;
         }
@@ -606,7 +648,8 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
             for (int mi = 0; mi < 2; mi++) {
                 const int k = c0 + GNB_NB + wm * 16 + mi * 8 + gid;
                 const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
-                Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1;
+                if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
+            else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
                 cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
                 wq[0] = v0; wq[1] = v1;
             }
@@ -645,6 +688,7 @@ cudaError_t gnb_rec_init() {
     cudaDeviceGetAttribute(&g_rk_sms, cudaDevAttrMultiProcessorCount, dev);
     return cudaSuccess;
 }
+int gnb_rec_real_enabled() { return g_rk_real; }
 void gnb_rec_set_option(const char* name, int value) {
     if (!strcmp(name, "rk_m3")) g_rk_m3 = value;
     else if (!strcmp(name, "rk_m3_mink")) g_rk_m3_mink = value;
@@ -703,12 +747,18 @@ struct Rec {
     cudaStream_t st; int M, N, naug; cplx* A; long strideA; int ld; int jordan;
     const GnbRecWork& ws; long launches;
     int nrb, ncb;
+    int mixr;                                                // real-stored leading columns (mixed layout), 0 = none
 
     cplx* inv(int c0) const { return ws.inv + (long)(c0 / GNB_NB) * ws.inv_blk_stride; }
     int* mv(int c0) const { return ws.moves + (long)(c0 / GNB_NB) * ws.moves_blk_stride; }
 
     void gemm(int ilo, int ihi, int jlo, int jhi, int klo, int khi, const cplx* P, int kskip) {
         if (ihi <= ilo || jhi <= jlo || khi <= klo) return;
+        if (mixr > 0 && jlo < mixr && jhi > mixr) {          // a launch never straddles the real-stored / complex boundary
+            gemm(ilo, ihi, jlo, mixr, klo, khi, P, kskip);
+            gemm(ilo, ihi, mixr, jhi, klo, khi, P, kskip);
+            return;
+        }
         RkGemmArgs g{};
         g.C = A; g.sC = strideA; g.ldc = ld;
         g.P = P; g.sP = ws.stridePk; g.nrb = nrb;
@@ -717,6 +767,7 @@ struct Rec {
         g.kskip = (kskip && g_rk_kskip) ? 1 : 0;
         g.nreal = g_rk_real ? ws.nreal : 0;
         g.preal = (g.nreal > 0 && khi <= g.nreal) ? 1 : 0;
+        g.mixr = mixr;
         const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);     // 128 x 32 tiles for 32-column strips
         const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
         const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
@@ -750,7 +801,7 @@ struct Rec {
             TraceScope ts("tourn", st, M);
             launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
                                               inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info,
-                                              (g_rk_real && c0 + GNB_NB <= ws.nreal) ? 1 : 0);
+                                              (g_rk_real && c0 + GNB_NB <= ws.nreal) ? 1 : 0, mixr);
         }
         TraceScope ts2("panel", st, M);
         if (live_lo < c0) {
@@ -762,7 +813,7 @@ struct Rec {
         const int rlo = jordan ? 0 : c0 + GNB_NB;
         if (rlo < N) {
             dim3 grid(std::min(cdiv_i(N - rlo, 8), 128), M);
-            k_rk_panel_save<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, rlo, mv(c0), ws.Ppk, ws.stridePk, nrb);
+            k_rk_panel_save<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, rlo, mv(c0), ws.Ppk, ws.stridePk, nrb, mixr);
             launches++;
         }
         if (jordan) {
@@ -778,14 +829,14 @@ struct Rec {
         const cplx* Lsrc = jordan ? ws.Lpk : ws.Ppk;
         if (nb <= 2) {
             TraceScope ts("wsolve", st, M);
-            if (g_rk_wsolve_mma) {
+            if (g_rk_wsolve_mma || mixr > 0) {             // the FMA kernel does not know the mixed layout
                 const int ntile = (jhi - jlo) / WM_TC;
                 const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
                 const int per = cdiv_i(ntile, split);
                 dim3 grid(cdiv_i(ntile, per), M);
                 k_rk_wsolve_mma<<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
                                                             nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
-                                                            ws.Wpk, ws.strideWk, ncb, g_rk_real ? ws.nreal : 0);
+                                                            ws.Wpk, ws.strideWk, ncb, g_rk_real ? ws.nreal : 0, mixr);
             } else {
                 const int ntile = cdiv_i(jhi - jlo, WS_TC);
                 const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
@@ -809,7 +860,7 @@ struct Rec {
         dim3 grid(cdiv_i(jhi - jlo, 32), M);
         TraceScope ts("movesA", st, M);
         k_rk_moves_A<<<grid, 256, 0, st>>>(A, strideA, ld, jlo, jhi, ws.moves, ws.moves_blk_stride, c0 / GNB_NB,
-                                           (c0 + w) / GNB_NB);
+                                           (c0 + w) / GNB_NB, mixr);
         launches++;
         trsm(c0, w, jlo, jhi);
         if (jordan) gemm(0, N, jlo, jhi, c0, c0 + w, ws.Ppk, 1);
@@ -857,7 +908,7 @@ struct Rec {
 long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
                        const GnbRecWork& ws) {
     if (M <= 0) return 0;
-    Rec e{st, M, N, naug, A, strideA, ld, jordan, ws, 0, N / 32, ld / 32};
+    Rec e{st, M, N, naug, A, strideA, ld, jordan, ws, 0, N / 32, (N + naug) / 32, (!jordan && g_rk_real) ? ws.mixr : 0};
     if (jordan) { gnb_launch_init_perm(st, M, ws.perm, ws.perm_stride, N); e.launches++; }
     e.factor(0, N, false, 0);
     if (!jordan && naug > 0) {

@@ -195,7 +195,8 @@ def _set(ctx, **opts):
         assert ctx.lib.gnb_dev_set_option(k.encode(), int(v)) == 0
 
 
-DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=2)
+DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=2,
+                rk_real=1, mixed_layout=1, rk_strip=1, rk_wsolve_mma=1)
 
 
 @pytest.mark.parametrize("N,nc", [(96, 8), (100, 7), (256, 16), (416, 33), (600, 40)])
@@ -224,7 +225,8 @@ def test_recursive_engine_matches_two_level_engine_and_numpy(ctx, N, nc):
     assert np.allclose(out[1][1], Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
 
 
-@pytest.mark.parametrize("opt", ["rk_m3", "rk_kskip", "contacts_last", "tourn_fp32", "rec_streams"])
+@pytest.mark.parametrize("opt", ["rk_m3", "rk_kskip", "contacts_last", "tourn_fp32", "rec_streams", "rk_real",
+                                 "mixed_layout", "rk_strip", "rk_wsolve_mma"])
 def test_recursive_engine_switches_do_not_change_results(ctx, opt):
     """3M arithmetic, block-upper K skipping, contacts-last ordering, FP32 nominating rounds and sub-batch streams
     are performance switches: results must stay within the parity tolerance of the plain path."""
@@ -286,7 +288,7 @@ def test_real_structure_shortcut_matches_complex_path(ctx):
         _set(ctx, rk_real=0)
         T0 = ctx.transmission(Er, 0, -1)
     finally:
-        _set(ctx, **DEFAULTS, rk_real=1)
+        _set(ctx, **DEFAULTS)
     assert relerr(T1, T0) < TOL
     Tref = np.array([O.transmission_restricted(e, F, S, st, g1, g2) for e in Er[::4]])
     assert np.allclose(T1[::4], Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
