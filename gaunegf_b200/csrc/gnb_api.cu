@@ -63,7 +63,7 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     DevBuf* bufs[] = {&c->dF, &c->dS, &c->dSig0, &c->A, &c->Pws, &c->LU, &c->moves, &c->cand0, &c->cand1,
                       &c->perm, &c->invperm, &c->info, &c->dE, &c->dW, &c->G, &c->Y, &c->Z, &c->Xr, &c->out,
                       &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
-                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
+                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->PpkR, &c->WpkR, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < GNB_MAX_SUBSTREAMS; i++) {
         if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
@@ -325,6 +325,7 @@ struct Lay {
     size_t bytes_per_energy(bool jordan) const {
         size_t b = (size_t)Np * ld * 16 + 8 * (size_t)Np + 32768;
         if (rec) b += gnb_rec_pk_elems(Np) * 16 * (jordan ? 2 : 1) + gnb_rec_wk_elems(Np, ldl()) * 16 + (size_t)(Np / 32) * (16384 + 4 * GNB_MOVES_STRIDE);
+        if (rec && mixr > 0) b += gnb_rec_pk_elems(Np) * 8 + gnb_rec_wk_elems(Np, ldl()) * 9;
         else if (jordan) b += (size_t)N * 2 * GNB_NB * 16;
         return b;
     }
@@ -341,7 +342,7 @@ static Lay make_layout(int N, int naug) {
     return L;
 }
 
-GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc) {
+GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc, int mixr) {
     GnbRecWork w{};
     *rc = GNB_OK;
     const int nblk = Np / 32;
@@ -361,7 +362,14 @@ GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc)
         need(c->perm, (size_t)M * Np * sizeof(int));
         need(c->invperm, (size_t)M * Np * sizeof(int));
     }
+    const size_t wkr = (size_t)(Np / 16) * (ld / 32) * RK_WRBLK + 4 * RK_WRBLK;
+    if (mixr > 0) {                       // real-packed operands of the real columns (same element counts, doubles)
+        need(c->PpkR, (size_t)M * pk * sizeof(double));
+        need(c->WpkR, (size_t)M * wkr * sizeof(double));
+    }
     if (e != cudaSuccess) { *rc = gnb_cuda_fail(c, e, "workspace allocation"); return w; }
+    w.PpkR = c->PpkR.as<double>(); w.stridePkR = (long)pk;
+    w.WpkR = c->WpkR.as<double>(); w.strideWkR = (long)wkr;
     w.cand0 = c->cand0.as<int>(); w.cand1 = c->cand1.as<int>(); w.cand_stride = cand_stride;
     w.inv = c->LU.as<cplx>(); w.inv_blk_stride = (long)M * GNB_NB * GNB_NB;
     w.moves = c->moves.as<int>(); w.moves_blk_stride = (long)M * GNB_MOVES_STRIDE;
@@ -385,7 +393,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
     int rc;
     const long strideA = (long)L.Np * L.ld;
     if (L.rec) {
-        GnbRecWork w = gnb_rec_work(c, M, L.Np, L.ldl(), jordan != 0, &rc);
+        GnbRecWork w = gnb_rec_work(c, M, L.Np, L.ldl(), jordan != 0, &rc, jordan ? 0 : L.mixr);
         if (rc) return rc;
         w.back_row_lo = L.back_row_lo;
         w.nreal = jordan ? 0 : L.nreal;
@@ -414,6 +422,8 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
                 ws.perm = w.perm ? w.perm + (long)m0 * w.perm_stride : nullptr;
                 ws.Ppk = w.Ppk + (long)m0 * w.stridePk; ws.Lpk = w.Lpk ? w.Lpk + (long)m0 * w.stridePk : nullptr;
                 ws.Wpk = w.Wpk + (long)m0 * w.strideWk;
+                ws.PpkR = w.PpkR ? w.PpkR + (long)m0 * w.stridePkR : nullptr;
+                ws.WpkR = w.WpkR ? w.WpkR + (long)m0 * w.strideWkR : nullptr;
                 GNB_CK(cudaStreamWaitEvent(c->sub[s], c->fork_ev, 0));
                 c->launches += gnb_eliminate_rec(c->sub[s], m1 - m0, L.Np, L.naugp, A + (long)m0 * strideA, strideA, L.ld,
                                                  jordan, ws);

@@ -87,7 +87,7 @@ struct gnb_ctx {
     std::vector<Contact> contacts;
     // workspaces
     DevBuf A, Pws, LU, moves, cand0, cand1, perm, invperm, info, dE, dW, G, Y, Z, Xr, out, dT, dDosT, dDosP,
-        sigB, gam1B, gam2B, cols, rows, in_stage, Ppk, Lpk, Wpk;
+        sigB, gam1B, gam2B, cols, rows, in_stage, Ppk, Lpk, Wpk, PpkR, WpkR;
     // chain1d fixed-point workspaces
     DevBuf cA, cB, cg, cgn, cT1, cM, cflags, ct;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -100,7 +100,7 @@ int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_ga
 int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE);     // leaves g in c->cg
 int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cplx* d_out);
 GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc);
-GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc);
+GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc, int mixr = 0);
 int gnb_fail(gnb_ctx* c, int code, const std::string& msg);
 int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where);
 

@@ -65,6 +65,10 @@ void gnb_launch_init_perm(cudaStream_t st, int M, int* perm, int stride, int N);
 #define RK_WPS 34                      // row stride (cplx) of a packed W block     [16 k][32 cols]
 #define RK_PBLK (32 * RK_PPS)
 #define RK_WBLK (16 * RK_WPS)
+#define RK_PRS 20                      // real-packed panel block  [32 rows][16 k] doubles, row stride 20
+#define RK_WRS 36                      // real-packed W block      [16 k][32 cols] doubles, row stride 36
+#define RK_PRBLK (32 * RK_PRS)
+#define RK_WRBLK (16 * RK_WRS)
 struct GnbRecWork {
     GnbGemmTimer* timer;
     int* cand0; int* cand1; int cand_stride;
@@ -73,6 +77,8 @@ struct GnbRecWork {
     int* perm; int perm_stride;        // JORDAN: running row permutation
     cplx* Ppk; cplx* Lpk; long stridePk;   // packed panels [M][N/16][N/32][32][RK_PPS]
     cplx* Wpk; long strideWk;          // packed pivot rows [M][N/16][ld/32][16][RK_WPS]
+    double* PpkR; double* WpkR;        // real-packed panels / pivot rows of the real columns (mixed layout); strides below
+    long stridePkR, strideWkR;
     int* info;
     int back_row_lo;                   // FORWARD: only rows >= back_row_lo of the solution are needed
     int nreal;                         // FORWARD: columns [0, nreal) of the matrices are real (0 = unknown / complex)

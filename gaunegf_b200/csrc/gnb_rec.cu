@@ -282,13 +282,178 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
 }
 
 // ------------------------------------------------------------------------------------------------
+// Rank-K update with a REAL-PACKED panel (mixed layout, panels left of mixr):
+//   PpkR[b][kc][rb][32][RK_PRS] doubles;   WR = 1: W real-packed WpkR[b][kc][cb][16][RK_WRS] doubles, C real-stored;
+//   WR = 0: W complex-packed (columns right of mixr: contact orbitals and augmented columns), C complex.
+// Same warp-specialised structure as k_rk_gemm; one real DMMA per tile product (WR = 1) or two (WR = 0).
+// Row strides 20 / 36 doubles keep the LDS.64 fragment loads conflict-free.
+// ------------------------------------------------------------------------------------------------
+struct RkGemmRpArgs {
+    cplx* C; long sC; int ldc;
+    const double* P; long sP; int nrb;
+    const void* W; long sW; int ncb;        // doubles (WR = 1) or cplx (WR = 0); sW in elements of that type
+    int ilo, ihi, jlo, jhi, klo, khi;
+    int mixr;
+};
+template <int RB, int CB, int WR> constexpr size_t rk_rp_smem() {
+    return (size_t)RK_ST * (RB * RK_PRBLK * 8 + CB * (WR ? RK_WRBLK * 8 : RK_WBLK * 16)) + 2 * RK_ST * 8;
+}
+
+template <int RB, int CB, int WR>
+__global__ void __launch_bounds__(288, WR ? 2 : 1) k_rk_gemm_rp(RkGemmRpArgs g, int nti, int ntj, int total) {
+    static_assert(RB * CB == 4, "8 consumer warps of 16 x 32");
+    constexpr int NCW = 8, WN = CB, MI = 2, NI = 4, KC = 16;
+    constexpr int TM = 32 * RB, TN = 32 * CB;
+    constexpr int PBYTES = RB * RK_PRBLK * 8, WBYTES = CB * (WR ? RK_WRBLK * 8 : RK_WBLK * 16), SBYTES = PBYTES + WBYTES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + RK_ST * SBYTES);
+    unsigned long long* empty = full + RK_ST;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_mat = nti * ntj;
+    const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < RK_ST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int kc0 = g.klo / KC, nch_all = (g.khi - g.klo) / KC;
+
+    if (warp == NCW) {
+        if (lane != 0) return;
+        int q = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int b = tile / per_mat, rem = tile - b * per_mat;
+            const int ti = rem / ntj, tj = rem - ti * ntj;
+            const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
+            const double* Pb = g.P + (long)b * g.sP + ((long)kc0 * g.nrb + i0 / 32) * RK_PRBLK;
+            const char* Wb = WR ? reinterpret_cast<const char*>(reinterpret_cast<const double*>(g.W) + (long)b * g.sW +
+                                                                ((long)kc0 * g.ncb + j0 / 32) * RK_WRBLK)
+                                : reinterpret_cast<const char*>(reinterpret_cast<const cplx*>(g.W) + (long)b * g.sW +
+                                                                ((long)kc0 * g.ncb + j0 / 32) * RK_WBLK);
+            const long wstep = (long)g.ncb * (WR ? RK_WRBLK * 8 : RK_WBLK * 16);
+            for (int ch = 0; ch < nch_all; ch++, q++) {
+                const int s = q % RK_ST;
+                if (q >= RK_ST) mbar_wait(&empty[s], ((q / RK_ST) - 1) & 1);
+                unsigned char* st = smem_raw + s * SBYTES;
+                mbar_expect_tx(&full[s], SBYTES);
+                bulk_g2s(st, Pb + (long)ch * g.nrb * RK_PRBLK, PBYTES, &full[s]);
+                bulk_g2s(st + PBYTES, Wb + ch * wstep, WBYTES, &full[s]);
+            }
+        }
+        return;
+    }
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+    double cre[MI][NI][2], cim[WR ? 1 : MI][WR ? 1 : NI][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) {
+            cre[mi][ni][0] = cre[mi][ni][1] = 0.0;
+            if (!WR) cim[mi][ni][0] = cim[mi][ni][1] = 0.0;
+        }
+    int q = 0;
+    for (int it = 0; it < my_tiles; it++) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / per_mat, rem = tile - b * per_mat;
+        const int ti = rem / ntj, tj = rem - ti * ntj;
+        const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
+        const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);
+        for (int ch = 0; ch < nch_all; ch++, q++) {
+            const int s = q % RK_ST;
+            mbar_wait(&full[s], (q / RK_ST) & 1);
+            if (active) {
+                const double* Ps = reinterpret_cast<const double*>(smem_raw + s * SBYTES) + (wm * 16 + gid) * RK_PRS + tig;
+                if (WR) {
+                    const double* Ws = reinterpret_cast<const double*>(smem_raw + s * SBYTES + PBYTES) + wn * RK_WRBLK + tig * RK_WRS + gid;
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        double af[MI], bf[NI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PRS + kk];
+#pragma unroll
+                        for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[kk * RK_WRS + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi], bf[ni]);
+                    }
+                } else {
+                    const cplx* Ws = reinterpret_cast<const cplx*>(smem_raw + s * SBYTES + PBYTES) + wn * RK_WBLK + tig * RK_WPS + gid;
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        double af[MI];
+                        cplx bf[NI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PRS + kk];
+#pragma unroll
+                        for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[kk * RK_WPS + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) {
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi], bf[ni].x);
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++)
+                                dmma884(cim[WR ? 0 : mi][WR ? 0 : ni][0], cim[WR ? 0 : mi][WR ? 0 : ni][1], af[mi], bf[ni].y);
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (active) {
+            if (WR) {
+                double* Cr = rk_real_view(g.C + (long)b * g.sC, g.mixr) + (long)(i0 + wm * 16 + gid) * 2 * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) {
+                    double2 v[NI];
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) v[ni] = *reinterpret_cast<const double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8);
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) {
+                        v[ni].x -= cre[mi][ni][0]; v[ni].y -= cre[mi][ni][1];
+                        cre[mi][ni][0] = cre[mi][ni][1] = 0.0;
+                        *reinterpret_cast<double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8) = v[ni];
+                    }
+                }
+            } else {
+                cplx* Cb = g.C + (long)b * g.sC + (long)(i0 + wm * 16 + gid) * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) {
+                    cplx v[NI][2];
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) {
+                        v[ni][0] = Cb[(long)(mi * 8) * g.ldc + ni * 8];
+                        v[ni][1] = Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1];
+                    }
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            v[ni][e].x -= cre[mi][ni][e]; v[ni][e].y -= cim[WR ? 0 : mi][WR ? 0 : ni][e];
+                            cre[mi][ni][e] = 0.0; cim[WR ? 0 : mi][WR ? 0 : ni][e] = 0.0;
+                        }
+                        Cb[(long)(mi * 8) * g.ldc + ni * 8] = v[ni][0];
+                        Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1] = v[ni][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Panel kernels of the base step (block K = [c0, c0 + 32))
 // ------------------------------------------------------------------------------------------------
 // Phase 1: Ppk[r][K] = A[src(r)][K] for rows r in [rlo, N) (src = row move of this block), zero for the pivot
 // rows.  Reads A only and writes Ppk only, so the row moves need no separate pass over the panel.
 __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ A, long strideA, int ld, int N, int c0,
                                                        int rlo, const int* __restrict__ moves, cplx* __restrict__ Ppk,
-                                                       long stridePk, int nrb, int mixr) {
+                                                       long stridePk, int nrb, int mixr, double* __restrict__ PpkR,
+                                                       long stridePkR) {
     __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
     __shared__ int s_nm;
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, wrp = t >> 5;
@@ -307,9 +472,12 @@ __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ 
         src = __reduce_max_sync(0xffffffffu, src == r ? -1 : src);
         if (src < 0) src = r;
         const bool piv = (r >= c0 && r < c0 + GNB_NB);
-        cplx v = cmake(0.0, 0.0);
-        if (!piv) v = (c0 < mixr) ? cmake(rk_real_view(Ab, mixr)[(long)src * 2 * ld + c0 + lane], 0.0) : Ab[(long)src * ld + c0 + lane];
-        Pb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk] = v;
+        const long off = ((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk;
+        if (c0 < mixr) {                                     // real-stored panel -> real-packed copy
+            PpkR[(long)b * stridePkR + off] = piv ? 0.0 : rk_real_view(Ab, mixr)[(long)src * 2 * ld + c0 + lane];
+        } else {
+            Pb[off] = piv ? cmake(0.0, 0.0) : Ab[(long)src * ld + c0 + lane];
+        }
     }
 }
 
@@ -406,7 +574,8 @@ __global__ void __launch_bounds__(256) k_rk_moves_A(cplx* __restrict__ A, long s
 // Row moves of block `blk` applied to the saved panels (K chunks [kc_lo, kc_hi) of Ppk).  JORDAN (Lpk != null):
 // afterwards the rows of the new pivot block are moved out of Ppk into Lpk (they are the L_ab blocks of the
 // forward W solve) and cleared, which leaves Ppk strictly block-upper on pivot rows.
-__global__ void __launch_bounds__(256) k_rk_moves_P(cplx* __restrict__ Ppk, cplx* __restrict__ Lpk, long stridePk, int nrb,
+template <typename ET>
+__global__ void __launch_bounds__(256) k_rk_moves_P(ET* __restrict__ Ppk, ET* __restrict__ Lpk, long stridePk, int nrb,
                                                     int kc_lo, int kc_hi, int c0, const int* __restrict__ moves) {
     __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
     const int b = blockIdx.y, t = threadIdx.x;
@@ -416,8 +585,8 @@ __global__ void __launch_bounds__(256) k_rk_moves_P(cplx* __restrict__ Ppk, cplx
     __syncthreads();
     const int kk = t & 15, m0 = t >> 4;                      // 16 moves per pass
     for (int kc = kc_lo + blockIdx.x; kc < kc_hi; kc += gridDim.x) {
-        cplx* Pc = Ppk + (long)b * stridePk + (long)kc * nrb * RK_PBLK;
-        cplx v[4];
+        ET* Pc = Ppk + (long)b * stridePk + (long)kc * nrb * RK_PBLK;
+        ET v[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int m = m0 + 16 * q;
@@ -431,12 +600,12 @@ __global__ void __launch_bounds__(256) k_rk_moves_P(cplx* __restrict__ Ppk, cplx
         }
         if (Lpk) {
             __syncthreads();
-            cplx* Lc = Lpk + (long)b * stridePk + (long)kc * nrb * RK_PBLK + (long)(c0 >> 5) * RK_PBLK;
-            cplx* Pr = Pc + (long)(c0 >> 5) * RK_PBLK;
+            ET* Lc = Lpk + (long)b * stridePk + (long)kc * nrb * RK_PBLK + (long)(c0 >> 5) * RK_PBLK;
+            ET* Pr = Pc + (long)(c0 >> 5) * RK_PBLK;
             for (int e = t; e < 32 * 16; e += 256) {
                 const int off = (e >> 4) * RK_PPS + (e & 15);
                 Lc[off] = Pr[off];
-                Pr[off] = cmake(0.0, 0.0);
+                Pr[off] = ET();
             }
         }
         __syncthreads();
@@ -572,7 +741,8 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
                                                           const cplx* __restrict__ inv_a, const cplx* __restrict__ inv_b,
                                                           const cplx* __restrict__ Lsrc, long stridePk, int nrb,
                                                           cplx* __restrict__ Wpk, long strideWk, int ncb, int nreal,
-                                                          int mixr) {
+                                                          int mixr, const double* __restrict__ PpkR, long stridePkR,
+                                                          double* __restrict__ WpkR, long strideWkR) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);            // [3][32][WM_AS]: inv_a, L_ba, inv_b
     cplx* sB = sA + 3 * GNB_NB * WM_AS;                      // [64][WM_BS]: R_a / W_a rows, then R_b rows
@@ -585,8 +755,9 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
         if (nb == 2) {
             const int cb = c0 + GNB_NB, k = c0 + j;
             sA[(2 * GNB_NB + i) * WM_AS + j] = inv_b[(long)b * GNB_NB * GNB_NB + idx];
-            sA[(GNB_NB + i) * WM_AS + j] =
-                Lsrc[(long)b * stridePk + ((long)(k >> 4) * nrb + (cb >> 5)) * RK_PBLK + i * RK_PPS + (k & 15)];
+            const long loff = ((long)(k >> 4) * nrb + (cb >> 5)) * RK_PBLK + i * RK_PPS + (k & 15);
+            sA[(GNB_NB + i) * WM_AS + j] = (c0 + GNB_NB <= mixr) ? cmake(PpkR[(long)b * stridePkR + loff], 0.0)   // panel a is real-packed
+                                                                     : Lsrc[(long)b * stridePk + loff];
         }
     }
     const int nrows = nb * GNB_NB;
@@ -606,6 +777,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
         const int mode = (c0 + nrows <= nreal) ? (cs + WM_TC <= nreal ? 1 : 2) : 3;
         const int col = cs + wn * 8 + tig * 2;                // this thread's two adjacent output columns
         cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
+        double* Wr = WpkR + (long)b * strideWkR + (long)(col >> 5) * RK_WRBLK + (col & 31);   // real-packed copy (rstore tiles)
         // ---- W_a = inv_a R_a
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
@@ -616,8 +788,12 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
             const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
             if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
             else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
-            cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
-            wq[0] = v0; wq[1] = v1;
+            if (rstore) {
+                *reinterpret_cast<double2*>(Wr + (long)(k >> 4) * ncb * RK_WRBLK + (k & 15) * RK_WRS) = make_double2(v0.x, v1.x);
+            } else {
+                cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
+                wq[0] = v0; wq[1] = v1;
+            }
         }
         if (nb == 2) {
             __syncthreads();                                  // every warp is done reading R_a
@@ -650,8 +826,12 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
                 const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
                 if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
             else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
-                cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
-                wq[0] = v0; wq[1] = v1;
+                if (rstore) {
+                    *reinterpret_cast<double2*>(Wr + (long)(k >> 4) * ncb * RK_WRBLK + (k & 15) * RK_WRS) = make_double2(v0.x, v1.x);
+                } else {
+                    cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
+                    wq[0] = v0; wq[1] = v1;
+                }
             }
         }
     }
@@ -680,6 +860,10 @@ cudaError_t gnb_rec_init() {
     if ((e = cudaFuncSetAttribute(k_rk_gemm<M3_, RB_, CB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                   (int)rk_smem<RB_, CB_>()))) return e;
     RK_ATTR(0, 2, 2) RK_ATTR(1, 2, 2) RK_ATTR(0, 4, 1) RK_ATTR(1, 4, 1)
+#define RK_RP_ATTR(RB_, CB_, WR_)                                                                                \
+    if ((e = cudaFuncSetAttribute(k_rk_gemm_rp<RB_, CB_, WR_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)rk_rp_smem<RB_, CB_, WR_>()))) return e;
+    RK_RP_ATTR(2, 2, 1) RK_RP_ATTR(2, 2, 0) RK_RP_ATTR(4, 1, 1) RK_RP_ATTR(4, 1, 0)
     if ((e = cudaFuncSetAttribute(k_rk_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_rk_wsolve_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWmSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_rk_panel_fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmem))) return e;
@@ -759,6 +943,37 @@ struct Rec {
             gemm(ilo, ihi, mixr, jhi, klo, khi, P, kskip);
             return;
         }
+        if (mixr > 0 && klo < mixr && khi > mixr) {          // panels left of mixr are real-packed, the others complex
+            gemm(ilo, ihi, jlo, jhi, klo, mixr, P, kskip);
+            gemm(ilo, ihi, jlo, jhi, mixr, khi, P, kskip);
+            return;
+        }
+        if (mixr > 0 && khi <= mixr) {                       // real-packed panel (mixed layout)
+            const bool wr = jhi <= mixr;                    // real-stored columns: real-packed W, real C
+            RkGemmRpArgs r{};
+            r.C = A; r.sC = strideA; r.ldc = ld;
+            r.P = ws.PpkR; r.sP = ws.stridePkR; r.nrb = nrb;
+            r.W = wr ? (const void*)ws.WpkR : (const void*)ws.Wpk; r.sW = wr ? ws.strideWkR : ws.strideWk; r.ncb = ncb;
+            r.ilo = ilo; r.ihi = ihi; r.jlo = jlo; r.jhi = jhi; r.klo = klo; r.khi = khi; r.mixr = mixr;
+            const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);
+            const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
+            const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
+            const long total = (long)M * nti * ntj;
+            const int grid = (int)std::min<long>(total, (long)g_rk_sms * (wr ? 2 : 1));
+            const double flops = (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M * (wr ? 2.0 : 4.0);
+            TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
+            if (ws.timer) ws.timer->begin(st);
+            if (strip) {
+                if (wr) k_rk_gemm_rp<4, 1, 1><<<grid, 288, rk_rp_smem<4, 1, 1>(), st>>>(r, nti, ntj, (int)total);
+                else k_rk_gemm_rp<4, 1, 0><<<grid, 288, rk_rp_smem<4, 1, 0>(), st>>>(r, nti, ntj, (int)total);
+            } else {
+                if (wr) k_rk_gemm_rp<2, 2, 1><<<grid, 288, rk_rp_smem<2, 2, 1>(), st>>>(r, nti, ntj, (int)total);
+                else k_rk_gemm_rp<2, 2, 0><<<grid, 288, rk_rp_smem<2, 2, 0>(), st>>>(r, nti, ntj, (int)total);
+            }
+            if (ws.timer) ws.timer->end(st, flops);
+            launches++;
+            return;
+        }
         RkGemmArgs g{};
         g.C = A; g.sC = strideA; g.ldc = ld;
         g.P = P; g.sP = ws.stridePk; g.nrb = nrb;
@@ -804,16 +1019,27 @@ struct Rec {
                                               (g_rk_real && c0 + GNB_NB <= ws.nreal) ? 1 : 0, mixr);
         }
         TraceScope ts2("panel", st, M);
+        const int rp = mixr > 0 ? 1 : 0;                   // panels left of mixr live real-packed in PpkR
         if (live_lo < c0) {
-            dim3 grid(std::min((c0 - live_lo) / 16, 64), M);
-            k_rk_moves_P<<<grid, 256, 0, st>>>(ws.Ppk, jordan ? ws.Lpk : nullptr, ws.stridePk, nrb, live_lo / 16, c0 / 16,
-                                               c0, mv(c0));
-            launches++;
+            const int split = rp ? std::min(c0, mixr) : live_lo;       // [live_lo, split): real-packed chunks
+            if (split > live_lo) {
+                dim3 grid(std::min((split - live_lo) / 16, 64), M);
+                k_rk_moves_P<double><<<grid, 256, 0, st>>>(ws.PpkR, (double*)nullptr, ws.stridePkR, nrb, live_lo / 16, split / 16,
+                                                           c0, mv(c0));
+                launches++;
+            }
+            if (c0 > split) {
+                dim3 grid(std::min((c0 - split) / 16, 64), M);
+                k_rk_moves_P<cplx><<<grid, 256, 0, st>>>(ws.Ppk, jordan ? ws.Lpk : (cplx*)nullptr, ws.stridePk, nrb, split / 16,
+                                                         c0 / 16, c0, mv(c0));
+                launches++;
+            }
         }
         const int rlo = jordan ? 0 : c0 + GNB_NB;
         if (rlo < N) {
             dim3 grid(std::min(cdiv_i(N - rlo, 8), 128), M);
-            k_rk_panel_save<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, rlo, mv(c0), ws.Ppk, ws.stridePk, nrb, mixr);
+            k_rk_panel_save<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, rlo, mv(c0), ws.Ppk, ws.stridePk, nrb, mixr, ws.PpkR,
+                                                  ws.stridePkR);
             launches++;
         }
         if (jordan) {
@@ -836,7 +1062,8 @@ struct Rec {
                 dim3 grid(cdiv_i(ntile, per), M);
                 k_rk_wsolve_mma<<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
                                                             nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
-                                                            ws.Wpk, ws.strideWk, ncb, g_rk_real ? ws.nreal : 0, mixr);
+                                                            ws.Wpk, ws.strideWk, ncb, g_rk_real ? ws.nreal : 0, mixr, ws.PpkR,
+                                                            ws.stridePkR, ws.WpkR, ws.strideWkR);
             } else {
                 const int ntile = cdiv_i(jhi - jlo, WS_TC);
                 const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
