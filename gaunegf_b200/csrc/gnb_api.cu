@@ -24,6 +24,8 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
 static int g_mixed_layout = 1;    // transmission: store the real columns as doubles (mixed layout, gnb_rec.cu)
 static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
+static int g_small = 1;           // N <= GNB_SMALL_MAX_N: one CTA per energy, matrix in shared memory (gnb_small.cu)
+int gnb_small_enabled() { return g_small; }
 static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
 
 extern "C" const char* gnb_version(void) { return "gaunegf_b200 0.1 (sm_100a)"; }
@@ -38,7 +40,7 @@ extern "C" int gnb_create(gnb_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GNB_ERR_CUDA; }
     gnb_ctx* c = new gnb_ctx();
     c->device = device;
-    if (gnb_kernels_init() != cudaSuccess || gnb_rec_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+    if (gnb_kernels_init() != cudaSuccess || gnb_rec_init() != cudaSuccess || gnb_small_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
         cudaEventCreate(&c->ev1) != cudaSuccess) {
         cudaGetLastError();
         delete c;
@@ -100,6 +102,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "gemm_bm")) gnb_set_gemm_bm(value);
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
+    else if (!strcmp(name, "small_fused")) g_small = value;
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
@@ -526,6 +529,28 @@ static int put_chunk_scalars(gnb_ctx* c, const double* E, const double* w, int k
     return GNB_OK;
 }
 
+// Small-orbital-count path (gnb_small.cu): is it usable for this call, and the common part of its arguments
+static bool small_ok(const gnb_ctx* c, bool use_desc) {
+    return g_small && c->N <= GNB_SMALL_MAX_N && (!use_desc || c->contacts.size() <= GNB_SMALL_MAX_CONTACTS);
+}
+static GnbSmallArgs small_args(gnb_ctx* c, int m, const cplx* dE, bool use_desc, const cplx* sig_const,
+                               const cplx* sig_batch) {
+    GnbSmallArgs a{};
+    a.N = c->N; a.M = m; a.E = dE;
+    a.F = c->dF.as<cplx>(); a.S = c->dS.as<cplx>();
+    a.Sig0 = use_desc ? (c->has_sig0 ? c->dSig0.as<cplx>() : nullptr) : sig_const;
+    a.SigB = sig_batch; a.strideSigB = (long)c->N * c->N;
+    a.info = c->info.as<int>();
+    if (use_desc)
+        for (auto& ct : c->contacts) {
+            GnbSmallContact& s = a.ct[a.ncontacts++];
+            s.inds = ct.d_inds.as<int>(); s.nc = ct.nc;
+            s.blk = ct.blk_ptr; s.blk_stride = ct.blk_stride;
+            s.gam = ct.gam_ptr; s.gam_stride = ct.gam_stride;
+        }
+    return a;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Full-inverse family: green / dos / gr_int (+ dense variants)
 // ---------------------------------------------------------------------------------------------
@@ -549,6 +574,8 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     if (sig.p && sig.stride) per += nn * 16;
     if (g1.p && g1.stride) per += nn * 16;
     if (g2.p && g2.stride) per += nn * 16;
+    const bool small = small_ok(c, use_desc);
+    if (small) per = (size_t)(2 + (sig.p && sig.stride) + 2 * (g1.p && g1.stride) + 2) * nn * 16 + (size_t)N * 16 + 64;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     cplx* d_out = nullptr;
     if (mode == MODE_GRINT || mode == MODE_GLESS_DENSE) {
@@ -559,26 +586,49 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         const int m = std::min(Mc, M - k0);
         if ((rc = put_chunk_scalars(c, E, w, k0, m))) return rc;
         const cplx* dE = c->dE.as<cplx>();
-        GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
-        cplx* A = c->A.as<cplx>();
-        const long strideA = (long)Np * ld;
         const cplx *sc = nullptr, *sb = nullptr;
         if (use_desc) {
             if ((rc = prepare_sigma(c, m, dE, 0))) return rc;
         } else if ((rc = stage_dense(c, c->sigB, sig, k0, m, &sc, &sb))) return rc;
-        if ((rc = pad_chunk(c, m, L, A))) return rc;
-        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, use_desc, sc, sb))) return rc;
-        if ((rc = run_eliminate(c, m, L, A, 1))) return rc;
-        gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), Np, Np);
-        c->launches++;
-        const int* inv = c->invperm.as<int>();
+        cplx* A = nullptr;                       // where the consumers below find (P A)^-1 ...
+        long strideA = (long)Np * ld;
+        int lda = ld;
+        const int* inv = nullptr;                // ... and its column order (null = natural)
         const int pst = Np;                      // stride of the permutation arrays
         cplx* G = nullptr;
         if (needG) {
             if (mode == MODE_GREEN && loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(out0) + (size_t)k0 * nn;
             else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
-            gnb_launch_unpermute(c->stream, m, N, A, strideA, ld, inv, pst, G, (long)nn);
+        }
+        if (small) {
+            // one CTA per energy: assembly, pivoted Gauss-Jordan and (for DOS) the reduction stay in shared memory
+            GnbSmallArgs sa = small_args(c, m, dE, use_desc, sc, sb);
+            if (mode == MODE_DOS) {
+                GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
+                if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
+                sa.mode = GNB_SMALL_DOS;
+                sa.dos_tot = c->dDosT.as<double>(); sa.dos_site = out1 ? c->dDosP.as<double>() : nullptr;
+            } else {
+                if (!G) { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
+                sa.mode = GNB_SMALL_GREEN;
+                sa.G = G; sa.strideG = (long)nn; sa.ldg = N;
+            }
+            gnb_launch_small(c->stream, sa);
             c->launches++;
+            A = G; strideA = (long)nn; lda = N;
+        } else {
+            GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
+            A = c->A.as<cplx>();
+            if ((rc = pad_chunk(c, m, L, A))) return rc;
+            if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, use_desc, sc, sb))) return rc;
+            if ((rc = run_eliminate(c, m, L, A, 1))) return rc;
+            gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), Np, Np);
+            c->launches++;
+            inv = c->invperm.as<int>();
+            if (needG) {
+                gnb_launch_unpermute(c->stream, m, N, A, strideA, ld, inv, pst, G, (long)nn);
+                c->launches++;
+            }
         }
         if (mode == MODE_GREEN) {
             if (loc == GNB_HOST)
@@ -587,15 +637,17 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         } else if (mode == MODE_DOS) {
             GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
             if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
-            gnb_launch_dos(c->stream, m, N, A, strideA, ld, inv, pst, c->dDosT.as<double>(),
-                           out1 ? c->dDosP.as<double>() : nullptr);
-            c->launches++;
+            if (!small) {
+                gnb_launch_dos(c->stream, m, N, A, strideA, lda, inv, pst, c->dDosT.as<double>(),
+                               out1 ? c->dDosP.as<double>() : nullptr);
+                c->launches++;
+            }
             GNB_CK(cudaMemcpyAsync(out0 + k0, c->dDosT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             if (out1)
                 GNB_CK(cudaMemcpyAsync(out1 + (size_t)k0 * N, c->dDosP.p, (size_t)m * N * sizeof(double),
                                        cudaMemcpyDeviceToHost, c->stream));
         } else if (mode == MODE_GRINT) {
-            gnb_launch_weighted_sum(c->stream, m, N, A, strideA, ld, inv, pst, c->dW.as<cplx>(), d_out, k0 > 0);
+            gnb_launch_weighted_sum(c->stream, m, N, A, strideA, lda, inv, pst, c->dW.as<cplx>(), d_out, k0 > 0);
             c->launches++;
         } else if (mode == MODE_T_DENSE) {
             const cplx *g1c, *g1b, *g2c, *g2b;
@@ -726,6 +778,27 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
     if (rc) return rc;
     const int N = c->N;
     const int n1 = c->contacts[ca].nc, n2 = c->contacts[cb].nc;
+    if (small_ok(c, true)) {
+        // N <= 119: one CTA per energy, G stays in shared memory and only T(E) is written (gnb_small.cu)
+        size_t per = 1024;
+        for (auto& ct : c->contacts) per += (size_t)ct.nc * ct.nc * 16 * 12;
+        const int Mc = chunk_size(c, std::max(M, 1), per);
+        for (int k0 = 0; k0 < M; k0 += Mc) {
+            const int m = std::min(Mc, M - k0);
+            if ((rc = put_chunk_scalars(c, E, nullptr, k0, m))) return rc;
+            const cplx* dE = c->dE.as<cplx>();
+            if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
+            GNB_CK(c->dT.ensure((size_t)m * sizeof(double)));
+            GnbSmallArgs sa = small_args(c, m, dE, true, nullptr, nullptr);
+            sa.mode = GNB_SMALL_T; sa.ca = ca; sa.cb = cb; sa.T = c->dT.as<double>();
+            gnb_launch_small(c->stream, sa);
+            c->launches++;
+            GNB_CK(cudaMemcpyAsync(T + k0, c->dT.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            GNB_CK(cudaGetLastError());
+            if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));
+        }
+        return end_call(c);
+    }
     Lay L = make_layout(N, n2);
     const int Np = L.Np;
     // Contacts-last ordering: with the orbitals of the two contacts moved to the end (symmetric permutation
@@ -914,15 +987,28 @@ extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, do
     const int Mc = chunk_size(c, std::max(M, 1), per);
     for (int k0 = 0; k0 < M; k0 += Mc) {
         const int m = std::min(Mc, M - k0);
-        if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;
-        cplx* A = c->A.as<cplx>();
-        if ((rc = run_eliminate(c, m, n, 0, A, (long)nn, n, 1))) return rc;
-        gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), n, n);
         cplx* G;
         if (loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(Aout) + (size_t)k0 * nn;
         else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
-        gnb_launch_unpermute(c->stream, m, n, A, (long)nn, n, c->invperm.as<int>(), n, G, (long)nn);
-        c->launches += 2;
+        if (g_small && n <= GNB_SMALL_MAX_N) {            // one CTA per matrix, in shared memory (gnb_small.cu)
+            const cplx* Araw = reinterpret_cast<const cplx*>(Ain) + (size_t)k0 * nn;
+            if (loc == GNB_HOST) {
+                if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;
+                Araw = c->A.as<cplx>();
+            }
+            GnbSmallArgs sa{};
+            sa.N = n; sa.M = m; sa.mode = GNB_SMALL_GREEN; sa.Araw = Araw; sa.info = c->info.as<int>();
+            sa.G = G; sa.strideG = (long)nn; sa.ldg = n;
+            gnb_launch_small(c->stream, sa);
+            c->launches++;
+        } else {
+            if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;
+            cplx* A = c->A.as<cplx>();
+            if ((rc = run_eliminate(c, m, n, 0, A, (long)nn, n, 1))) return rc;
+            gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), n, n);
+            gnb_launch_unpermute(c->stream, m, n, A, (long)nn, n, c->invperm.as<int>(), n, G, (long)nn);
+            c->launches += 2;
+        }
         if (loc == GNB_HOST)
             GNB_CK(cudaMemcpyAsync(Aout + (size_t)k0 * nn * 2, G, (size_t)m * nn * sizeof(cplx),
                                    cudaMemcpyDeviceToHost, c->stream));

@@ -92,6 +92,30 @@ int gnb_rec_real_enabled();
 long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long strideA, int ld, int jordan,
                        const GnbRecWork& ws);
 
+// gnb_small.cu : one CTA per energy, matrix resident in shared memory (N <= GNB_SMALL_MAX_N)
+#define GNB_SMALL_MAX_N 119            // N*(N|1)*16 B + bookkeeping <= 227 KB
+#define GNB_SMALL_MAX_CONTACTS 6
+enum { GNB_SMALL_GREEN = 0, GNB_SMALL_DOS = 1, GNB_SMALL_T = 2 };
+struct GnbSmallContact {
+    const int* inds; int nc;
+    const cplx* blk; long blk_stride;      // Sigma block per energy (stride 0: energy independent)
+    const cplx* gam; long gam_stride;      // Gamma block (mode T only)
+};
+struct GnbSmallArgs {
+    int N, M, mode;
+    const cplx *F, *S, *Sig0, *SigB; long strideSigB;   // Sig0: constant dense (or null); SigB: per energy (or null)
+    const cplx* E;
+    const cplx* Araw;                      // non-null: invert these [M][N][N] matrices instead of assembling
+    int ncontacts; GnbSmallContact ct[GNB_SMALL_MAX_CONTACTS];
+    cplx* G; long strideG; int ldg;        // GREEN
+    double* dos_tot; double* dos_site;     // DOS (dos_site may be null)
+    int ca, cb; double* T;                 // T
+    int* info;
+};
+cudaError_t gnb_small_init();
+int gnb_small_enabled();               // developer switch "small_fused" (gnb_api.cu)
+void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a);
+
 // gnb_reduce.cu
 void gnb_launch_invperm(cudaStream_t st, int M, const int* perm, int* invperm, int stride, int N);
 void gnb_launch_weighted_sum(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld,

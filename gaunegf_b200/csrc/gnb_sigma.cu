@@ -100,6 +100,15 @@ __global__ void k_chain_export(const ChainFlags* f, const double* diffs, int M, 
 
 static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
     int rc;
+    if (gnb_small_enabled() && nc <= GNB_SMALL_MAX_N) {      // one CTA per matrix, in shared memory (gnb_small.cu)
+        GnbSmallArgs sa{};
+        sa.N = nc; sa.M = M; sa.mode = GNB_SMALL_GREEN; sa.Araw = Min; sa.info = c->info.as<int>();
+        sa.G = Gout; sa.strideG = (long)nc * nc; sa.ldg = nc;
+        gnb_launch_small(c->stream, sa);
+        c->launches++;
+        GNB_CK(cudaGetLastError());
+        return GNB_OK;
+    }
     GnbElimWork w = gnb_elim_work(c, M, nc, true, &rc);
     if (rc) return rc;
     const long nn = (long)nc * nc;

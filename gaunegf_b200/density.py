@@ -5,8 +5,8 @@ builds them; every batch of energies is evaluated on the B200 through integrate.
 import numpy as np
 from scipy.special import roots_legendre
 
-from .config import (TEMPERATURE, ADAPTIVE_INTEGRATION_TOL, FERMI_CALCULATION_TOL, N_KT, MAX_CYCLES,
-                     MAX_GRID_POINTS)
+from .config import (TEMPERATURE, ADAPTIVE_INTEGRATION_TOL, FERMI_CALCULATION_TOL, FERMI_SEARCH_CYCLES, N_KT,
+                     ENERGY_MIN, MAX_CYCLES, MAX_GRID_POINTS)
 from .integrate import GrInt, GrLessInt
 from ._native import default_context
 from .sigma_plan import ObjectPlan, DESC, DENSE_CONST
@@ -14,6 +14,7 @@ from .sigma_plan import ObjectPlan, DESC, DENSE_CONST
 # CONSTANTS (density.py:59-61)
 har_to_eV = 27.211386   # eV/Hartree
 kB = 8.617e-5           # eV/Kelvin
+FERMI_DEBUG = False     # density.py:57
 
 
 def fermi(E, mu, T):
@@ -248,3 +249,362 @@ def calcEmin(F, S, g, tol=FERMI_CALCULATION_TOL, maxN=MAX_CYCLES):
         print(f'Warning: Emin still not within tolerance (final value = {dP}) after {maxN} energy samples')
     print(f'Calculated Emin: {Emin} eV, DOS = {dP:.2E}')
     return Emin
+
+
+# ---- grid fits and Fermi-level searches (density.py:836-1515) ------------------
+# Host-side root finding over the GPU drivers above: every probe of the electron count is one
+# contour integral (densityComplexN -> integrate.GrInt -> one batched launch sequence on the B200).
+def _diag_change(new, old):
+    return max(abs(np.diag(new - old)))
+
+
+def _doubling_fit(evaluate, start, tol, cap, report):
+    """Double the point count until the largest change of a diagonal density element is <= tol
+    (the loop shared by integralFit / integralFitNEGF, density.py:878-913, 949-964).  Returns the
+    last count that was still needed (the converged count halved), as the reference does."""
+    n, change, prev = start, np.inf, None
+    while change > tol and n < cap:
+        n *= 2
+        cur = evaluate(n)
+        change = _diag_change(cur, 0 * cur if prev is None else prev)
+        report(change, cur)
+        prev = cur
+    return n, change
+
+
+def integralFit(F, S, g, mu, Eminf=ENERGY_MIN, tol=FERMI_CALCULATION_TOL, T=TEMPERATURE, maxN=MAX_CYCLES):
+    """(Emin, N1, N2): contour start from the DOS tail, then the number of complex-contour and of real-axis
+    points needed for `tol` on the density diagonal (density.py:836-914)."""
+    Emin = calcEmin(F, S, g, tol, maxN)
+
+    Ncomplex, dP = _doubling_fit(lambda n: np.real(densityComplexN(F, S, g, Emin, mu, n, T=T)), 4, tol, maxN,
+                                 lambda d, rho: print(f"MaxDP = {d:.2E}, N = {sum(np.diag(rho).real):2f}"))
+    if dP < tol:
+        Ncomplex /= 2
+    elif Ncomplex >= maxN and dP > tol:
+        print(f'Warning: Ncomplex still not within tolerance (final value = {dP})')
+    print(f'Final Ncomplex: {Ncomplex}')
+
+    Nreal, dP = _doubling_fit(lambda n: np.real(densityRealN(F, S, g, Eminf, Emin, n, T=0)), 8, tol, maxN,
+                              lambda d, rho: print(f"MaxDP = {d:.2E}"))
+    if dP < tol:
+        Nreal /= 2
+    elif Nreal >= maxN and dP > tol:
+        print(f'Warning: Nreal still not within tolerance (final value = {dP})')
+    print(f'Final Nreal: {Nreal}')
+    return Emin, Ncomplex, Nreal
+
+
+def integralFitNEGF(F, S, g, fermi, qV, Eminf=ENERGY_MIN, tol=FERMI_CALCULATION_TOL, T=TEMPERATURE,
+                    maxGrid=MAX_GRID_POINTS):
+    """Number of real-axis points for the non-equilibrium window integrals (density.py:916-964)."""
+    def both_windows(n):
+        rho = np.real(densityGridN(F, S, g, fermi, fermi + (qV / 2), ind=0, N=n, T=T))
+        return rho + np.real(densityGridN(F, S, g, fermi, fermi - (qV / 2), ind=-1, N=n, T=T))
+
+    N, dP = _doubling_fit(both_windows, 8, tol, maxGrid, lambda d, rho: print(f"MaxDP = {d:.2E}"))
+    if dP < tol:
+        N /= 2
+    elif N >= maxGrid and dP > tol:
+        print(f'Warning: N still not within tolerance (final value = {dP})')
+    print(f'Final Nnegf: {N}')
+    return N
+
+
+def _electrons(P, S, nOrbs=0):
+    PS = P @ S
+    return np.trace(PS if nOrbs == 0 else PS[-nOrbs:, -nOrbs:])
+
+
+def _mid_gap(F, S, ne, per_cell=1, hermitian=False):
+    """sorted real eigenvalues of inv(S) F and the middle of the gap above orbital per_cell*ne"""
+    M = np.linalg.solve(np.asarray(S), np.eye(len(S))) @ np.asarray(F)
+    orbs = np.sort(np.real(np.linalg.eigvalsh(M) if hermitian else np.linalg.eigvals(M)))
+    k = per_cell * int(ne)
+    return orbs, (orbs[k - 1] + orbs[k]) / 2
+
+
+def getFermiContact(g, ne, tol=FERMI_CALCULATION_TOL, Eminf=ENERGY_MIN, maxcycles=MAX_CYCLES, T=TEMPERATURE,
+                    nOrbs=0):
+    """Fermi energy of a contact treated as its own system (density.py:967-1003)."""
+    S, F = g.S, g.F
+    orbs, fermi_guess = _mid_gap(F, S, ne)
+    Emin, N1, N2 = integralFit(F, S, g, fermi_guess, Eminf, tol, T, maxN=maxcycles)
+    return calcFermi(g, ne, Emin, max(orbs), fermi_guess, N1, N2, Eminf, T, tol, maxcycles, nOrbs)[0]
+
+
+def getFermi1DContact(gSys, ne, ind=0, tol=FERMI_CALCULATION_TOL, Eminf=ENERGY_MIN, T=TEMPERATURE,
+                      maxcycles=MAX_CYCLES):
+    """(fermi, Emin, N1, N2) of the periodic chain behind contact `ind` of a surfG1D system
+    (density.py:1005-1053): integration parameters from a two-cell model, search on the one-cell contact."""
+    from .surfG1D import surfG
+    F, S = gSys.aList[ind], gSys.aSList[ind]
+    tau, stau = gSys.bList[ind], gSys.bSList[ind]
+    inds = np.arange(len(F))
+    g = surfG(F, S, [inds], [tau], [stau], eta=1e-6)
+    F2 = np.block([[F, tau], [tau.conj().T, F]])
+    S2 = np.block([[S, stau], [stau.T, S]])
+    g2 = surfG(F2, S2, [inds], [tau], [stau], eta=1e-6)
+    orbs, fermi_guess = _mid_gap(F2, S2, ne, per_cell=2, hermitian=True)
+    Emin, N1, N2 = integralFit(F2, S2, g2, fermi_guess, Eminf, tol, T, maxN=maxcycles)
+    return calcFermi(g, ne, Emin, max(orbs), fermi_guess, N1, N2, Eminf, T, tol, maxcycles)
+
+
+def calcFermi(g, ne, Emin, Emax, fermiGuess=0, N1=100, N2=50, Eminf=ENERGY_MIN, T=TEMPERATURE,
+              tol=FERMI_CALCULATION_TOL, maxcycles=MAX_CYCLES, nOrbs=0):
+    """Bisection on the electron count of the contact's own system between Emin and Emax
+    (density.py:1056-1143).  With N1/N2 = None the reference passes keywords its adaptive drivers do not
+    accept and raises; here those branches run the adaptive drivers."""
+    dos_eminf = _compute_dos_at_energy(Eminf, g.F, g.S, g.sigmaTot(Eminf))
+    print(f'Eminf DOS = {dos_eminf}')
+
+    def below(Tlow):
+        if N2 is None:
+            return _quiet(densityReal, g.F, g.S, g, Eminf, Emin, tol, Tlow)
+        return densityRealN(g.F, g.S, g, Eminf, Emin, N2, Tlow, showText=False)
+
+    def contour(mu):
+        if N1 is None:
+            return _quiet(densityComplex, g.F, g.S, g, Emin, mu, tol, T)
+        return densityComplexN(g.F, g.S, g, Emin, mu, N1, T, showText=False, method='legendre')
+
+    fermi = fermiGuess
+    nELow = _electrons(below(T), g.S, nOrbs)
+    print(f'Electrons below lowest onsite energy: {nELow}')
+    if nELow >= ne:
+        raise Exception('Calculated Fermi energy is below lowest orbital energy!')
+    Ncurr, counter, lBound, uBound = -1, 0, Emin, Emax
+    print('Calculating Fermi energy using bisection:')
+    while abs(ne - Ncurr) > tol and uBound - lBound > tol / 10 and counter < maxcycles:
+        g.setF(g.F, fermi, fermi)
+        Ncurr = _electrons(np.real(below(0) + contour(fermi)), g.S, nOrbs)
+        dN = ne - Ncurr
+        if dN > 0 and fermi > lBound:
+            lBound = fermi
+        elif dN < 0 and fermi < uBound:
+            uBound = fermi
+        if abs(ne - Ncurr) > tol:
+            fermi = (uBound + lBound) / 2
+        print("DN:", dN, "Fermi:", fermi, "Bounds:", lBound, uBound)
+        counter += 1
+    if abs(ne - Ncurr) > tol and counter > maxcycles:
+        print(f'Warning: Fermi energy still not within tolerance! Ef = {fermi:.2f} eV, N = {Ncurr:.2f})')
+    print(f'Finished after {counter} iterations, Ef = {fermi:.2f}')
+    return fermi, Emin, N1, N2
+
+
+def _quiet(f, *a, **k):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+def _contour_density(g, Emin, N, tol, T):
+    """P(mu) used by the device-level searches: fixed N-point contour, or the adaptive one for N = None"""
+    assert_n = len(g.F)
+    if N is None:
+        return assert_n, (lambda mu: densityComplex(g.F, g.S, g, Emin, mu, tol, T))
+    return assert_n, (lambda mu: densityComplexN(g.F, g.S, g, Emin, mu, N, T))
+
+
+def _probe(g, pMu, mu):
+    """move the contacts to mu, integrate, count electrons"""
+    g.setF(g.F, mu, mu)
+    P = pMu(mu)
+    return P, np.trace(P @ g.S).real
+
+
+def _track(bounds, E, n):
+    """bracket bookkeeping of the Muller / PolyFit searches: n = N(E) - ne"""
+    u, l = bounds
+    if n > 0:
+        u = E if u is None else min(u, E)
+    elif n < 0:
+        l = E if l is None else max(l, E)
+    return u, l
+
+
+def calcFermiBisect(g, ne, Emin, Ef, N, tol=ADAPTIVE_INTEGRATION_TOL, conv=FERMI_CALCULATION_TOL,
+                    maxcycles=FERMI_SEARCH_CYCLES, T=TEMPERATURE, uBound=None, lBound=None):
+    """Bracket-then-bisect search (density.py:1145-1201) -> (Ef, dE, P).  The bracket expansion sizes its steps
+    from a DOS sample that the reference takes with F and S exchanged (density.py:1176, SURVEY.md appendix
+    A.5); that call is reproduced as it is, because it decides which energies are visited."""
+    nbf, pMu = _contour_density(g, Emin, N, tol, T)
+    assert ne < nbf, "Number of electrons cannot exceed number of basis functions!"
+    E = Ef + 0.0
+    dE = tol
+    counter = 0
+    P, Ncurr = _probe(g, pMu, E)
+    while None in [uBound, lBound] and counter < maxcycles:
+        if Ncurr > ne:
+            uBound = E + 0.0
+            Ef = uBound
+            E -= dE
+        if Ncurr < ne:
+            lBound = E + 0.0
+            Ef = lBound
+            E += dE
+        if FERMI_DEBUG:
+            print(f"DEBUG: Ef={Ef:.2f}, dN={ne-Ncurr:.2E}, dE={dE:.2E}")
+        dos = _compute_dos_at_energy(E, g.S, g.F, g.sigmaTot(E))
+        dE = max(2 * abs(Ncurr - ne) / dos, dE)
+        counter += 1
+        P, Ncurr = _probe(g, pMu, E)
+    while abs(ne - Ncurr) > conv and counter < maxcycles and uBound != lBound:
+        dN = ne - Ncurr
+        if dN > 0 and Ef > lBound:
+            lBound = Ef + 0.0
+        elif dN < 0 and Ef < uBound:
+            uBound = Ef + 0.0
+        Ef = (uBound + lBound) / 2
+        dE = uBound - lBound
+        if FERMI_DEBUG:
+            print(f"DEBUG: Ef={Ef:.2f}, dN={dN:.2E}, dE={dE:.2E}")
+        counter += 1
+        if abs(dN) > conv:
+            g.setF(g.F, Ef, Ef)
+            P = pMu(Ef)
+            Ncurr = np.trace(P @ g.S)
+    if counter == maxcycles:
+        print(f'Warning: Max cycles reached, convergence = {abs(Ncurr-ne):.2E}')
+    elif uBound == lBound:
+        print(f'Warning: Bisection failed, convergence = {abs(Ncurr-ne):.2E}')
+    return Ef, dE, P
+
+
+def calcFermiSecant(g, ne, Emin, Ef, N, tol=ADAPTIVE_INTEGRATION_TOL, conv=FERMI_CALCULATION_TOL,
+                    maxcycles=FERMI_SEARCH_CYCLES, T=TEMPERATURE):
+    """Secant search on N(mu) - ne (density.py:1203-1238) -> (Ef, dE, P, |N - ne|)."""
+    nbf, pMu = _contour_density(g, Emin, N, tol, T)
+    assert ne < nbf, "Number of electrons cannot exceed number of basis functions!"
+    P, nCurr = _probe(g, pMu, Ef)
+    dE = conv
+    counter = 0
+    while abs(nCurr - ne) > conv and counter < maxcycles:
+        Ef += dE
+        P, nNext = _probe(g, pMu, Ef)
+        if FERMI_DEBUG:
+            print(f"DEBUG: Ef={Ef:.2f}, dN={nNext-ne:.2E}, dE={dE:.2E}")
+        counter += 1
+        if abs(nNext - nCurr) < 1e-10:
+            print('Warning: change in ne low, reducing step size')
+            dE *= 0.1
+            continue
+        dE = dE * ((ne - nCurr) / (nNext - nCurr)) - dE
+        nCurr = nNext + 0.0
+    Ef += dE
+    if counter == maxcycles:
+        print(f'Warning: Max cycles reached, convergence = {abs(nCurr-ne):.2E}')
+    return Ef, dE, P, abs(nCurr - ne)
+
+
+def calcFermiMuller(g, ne, Emin, Ef, N, tol=ADAPTIVE_INTEGRATION_TOL, conv=FERMI_CALCULATION_TOL,
+                    maxcycles=FERMI_SEARCH_CYCLES, T=TEMPERATURE):
+    """Muller's method (parabola through the last three probes) on N(mu) - ne (density.py:1240-1331)
+    -> (Ef, dE, P, |N - ne|, uBound, lBound)."""
+    nbf, pMu = _contour_density(g, Emin, N, tol, T)
+    assert ne < nbf, "Number of electrons cannot exceed number of basis functions!"
+    pts = [Ef, Ef - conv, Ef + conv]          # E2 (newest), E1, E0
+    vals, bounds = [], (None, None)
+    for E in pts:
+        P, cnt = _probe(g, pMu, E)
+        n = cnt - ne
+        bounds = _track(bounds, E, n)
+        if abs(n) < conv:
+            return E, 0, P, abs(n), bounds[0], bounds[1]
+        vals.append(n)
+    (E2, E1, E0), (n2, n1, n0) = pts, vals
+    counter = 3
+    while counter < maxcycles:
+        h0, h1 = E0 - E2, E1 - E2
+        d0, d1 = n0 - n2, n1 - n2
+        det = h0 * h1 * (h0 - h1)
+        a = (d0 * h1 - h0 * d1) / det
+        b = (h0 * h0 * d1 - h1 * h1 * d0) / det
+        disc = np.sqrt(b * b - 4 * a * n2) if b * b > 4 * a * n2 else 0
+        if b < 0:
+            disc = -disc
+        dE = -2 * n2 / (b + disc)
+        Enext = E2 + dE
+        if abs(Enext - E1) < abs(Enext - E0):     # keep the two old points that are nearest to the new one
+            E0, E1, n0, n1 = E1, E0, n1, n0
+        if abs(Enext - E2) < abs(Enext - E1):
+            E1, n1 = E2, n2
+        E2 = Enext
+        P, cnt = _probe(g, pMu, E2)
+        n2 = cnt - ne
+        bounds = _track(bounds, E2, n2)
+        if abs(n2) < conv:
+            break
+        if FERMI_DEBUG:
+            print(f"DEBUG: Ef={E2:.2f}, dN={n2:.2E}, dE={dE:.2E}")
+        counter += 1
+    if counter == maxcycles:
+        print(f'Warning: Max cycles reached, convergence = {abs(n2):.2E}')
+    return E2, dE, P, abs(n2), bounds[0], bounds[1]
+
+
+def calcFermiPolyFit(g, ne, Emin, Ef, N, tol=ADAPTIVE_INTEGRATION_TOL, conv=FERMI_CALCULATION_TOL,
+                     maxcycles=FERMI_SEARCH_CYCLES, T=TEMPERATURE, order=3):
+    """Root of a Huber-robust polynomial fit through all probes so far, smoothed by a shape-preserving
+    PCHIP interpolant (density.py:1333-1515) -> (Ef, dE, P, |N - ne|, uBound, lBound)."""
+    from scipy.interpolate import PchipInterpolator
+    from scipy.optimize import least_squares
+    nbf, pMu = _contour_density(g, Emin, N, tol, T)
+    assert ne < nbf, "Number of electrons cannot exceed number of basis functions!"
+    bounds = (None, None)
+    E = Ef
+    P, cnt = _probe(g, pMu, E)
+    n = cnt - ne
+    if abs(n) < conv:
+        return E, 0, P, abs(n), None, None
+    Es, ns = [E], [n]
+    step, n_first, counter = conv * 10, n, 1
+    while counter < maxcycles:                    # second probe far enough above the first to see N rise
+        E = Ef + step
+        P, cnt = _probe(g, pMu, E)
+        n = cnt - ne
+        bounds = _track(bounds, E, n)
+        if abs(n) < conv:
+            return E, step, P, abs(n), bounds[0], bounds[1]
+        if n - n_first > 0:
+            break
+        step *= 10
+        counter += 1
+        if FERMI_DEBUG:
+            print(f'Warning: Tried Ef = {E:2f} eV (too close to {Ef:2f} to get accurate dN {n-n_first:.2E})')
+    Es.append(E)
+    ns.append(n)
+    dE = step
+    while counter < maxcycles:
+        deg = min(len(ns) - 1, order)
+        Esort, nsort = zip(*sorted(zip(Es, ns)))
+        smooth = PchipInterpolator(Esort, nsort)(Es)
+        fit = least_squares(lambda cf: np.polyval(cf, Es) - smooth, np.polyfit(Es, ns, deg), loss='huber',
+                            f_scale=ADAPTIVE_INTEGRATION_TOL)
+        roots = np.roots(fit.x)
+        E_next = roots[np.argmin(np.abs(roots - Es[-1]))].real
+        wrong_way = (ns[-1] > 0 and E_next > Es[-1]) or (ns[-1] < 0 and E_next < Es[-1])
+        if wrong_way:                             # N(mu) must rise with mu: drop the probe, step 10 dE the right way
+            E_next = Es[-1] - abs(dE) * 10 if ns[-1] > 0 else Es[-1] + abs(dE) * 10
+            Es.pop()
+            ns.pop()
+            counter -= 1
+            if FERMI_DEBUG:
+                print('Warning: monotonicity exception corrected!')
+        E = E_next
+        P, cnt = _probe(g, pMu, E)
+        n = cnt - ne
+        bounds = _track(bounds, E, n)
+        Es.append(E)
+        ns.append(n)
+        dE = E - Es[-2]
+        if abs(n) < conv:
+            break
+        if FERMI_DEBUG:
+            print(f"Iter {counter}: E = {E:.6f}, n-ne = {n:.3e}, dE = {dE:.3e}, order = {deg}")
+        counter += 1
+    if counter >= maxcycles:
+        print(f'Warning: Max cycles reached, convergence = {abs(n):.2E}')
+    return E, dE, P, abs(n), bounds[0], bounds[1]

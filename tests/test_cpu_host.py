@@ -163,3 +163,17 @@ def test_energy_sharding_two_gloo_ranks(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+def test_n2_fermi_search_host_logic(golden, monkeypatch):
+    """the grid fits and Fermi searches are host root finding over the GPU drivers.  With the
+    drivers replaced by the numpy oracle the host logic must reproduce the reference's answers
+    (tests/golden/n2_fermi.npz, made by the unmodified reference)."""
+    import gaunegf_b200.density as D
+    from gaunegf_b200.surfGTester import surfGTest
+    from oracle import negf_oracle as O
+    from n2_cases import run_cases, compare
+    monkeypatch.setattr(D, "GrInt", O.GrInt)
+    monkeypatch.setattr(D, "GrLessInt", O.GrLessInt)
+    monkeypatch.setattr(D, "_compute_dos_at_energy", O.compute_dos_at_energy)
+    compare(run_cases(D, surfGTest, None), golden("n2_fermi"), 1e-9)

@@ -254,3 +254,14 @@ def test_utils_inv_and_size_independent_properties():
     s1, s2 = sy.block_sigma_vectors(N, 32, 0.1)
     T = tr.calculate_transmission(F, S, tr.SigmaCalculator(s1, s2), np.linspace(-1, 1, 64))
     assert np.all(T > -1e-12) and np.all(np.isfinite(T))
+
+
+def test_n2_fermi_searches(golden):
+    """SURVEY §8(f) N2 on the GPU path: integralFit / integralFitNEGF / calcFermi* / getFermi*Contact against the
+    unmodified reference's answers.  The searches divide integral differences by the DOS, so 1e-10 on the
+    integrals becomes <= 1e-8 on the located energies; point counts and brackets must match exactly."""
+    import gaunegf_b200.density as D
+    from gaunegf_b200.surfGTester import surfGTest
+    from gaunegf_b200.surfG1D import surfG
+    from n2_cases import run_cases, compare
+    compare(run_cases(D, surfGTest, surfG), golden("n2_fermi"), 1e-8)
