@@ -608,3 +608,39 @@ def calcFermiPolyFit(g, ne, Emin, Ef, N, tol=ADAPTIVE_INTEGRATION_TOL, conv=FERM
     if counter >= maxcycles:
         print(f'Warning: Max cycles reached, convergence = {abs(n):.2E}')
     return E, dE, P, abs(n), bounds[0], bounds[1]
+
+
+# ---- energy-INDEPENDENT analytic density (density.py:276-382) -----------------------
+# No energy grid: with a constant self-energy the integral of G Gamma G^+ has a closed form in the eigenbasis of
+# the (non-Hermitian) effective Hamiltonian.  Setup-time host linear algebra, one N x N eigenproblem per call site.
+def density(V, Vc, D, Gam, Emin, mu):
+    """Closed-form integral_{Emin}^{mu} G Gamma G^+ dE / 2 pi for an energy-independent Gamma (Eq. 27 of
+    PRB 65, 165401; density.py:276-329).  V, D: eigenvectors / eigenvalues of the effective Hamiltonian in the
+    orthogonalised basis, Vc = inv(V)^H."""
+    D = np.asarray(D)
+
+    def log_difference(limit):                    # log(1 - limit/D_i) - conj(log(1 - limit/D_j))
+        lg = np.emath.log(1 - (limit / D))
+        return lg[:, None] - lg.conj()[None, :]
+
+    weights = (log_difference(mu) - log_difference(Emin)) / (2 * np.pi * (D[:, None] - D.conj()[None, :]))
+    return V @ (weights * (Vc.conj().T @ Gam @ Vc)) @ V.conj().T
+
+
+def bisectFermi(V, Vc, D, Gam, Nexp, conv=FERMI_CALCULATION_TOL, Eminf=ENERGY_MIN):
+    """Chemical potential at which the analytic density holds Nexp electrons, by bisection between the lowest
+    and highest eigenvalue (density.py:331-382)."""
+    lo, hi = min(D.real), max(D.real)
+    dN, Niter = Nexp, 0
+    while abs(dN) > conv and Niter < 1000:
+        fermi_level = (lo + hi) / 2
+        dN = np.trace(density(V, Vc, D, Gam, Eminf, fermi_level)).real - Nexp
+        if dN > 0:
+            hi = fermi_level
+        else:
+            lo = fermi_level
+        Niter += 1
+    if Niter >= 1000:
+        print('Warning: Bisection search timed out after 1000 iterations!')
+    print(f'Bisection fermi search converged to {dN:.2E} in {Niter} iterations.')
+    return fermi_level

@@ -102,3 +102,15 @@ def contour_points(n, Emin=-30.0, mu=0.0):
     dz = 1j * r * np.exp(1j * theta)
     occ = (z <= mu) * 1
     return z, (np.pi / 2) * w * occ * dz
+
+
+def analytic_density_case(N, seed=5, nc=4):
+    """Inputs of the energy-independent analytic density (density.py:276-329): eigenvectors V, Vc = inv(V)^H and
+    eigenvalues D of X^H (F + Sigma) X with constant contact self-energies, and Gamma in the same basis."""
+    F, S = hermitian_pair(N, seed=seed)
+    X = np.linalg.inv(np.linalg.cholesky(S)).conj().T
+    sig = np.zeros((N, N), dtype=complex)
+    sig[:nc, :nc] = -0.1j * np.eye(nc)
+    sig[-nc:, -nc:] = -0.2j * np.eye(nc)
+    D, V = np.linalg.eig(X.conj().T @ (F + sig) @ X)
+    return V, np.linalg.inv(V).conj().T, D, X.conj().T @ (1j * (sig - sig.conj().T)) @ X

@@ -60,6 +60,11 @@ Fc, Sc, li, taus = sy.lead_device_lead(6, 12, seed=4, s_off=0.03)
 gs = s1d.surfG(Fc, Sc, [list(i) for i in li], [list(t) for t in taus], eta=1e-4)
 out["getFermi1DContact"] = scal(quiet(de.getFermi1DContact, gs, 3, 0, 1e-3, -1e6, 0.0, 30))
 
+# N4: energy-independent analytic density + bisectFermi (density.py:276-382)
+V4, Vc4, D4, Gam4 = sy.analytic_density_case(30, seed=5)
+out["n4_density"] = de.density(V4, Vc4, D4, Gam4, -50.0, 0.1)
+out["n4_bisectFermi"] = np.array([quiet(de.bisectFermi, V4, Vc4, D4, Gam4, 12.0)])
+
 path = os.path.join(HERE, "n2_fermi.npz")
 np.savez_compressed(path, **out)
 print(f"n2_fermi: {os.path.getsize(path) / 1024:.1f} KiB")

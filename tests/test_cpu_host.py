@@ -177,3 +177,16 @@ def test_n2_fermi_search_host_logic(golden, monkeypatch):
     monkeypatch.setattr(D, "GrLessInt", O.GrLessInt)
     monkeypatch.setattr(D, "_compute_dos_at_energy", O.compute_dos_at_energy)
     compare(run_cases(D, surfGTest, None), golden("n2_fermi"), 1e-9)
+
+
+def test_n4_analytic_density(golden):
+    """closed-form density for constant self-energies + its bisection (host numpy)"""
+    import contextlib, io
+    from gaunegf_b200 import density as D
+    G = golden("n2_fermi")
+    V, Vc, Dv, Gam = sy.analytic_density_case(30, seed=5)
+    P = D.density(V, Vc, Dv, Gam, -50.0, 0.1)
+    assert np.max(np.abs(P - G["n4_density"])) < 1e-10 * np.max(np.abs(G["n4_density"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        mu = D.bisectFermi(V, Vc, Dv, Gam, 12.0)
+    assert abs(mu - G["n4_bisectFermi"][0]) < 1e-9
