@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(NT) k_small_gj(const GnbSmallArgs a) {
     cplx* Am = reinterpret_cast<cplx*>(sm_raw);
     int* rowsrc = reinterpret_cast<int*>(Am + (size_t)N * ld);
     int* q = rowsrc + N;
-    double* red = reinterpret_cast<double*>(q + N + (N & 1));      // [NT/32] (8-byte aligned)
+    double* red = reinterpret_cast<double*>(q + N);                // [NT/32] (2N ints: 8-byte aligned)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr int NW = NT / 32;
     const int e = blockIdx.x;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NT) k_small_gj(const GnbSmallArgs a) {
 
 size_t small_smem(int N, int nt) {
     const int ld = N | 1;
-    return (size_t)N * ld * sizeof(cplx) + (size_t)(2 * N + (N & 1)) * sizeof(int) + (size_t)(nt / 32) * sizeof(double);
+    return (size_t)N * ld * sizeof(cplx) + (size_t)(2 * N) * sizeof(int) + (size_t)(nt / 32) * sizeof(double);
 }
 
 }  // namespace

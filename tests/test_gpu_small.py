@@ -85,12 +85,12 @@ def test_small_overlapping_contacts_and_chunks(ctx):
     ctx.sigma_add_const_block(i2, b2)
     s1 = np.zeros((N, N), complex); s1[np.ix_(i1, i1)] = b1
     s2 = np.zeros((N, N), complex); s2[np.ix_(i2, i2)] = b2
-    E = np.linspace(-1, 1, 333)
+    E = np.linspace(-1, 1, 3000)
     T = ctx.transmission(E, 0, 1)
     g1, g2 = 1j * (s1 - s1.conj().T), 1j * (s2 - s2.conj().T)
     Tref = np.array([O.transmission_restricted(e, F, S, s1 + s2, g1, g2) for e in E])
     assert np.allclose(T, Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
-    ctx.set_workspace_limit(1 << 20)
+    ctx.set_workspace_limit(64 << 20)          # -> 3 chunks of the energy list
     try:
         T2 = ctx.transmission(E, 0, 1)
         d2 = ctx.dos(E)[0]
