@@ -24,7 +24,7 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
 static int g_mixed_layout = 1;    // transmission: store the real columns as doubles (mixed layout, gnb_rec.cu)
 static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
-static int g_small = 1;           // N <= GNB_SMALL_MAX_N: one CTA per energy, matrix in shared memory (gnb_small.cu)
+static int g_small = 1;           // N <= gnb_small_max_n(): one CTA per energy, matrix on chip (gnb_small.cu)
 int gnb_small_enabled() { return g_small; }
 static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
 
@@ -103,6 +103,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
     else if (!strcmp(name, "small_fused")) g_small = value;
+    else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
@@ -531,7 +532,7 @@ static int put_chunk_scalars(gnb_ctx* c, const double* E, const double* w, int k
 
 // Small-orbital-count path (gnb_small.cu): is it usable for this call, and the common part of its arguments
 static bool small_ok(const gnb_ctx* c, bool use_desc) {
-    return g_small && c->N <= GNB_SMALL_MAX_N && (!use_desc || c->contacts.size() <= GNB_SMALL_MAX_CONTACTS);
+    return g_small && c->N <= gnb_small_max_n() && (!use_desc || c->contacts.size() <= GNB_SMALL_MAX_CONTACTS);
 }
 static GnbSmallArgs small_args(gnb_ctx* c, int m, const cplx* dE, bool use_desc, const cplx* sig_const,
                                const cplx* sig_batch) {
@@ -779,7 +780,7 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
     const int N = c->N;
     const int n1 = c->contacts[ca].nc, n2 = c->contacts[cb].nc;
     if (small_ok(c, true)) {
-        // N <= 119: one CTA per energy, G stays in shared memory and only T(E) is written (gnb_small.cu)
+        // N <= 96: one CTA per energy, G stays on chip and only T(E) is written (gnb_small.cu)
         size_t per = 1024;
         for (auto& ct : c->contacts) per += (size_t)ct.nc * ct.nc * 16 * 12;
         const int Mc = chunk_size(c, std::max(M, 1), per);
@@ -990,7 +991,7 @@ extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, do
         cplx* G;
         if (loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(Aout) + (size_t)k0 * nn;
         else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
-        if (g_small && n <= GNB_SMALL_MAX_N) {            // one CTA per matrix, in shared memory (gnb_small.cu)
+        if (g_small && n <= gnb_small_max_n()) {          // one CTA per matrix, on chip (gnb_small.cu)
             const cplx* Araw = reinterpret_cast<const cplx*>(Ain) + (size_t)k0 * nn;
             if (loc == GNB_HOST) {
                 if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;

@@ -100,7 +100,7 @@ __global__ void k_chain_export(const ChainFlags* f, const double* diffs, int M, 
 
 static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
     int rc;
-    if (gnb_small_enabled() && nc <= GNB_SMALL_MAX_N) {      // one CTA per matrix, in shared memory (gnb_small.cu)
+    if (gnb_small_enabled() && nc <= gnb_small_max_n()) {    // one CTA per matrix, on chip (gnb_small.cu)
         GnbSmallArgs sa{};
         sa.N = nc; sa.M = M; sa.mode = GNB_SMALL_GREEN; sa.Araw = Min; sa.info = c->info.as<int>();
         sa.G = Gout; sa.strideG = (long)nc * nc; sa.ldg = nc;

@@ -1,21 +1,33 @@
-// Small-orbital-count path: ONE CTA per energy point, the whole matrix in shared memory.
+// Small-orbital-count path: ONE CTA per energy point, the whole matrix on chip (BASELINE cfg 1: N = 64).
 //
-// For N <= GNB_SMALL_MAX_N (119: N*(N|1)*16 B + bookkeeping fits the 227 KB of one sm_100a CTA) the kernel
-// assembles A = E S - F - Sigma0 - Sigma_k(E) in shared memory, inverts it in place with a partially pivoted
-// Gauss-Jordan elimination (every warp finds the pivot of a column redundantly with warp shuffles, so there is no
-// broadcast step; two CTA barriers per column), and reduces G = A^-1 on chip:
+// The kernels assemble A = E S - F - Sigma0 - Sigma_k(E), invert it in place with a pivoted Gauss-Jordan
+// elimination and reduce G = A^-1 without leaving the SM:
 //   mode GREEN : G written out (consumers that need the whole matrix, utils.inv / integrate.py:67-71)
 //   mode DOS   : -Im diag(G)/pi per orbital and its sum (transport.py:183-190)
-//   mode T     : Re Tr[Gamma1 G Gamma2 G^H] from the contact blocks of G only (transport.py:150-157); G never leaves
-//                the SM.
-// Replaces assemble + tournament-pivoted block elimination + reduction launches of the lock-step engines, whose
-// per-launch parallelism (energies x 32-column blocks) is too thin at these sizes (BASELINE cfg 1: N = 64).
+//   mode T     : Re Tr[Gamma1 G Gamma2 G^H] from the contact block G[C1, C2] only (transport.py:150-157)
+// so a whole cohTrans / DOS call is ONE launch instead of assemble + (tournament, panel, update) x N/32 + reductions.
+//
+//   k_reg_gj   (N <= 96, default): matrix in REGISTERS, a column spread over the lanes of one warp, pivot search by
+//              warp REDUX/shuffle in the owning warp, one CTA barrier per column, pure-FMA register-tile update.
+//   k_small_gj (N <= 119, developer switch small_reg=0): matrix in SHARED MEMORY (N*(N|1)*16 B + bookkeeping fits
+//              the 227 KB of one sm_100a CTA), every warp finds the pivot redundantly, two barriers per column.  Every
+//              step reads and writes the whole matrix through shared memory, which bounds it at ~3.5 TFLOP/s; the
+//              lock-step block engine is faster at those sizes (profiles/r01_small_probe.json), so it is not a default.
+#include <algorithm>
+#include <type_traits>
 #include "gnb_common.cuh"
 #include "gnb_kernels.h"
 
 namespace {
 
 constexpr double kInvPi = 0.31830988618379067154;
+
+// 1 / v = conj(v) / |v|^2 with one hardware-seeded reciprocal (MUFU.RCP64H + Newton steps) instead of the three
+// IEEE divisions of Smith's algorithm: the reciprocal pivot sits on the critical path of every elimination step.
+__device__ __forceinline__ cplx crcp_fast(cplx v) {
+    const double inv = __drcp_rn(fma(v.x, v.x, v.y * v.y));
+    return cmake(v.x * inv, -v.y * inv);
+}
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_small_gj(const GnbSmallArgs a) {
@@ -76,7 +88,7 @@ __global__ void __launch_bounds__(NT) k_small_gj(const GnbSmallArgs a) {
             if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
         }
         if (best == 0.0 && t == 0) *a.info = 1;                    // exactly singular column (NaNs pass silently)
-        const cplx r = cdiv(cmake(1.0, 0.0), Am[p * ld + k]);
+        const cplx r = crcp_fast(Am[p * ld + k]);
         const cplx akk = Am[k * ld + k];                           // becomes the multiplier of the swapped-out row
         cplx rs[4], rk[4];
 #pragma unroll
@@ -158,6 +170,252 @@ __global__ void __launch_bounds__(NT) k_small_gj(const GnbSmallArgs a) {
     }
 }
 
+// if-chain over a WARP-UNIFORM index with the index as a compile-time constant inside fn: register arrays are
+// addressed statically without per-element selects
+template <int I, int NMAX, class F>
+__device__ __forceinline__ void static_switch(int i, F&& fn) {
+    if constexpr (I < NMAX) {
+        if (i == I) fn(std::integral_constant<int, I>{});
+        else static_switch<I + 1, NMAX>(i, fn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident variant (N <= 96): the matrix lives in the register file, distributed so that a matrix COLUMN is
+// spread over the 32 lanes of ONE warp:  thread (lane, warp) owns rows lane + 32 a (a < RA) and columns
+// warp + NW b (b < CB).  Step k of the (implicitly pivoted, no row exchanges) Gauss-Jordan inverse:
+//   1. the warp that owns column k finds the pivot among the rows not used yet with warp shuffles, publishes the
+//      multiplier column, the pivot row index and the reciprocal pivot in shared memory;        -- barrier --
+//   2. every thread reads its RA multipliers, gets the pivot-row entries of its CB columns by warp shuffle from
+//      lane p % 32 of its own warp, and updates its RA x CB register tile with pure FMAs.
+// One barrier per column; shared-memory traffic per step is RA complex reads per thread instead of a read and a
+// write of every matrix element (the shared-memory-resident kernel above is bound by exactly that).  Without row exchanges the in-place result is stored[i][m] = G[invp[i]][piv[m]] (piv[k] = pivot row
+// of step k); the epilogues address G through these two maps.
+template <int RA, int CB, int NW>
+__global__ void __launch_bounds__(32 * NW, (RA * CB <= 16) ? 2 : 1) k_reg_gj(const GnbSmallArgs a) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    constexpr int NT = 32 * NW, NR = 32 * RA;
+    const int N = a.N, ld = N | 1;
+    cplx* colbuf = reinterpret_cast<cplx*>(sm_raw);                  // [2][NR]   multipliers of step k (parity k & 1)
+    cplx* rinfo = colbuf + 2 * NR;                                   // [2]       reciprocal pivot
+    int* piv = reinterpret_cast<int*>(rinfo + 2);                    // [NR] pivot row of step k
+    int* invp = piv + NR;                                            // [NR] step at which row i was the pivot row
+    int* pos1 = invp + NR;                                           // [NR] position of an orbital in contact ca / cb
+    int* pos2 = pos1 + NR;
+    double* red = reinterpret_cast<double*>(pos2 + NR);              // [NW]
+    cplx* slab = reinterpret_cast<cplx*>(red + NW + (NW & 1));       // [32][ld] staging / G12 buffer
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int e = blockIdx.x;
+    cplx A[RA][CB];
+
+    // ---- assemble through a 32-row slab so that the global reads are coalesced
+    {
+        const cplx E = a.Araw ? cmake(0.0, 0.0) : a.E[e];
+        const cplx* SB = a.SigB ? a.SigB + (size_t)e * a.strideSigB : nullptr;
+        const cplx* Ar = a.Araw ? a.Araw + (size_t)e * N * N : nullptr;
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int r0 = 32 * ra;
+            for (int rr = warp; rr < 32 && r0 + rr < N; rr += NW)
+                for (int j = lane; j < N; j += 32) {
+                    const size_t g = (size_t)(r0 + rr) * N + j;
+                    cplx v;
+                    if (Ar) v = Ar[g];
+                    else {
+                        v = csub(cmul(E, a.S[g]), a.F[g]);
+                        if (a.Sig0) v = csub(v, a.Sig0[g]);
+                        if (SB) v = csub(v, SB[g]);
+                    }
+                    slab[rr * ld + j] = v;
+                }
+            __syncthreads();
+            for (int cidx = 0; cidx < a.ncontacts; cidx++) {          // contacts may overlap: one at a time
+                const GnbSmallContact& ct = a.ct[cidx];
+                const cplx* blk = ct.blk + (size_t)e * ct.blk_stride;
+                for (int idx = t; idx < ct.nc * ct.nc; idx += NT) {
+                    const int r = idx / ct.nc, cc = idx - r * ct.nc;
+                    const int row = ct.inds[r] - r0;
+                    if (row >= 0 && row < 32) {
+                        cplx* p = &slab[row * ld + ct.inds[cc]];
+                        *p = csub(*p, blk[idx]);
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                const int j = warp + NW * b;
+                A[ra][b] = (r0 + lane < N && j < N) ? slab[lane * ld + j] : cmake(0.0, 0.0);
+            }
+            __syncthreads();
+        }
+    }
+
+    unsigned used = 0;                                                // bit ra: row lane + 32 ra was a pivot row
+    for (int k = 0; k < N; k++) {
+        const int par = k & 1;
+        if (warp == k % NW) {                                         // ---- 1. pivot search in the owning warp
+            cplx colv[RA];
+            static_switch<0, CB>(k / NW, [&](auto B) {
+#pragma unroll
+                for (int ra = 0; ra < RA; ra++) colv[ra] = A[ra][B.value];
+            });
+            // largest |a|^2 among my unused rows as an ordered int key (non-negative floats order like ints; single
+            // precision is ample for CHOOSING a pivot), then two REDUX steps: max key, lowest row holding it
+            int bk = -1, bi = 0x7fffffff;
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++) {
+                const int i = lane + 32 * ra;
+                const int key = __float_as_int(__double2float_rn(fma(colv[ra].x, colv[ra].x, colv[ra].y * colv[ra].y))) &
+                                0x7fffffff;                           // NaN -> largest
+                if (!((used >> ra) & 1) && i < N && key > bk) { bk = key; bi = i; }
+            }
+            const int kmax = __reduce_max_sync(0xffffffffu, bk);
+            const int p = __reduce_min_sync(0xffffffffu, bk == kmax ? bi : 0x7fffffff);
+            cplx pv = colv[0];
+#pragma unroll
+            for (int ra = 1; ra < RA; ra++)
+                if (ra == (p >> 5)) pv = colv[ra];
+            pv.x = __shfl_sync(0xffffffffu, pv.x, p & 31);
+            pv.y = __shfl_sync(0xffffffffu, pv.y, p & 31);
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++) colbuf[par * NR + lane + 32 * ra] = colv[ra];
+            if (lane == 0) {
+                if (pv.x == 0.0 && pv.y == 0.0) *a.info = 1;          // exactly singular column
+                rinfo[par] = crcp_fast(pv);
+                piv[k] = p;
+                invp[p] = k;
+            }
+            // column k restarts from zero, with a 1 in the pivot row: the update below then leaves -f r in it (and r
+            // in the pivot row)
+            static_switch<0, CB>(k / NW, [&](auto B) {
+#pragma unroll
+                for (int ra = 0; ra < RA; ra++)
+                    A[ra][B.value] = cmake((lane == (p & 31) && ra == (p >> 5)) ? 1.0 : 0.0, 0.0);
+            });
+        }
+        __syncthreads();
+        // ---- 2. every thread: multipliers f r of its rows, the pivot-row entries of its columns by shuffle from
+        //         lane p % 32 (unscaled: the scaling rides on the multipliers), then a pure-FMA tile update.
+        //         Pivot row: its entries restart from 0 with multiplier -r  ->  r v exactly.
+        const int p = piv[k];
+        const cplx r = rinfo[par];
+        const int psrc = p & 31;
+        const bool mine = lane == psrc;
+        if (mine) used |= 1u << (p >> 5);
+        cplx f[RA];
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) f[ra] = cmul(colbuf[par * NR + lane + 32 * ra], r);
+        static_switch<0, RA>(p >> 5, [&](auto PA) {
+            if (mine) f[PA.value] = cneg(r);
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                cplx v = A[PA.value][b];
+                v.x = __shfl_sync(0xffffffffu, v.x, psrc);
+                v.y = __shfl_sync(0xffffffffu, v.y, psrc);
+                if (mine) A[PA.value][b] = cmake(0.0, 0.0);
+#pragma unroll
+                for (int ra = 0; ra < RA; ra++) A[ra][b] = cfnma(A[ra][b], f[ra], v);
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- epilogues: stored[i][m] = G[invp[i]][piv[m]]
+    if (a.mode == GNB_SMALL_GREEN) {
+        cplx* G = a.G + (size_t)e * a.strideG;
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int i = lane + 32 * ra;
+            if (i >= N) continue;
+            const size_t row = (size_t)invp[i] * a.ldg;
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                const int m = warp + NW * b;
+                if (m < N) G[row + piv[m]] = A[ra][b];
+            }
+        }
+        return;
+    }
+    double acc = 0.0;
+    if (a.mode == GNB_SMALL_DOS) {
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int i = lane + 32 * ra;
+            if (i >= N) continue;
+            const int gr = invp[i];
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                const int m = warp + NW * b;
+                if (m < N && piv[m] == gr) {
+                    const double d = -A[ra][b].y * kInvPi;
+                    if (a.dos_site) a.dos_site[(size_t)e * N + gr] = d;
+                    acc += d;
+                }
+            }
+        }
+    } else {                                                          // GNB_SMALL_T: gather G12 = G[C1, C2], then reduce
+        const GnbSmallContact& c1 = a.ct[a.ca];
+        const GnbSmallContact& c2 = a.ct[a.cb];
+        const int n1 = c1.nc, n2 = c2.nc;
+        for (int i = t; i < N; i += NT) { pos1[i] = -1; pos2[i] = -1; }
+        __syncthreads();
+        for (int i = t; i < n1; i += NT) pos1[c1.inds[i]] = i;
+        for (int i = t; i < n2; i += NT) pos2[c2.inds[i]] = i;
+        __syncthreads();
+        cplx* G12 = slab;
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int i = lane + 32 * ra;
+            if (i >= N) continue;
+            const int b1 = pos1[invp[i]];
+            if (b1 < 0) continue;
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                const int m = warp + NW * b;
+                if (m < N) {
+                    const int d2 = pos2[piv[m]];
+                    if (d2 >= 0) G12[b1 * n2 + d2] = A[ra][b];
+                }
+            }
+        }
+        __syncthreads();
+        const cplx* g1 = c1.gam + (size_t)e * c1.gam_stride;
+        const cplx* g2 = c2.gam + (size_t)e * c2.gam_stride;
+        for (int idx = t; idx < n1 * n2; idx += NT) {
+            const int b = idx / n2, d = idx - b * n2;
+            cplx Y = cmake(0.0, 0.0), W = cmake(0.0, 0.0);
+            for (int cc = 0; cc < n2; cc++) Y = cfma(Y, G12[b * n2 + cc], g2[cc * n2 + d]);
+            for (int aa = 0; aa < n1; aa++) W = cfma(W, cconj(g1[aa * n1 + b]), G12[aa * n2 + d]);
+            acc += Y.x * W.x + Y.y * W.y;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < NW; w++) s += red[w];
+        if (a.mode == GNB_SMALL_DOS) a.dos_tot[e] = s;
+        else a.T[e] = s;
+    }
+}
+
+template <int RA, int CB, int NW>
+size_t reg_smem(const GnbSmallArgs& a) {
+    const int N = a.N, ld = N | 1;
+    size_t slab = (size_t)32 * ld;
+    if (a.mode == GNB_SMALL_T) slab = std::max(slab, (size_t)a.ct[a.ca].nc * a.ct[a.cb].nc);
+    return (size_t)(2 * 32 * RA + 2 + slab) * sizeof(cplx) + (size_t)4 * 32 * RA * sizeof(int) +
+           (size_t)(NW + (NW & 1)) * sizeof(double);
+}
+
+template <int RA, int CB, int NW>
+void launch_reg(cudaStream_t st, const GnbSmallArgs& a) {
+    k_reg_gj<RA, CB, NW><<<a.M, 32 * NW, reg_smem<RA, CB, NW>(a), st>>>(a);
+}
+
 size_t small_smem(int N, int nt) {
     const int ld = N | 1;
     return (size_t)N * ld * sizeof(cplx) + (size_t)(2 * N) * sizeof(int) + (size_t)(nt / 32) * sizeof(double);
@@ -165,16 +423,32 @@ size_t small_smem(int N, int nt) {
 
 }  // namespace
 
+static int g_reg_resident = 1;          // developer switch "small_reg"
+void gnb_small_set_reg(int on) { g_reg_resident = on; }
+// Largest N the one-CTA-per-energy path takes.  Measured on B200 (tools/small_probe.py, profiles/r01_small_probe.json):
+// the register-resident kernel beats the lock-step block engine up to its limit of 96; the shared-memory-resident
+// kernel (97..119) does not (it is bound by shared-memory bandwidth), so it only runs when asked for (small_reg=0).
+int gnb_small_max_n() { return g_reg_resident ? GNB_SMALL_REG_MAX_N : GNB_SMALL_MAX_N; }
+
 cudaError_t gnb_small_init() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_small_gj<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_small_gj<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
-    return cudaFuncSetAttribute(k_small_gj<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if ((e = cudaFuncSetAttribute(k_small_gj<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_reg_gj<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_reg_gj<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    return cudaFuncSetAttribute(k_reg_gj<3, 6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a) {
     if (a.M <= 0) return;
     const int N = a.N;
+    if (g_reg_resident && N <= GNB_SMALL_REG_MAX_N) {
+        if (N <= 32) launch_reg<1, 8, 4>(st, a);
+        else if (N <= 64) launch_reg<2, 8, 8>(st, a);
+        else launch_reg<3, 6, 16>(st, a);
+        return;
+    }
     if (N <= 32) k_small_gj<128><<<a.M, 128, small_smem(N, 128), st>>>(a);
     else if (N <= 64) k_small_gj<256><<<a.M, 256, small_smem(N, 256), st>>>(a);
     else k_small_gj<512><<<a.M, 512, small_smem(N, 512), st>>>(a);

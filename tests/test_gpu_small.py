@@ -12,18 +12,26 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-def _small(ctx, on):
+def _small(ctx, on, reg=1):
+    """on: one-CTA-per-energy path; reg: register-resident (N <= 96) or shared-memory-resident kernel"""
     ctx.lib.gnb_dev_set_option(b"small_fused", int(on))
+    ctx.lib.gnb_dev_set_option(b"small_reg", int(reg))
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 97, 118, 119, 120])
-def test_small_inverse_batch(ctx, n):
-    """utils.inv (utils.py:52-54): n <= 119 runs in shared memory, 120 on the block engine"""
+@pytest.mark.parametrize("reg", [1, 0])
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 96, 97, 118, 119, 120])
+def test_small_inverse_batch(ctx, n, reg):
+    """utils.inv (utils.py:52-54): reg=1: n <= 96 in registers, above on the block engine; reg=0: n <= 119 in shared memory"""
     rng = np.random.default_rng(n)
     A = rng.standard_normal((9, n, n)) + 1j * rng.standard_normal((9, n, n))
     A[3] = np.triu(A[3]) + np.eye(n) * 1e-3          # forces row exchanges to matter little / much
     A[4][[0, n - 1]] = A[4][[n - 1, 0]]
-    Ai = ctx.inverse_batch(A)
+    A[5] = np.roll(np.eye(n), 1, axis=0) * (1 + 2j) + 1e-3 * A[5]      # every pivot off the diagonal
+    _small(ctx, 1, reg)
+    try:
+        Ai = ctx.inverse_batch(A)
+    finally:
+        _small(ctx, 1)
     ref = np.linalg.inv(A)
     for k in range(9):
         assert relerr(Ai[k], ref[k]) < 1e-11 * max(1.0, np.linalg.cond(A[k]) / 100)
@@ -44,15 +52,16 @@ def test_small_matches_block_engine_and_oracle(ctx, N, nc):
     z, w = sy.contour_points(10, -8.0, 0.0)
     out = {}
     try:
-        for on in (1, 0):
-            _small(ctx, on)
-            out[on] = (ctx.green(E[-4:]), ctx.transmission(Er, 0, -1), ctx.transmission(Er, 1, 0),
-                       ctx.transmission(Er, 0, 0), *ctx.dos(E), ctx.gr_int(z, w), ctx.dos_dense(E, st)[0],
-                       ctx.gr_int_dense(z, w, st))
+        for on, reg in ((1, 1), (1, 0), (0, 0)):
+            _small(ctx, on, reg)
+            out[on + reg] = (ctx.green(E[-4:]), ctx.transmission(Er, 0, -1), ctx.transmission(Er, 1, 0),
+                             ctx.transmission(Er, 0, 0), *ctx.dos(E), ctx.gr_int(z, w), ctx.dos_dense(E, st)[0],
+                             ctx.gr_int_dense(z, w, st))
     finally:
         _small(ctx, 1)
-    for a, b in zip(out[1], out[0]):
-        assert relerr(a, b) < TOL
+    for a, b, c in zip(out[2], out[1], out[0]):      # registers / shared memory / block engine
+        assert relerr(a, c) < TOL and relerr(b, c) < TOL
+    out[1] = out[2]
     Gref = np.array([O.gr_matrix(st, e, F, S) for e in E[-4:]])
     assert relerr(out[1][0], Gref) < TOL
     g1 = 1j * (sig[0] - sig[0].conj().T)
@@ -90,6 +99,11 @@ def test_small_overlapping_contacts_and_chunks(ctx):
     g1, g2 = 1j * (s1 - s1.conj().T), 1j * (s2 - s2.conj().T)
     Tref = np.array([O.transmission_restricted(e, F, S, s1 + s2, g1, g2) for e in E])
     assert np.allclose(T, Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
+    _small(ctx, 1, 0)
+    try:
+        assert np.allclose(ctx.transmission(E, 0, 1), Tref, rtol=1e-9, atol=1e-12 * np.abs(Tref).max())
+    finally:
+        _small(ctx, 1)
     ctx.set_workspace_limit(64 << 20)          # -> 3 chunks of the energy list
     try:
         T2 = ctx.transmission(E, 0, 1)

@@ -26,7 +26,7 @@ def timed(f, reps=5):
     return float(np.median(ts))
 
 
-for N, nc, M in ((64, 1, 1000), (64, 1, 20000), (96, 16, 20000), (119, 32, 20000)):
+for N, nc, M in ((64, 1, 1000), (64, 1, 20000), (32, 4, 20000), (96, 16, 20000), (119, 32, 20000), (64, 1, 12), (96, 16, 12), (119, 32, 12), (119, 32, 108)):
     if nc == 1:
         F, S, s1, s2 = sy.chain(N)
         blocks = [([0], [[s1[0]]]), ([N - 1], [[s2[N - 1]]])]
@@ -42,15 +42,19 @@ for N, nc, M in ((64, 1, 1000), (64, 1, 20000), (96, 16, 20000), (119, 32, 20000
     z = E + 0.05j
     w = np.full(M, 1.0 / M, dtype=complex)
     row = {"N": N, "nc": nc, "M": M}
-    for on in (1, 0):
+    for on, reg, tag in ((1, 1, "reg"), (1, 0, "smem"), (0, 0, "block")):
+        if tag == "reg" and N > 96:
+            continue
         ctx.lib.gnb_dev_set_option(b"small_fused", on)
-        tag = "smem" if on else "block"
+        ctx.lib.gnb_dev_set_option(b"small_reg", reg)
         row[f"T_{tag}_pts_per_s"] = M / timed(lambda: ctx.transmission(E, 0, -1))
         row[f"DOS_{tag}_pts_per_s"] = M / timed(lambda: ctx.dos(E))
         row[f"GrInt_{tag}_pts_per_s"] = M / timed(lambda: ctx.gr_int(z, w))
     ctx.lib.gnb_dev_set_option(b"small_fused", 1)
+    ctx.lib.gnb_dev_set_option(b"small_reg", 1)
     row["T_flops_per_pt_gj"] = 8.0 * N ** 3
-    row["T_smem_tflops"] = row["T_smem_pts_per_s"] * 8.0 * N ** 3 / 1e12
+    best = "reg" if N <= 96 else "smem"
+    row["T_%s_tflops" % best] = row["T_%s_pts_per_s" % best] * 8.0 * N ** 3 / 1e12
     out.append(row)
     print(json.dumps(row))
 json.dump(out, open("gpurun_out/small_probe.json", "w"), indent=1)
