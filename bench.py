@@ -250,7 +250,7 @@ def run_ours(args):
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_rk_gemm_ncu.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01c_rk_gemm_ncu.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -263,7 +263,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor",
-                         "kernel": "k_rk_gemm (complex128 rank-K update C -= P W, K = 32..512, packed operands, DMMA.8x8x4). "
+                         "kernel": "k_rk_gemm / k_rk_gemm_rp (rank-K update C -= P W of the complex128 elimination, K = 32..512, packed "
+                                   "operands by cp.async.bulk, DMMA.8x8x4; _rp = real-packed operands of the real columns). "
                                    "achieved counts EXECUTED arithmetic in 4-multiplication-equivalent flops: 8 per complex "
                                    "MAC, 4 where the panel is real, 2 where panel and pivot rows are real (real F, S, E with "
                                    "the contact orbitals ordered last keep every column left of the contacts exactly real); "

@@ -180,6 +180,14 @@ __device__ __forceinline__ void static_switch(int i, F&& fn) {
     }
 }
 
+template <int I, int NMAX, class F>
+__device__ __forceinline__ void static_for(F&& fn) {
+    if constexpr (I < NMAX) {
+        fn(std::integral_constant<int, I>{});
+        static_for<I + 1, NMAX>(fn);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Register-resident variant (N <= 96): the matrix lives in the register file, distributed so that a matrix COLUMN is
 // spread over the 32 lanes of ONE warp:  thread (lane, warp) owns rows lane + 32 a (a < RA) and columns
@@ -188,6 +196,8 @@ __device__ __forceinline__ void static_switch(int i, F&& fn) {
 //      multiplier column, the pivot row index and the reciprocal pivot in shared memory;        -- barrier --
 //   2. every thread reads its RA multipliers, gets the pivot-row entries of its CB columns by warp shuffle from
 //      lane p % 32 of its own warp, and updates its RA x CB register tile with pure FMAs.
+//   3. look-ahead: the owner of column k+1 updates that column first and publishes its pivot (bar.arrive on a named
+//      barrier) before finishing its step-k update, so the search is hidden behind the other warps' updates.
 // One barrier per column; shared-memory traffic per step is RA complex reads per thread instead of a read and a
 // write of every matrix element (the shared-memory-resident kernel above is bound by exactly that).  Without row exchanges the in-place result is stored[i][m] = G[invp[i]][piv[m]] (piv[k] = pivot row
 // of step k); the epilogues address G through these two maps.
@@ -252,49 +262,63 @@ __global__ void __launch_bounds__(32 * NW, (RA * CB <= 16) ? 2 : 1) k_reg_gj(con
     }
 
     unsigned used = 0;                                                // bit ra: row lane + 32 ra was a pivot row
+
+    // ---- 1. pivot search of column kk, by the warp that owns it (the column is entirely in its registers)
+    auto pivot_search = [&](int kk) {
+        const int pr = kk & 1;
+        cplx colv[RA];
+        static_switch<0, CB>(kk / NW, [&](auto B) {
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++) colv[ra] = A[ra][B.value];
+        });
+        // largest |a|^2 among my unused rows as an ordered int key (non-negative floats order like ints; single
+        // precision is ample for CHOOSING a pivot), then two REDUX steps: max key, lowest row holding it
+        int bk = -1, bi = 0x7fffffff;
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int i = lane + 32 * ra;
+            const int key = __float_as_int(__double2float_rn(fma(colv[ra].x, colv[ra].x, colv[ra].y * colv[ra].y))) &
+                            0x7fffffff;                               // NaN -> largest
+            if (!((used >> ra) & 1) && i < N && key > bk) { bk = key; bi = i; }
+        }
+        const int kmax = __reduce_max_sync(0xffffffffu, bk);
+        const int p = __reduce_min_sync(0xffffffffu, bk == kmax ? bi : 0x7fffffff);
+        cplx pv = colv[0];
+#pragma unroll
+        for (int ra = 1; ra < RA; ra++)
+            if (ra == (p >> 5)) pv = colv[ra];
+        pv.x = __shfl_sync(0xffffffffu, pv.x, p & 31);
+        pv.y = __shfl_sync(0xffffffffu, pv.y, p & 31);
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) colbuf[pr * NR + lane + 32 * ra] = colv[ra];
+        if (lane == 0) {
+            if (pv.x == 0.0 && pv.y == 0.0) *a.info = 1;              // exactly singular column
+            rinfo[pr] = crcp_fast(pv);
+            piv[kk] = p;
+            invp[p] = kk;
+        }
+        // column kk restarts from zero, with a 1 in the pivot row: the update then leaves -f r in it (and r in
+        // the pivot row)
+        static_switch<0, CB>(kk / NW, [&](auto B) {
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++)
+                A[ra][B.value] = cmake((lane == (p & 31) && ra == (p >> 5)) ? 1.0 : 0.0, 0.0);
+        });
+    };
+
+    // Look-ahead: the warp that owns column k+1 updates that column first, searches its pivot and publishes it
+    // (bar.arrive, named barrier 1 + parity) BEFORE finishing its own step-k update; the other warps meet it with
+    // bar.sync at the top of step k+1.  The pivot search is therefore off the critical path of every step; all NT
+    // threads take part in every barrier phase, so no warp runs more than one step ahead and the double-buffered
+    // colbuf / rinfo are safe.
+    if (warp == 0) pivot_search(0);
+    __syncthreads();
     for (int k = 0; k < N; k++) {
         const int par = k & 1;
-        if (warp == k % NW) {                                         // ---- 1. pivot search in the owning warp
-            cplx colv[RA];
-            static_switch<0, CB>(k / NW, [&](auto B) {
-#pragma unroll
-                for (int ra = 0; ra < RA; ra++) colv[ra] = A[ra][B.value];
-            });
-            // largest |a|^2 among my unused rows as an ordered int key (non-negative floats order like ints; single
-            // precision is ample for CHOOSING a pivot), then two REDUX steps: max key, lowest row holding it
-            int bk = -1, bi = 0x7fffffff;
-#pragma unroll
-            for (int ra = 0; ra < RA; ra++) {
-                const int i = lane + 32 * ra;
-                const int key = __float_as_int(__double2float_rn(fma(colv[ra].x, colv[ra].x, colv[ra].y * colv[ra].y))) &
-                                0x7fffffff;                           // NaN -> largest
-                if (!((used >> ra) & 1) && i < N && key > bk) { bk = key; bi = i; }
-            }
-            const int kmax = __reduce_max_sync(0xffffffffu, bk);
-            const int p = __reduce_min_sync(0xffffffffu, bk == kmax ? bi : 0x7fffffff);
-            cplx pv = colv[0];
-#pragma unroll
-            for (int ra = 1; ra < RA; ra++)
-                if (ra == (p >> 5)) pv = colv[ra];
-            pv.x = __shfl_sync(0xffffffffu, pv.x, p & 31);
-            pv.y = __shfl_sync(0xffffffffu, pv.y, p & 31);
-#pragma unroll
-            for (int ra = 0; ra < RA; ra++) colbuf[par * NR + lane + 32 * ra] = colv[ra];
-            if (lane == 0) {
-                if (pv.x == 0.0 && pv.y == 0.0) *a.info = 1;          // exactly singular column
-                rinfo[par] = crcp_fast(pv);
-                piv[k] = p;
-                invp[p] = k;
-            }
-            // column k restarts from zero, with a 1 in the pivot row: the update below then leaves -f r in it (and r
-            // in the pivot row)
-            static_switch<0, CB>(k / NW, [&](auto B) {
-#pragma unroll
-                for (int ra = 0; ra < RA; ra++)
-                    A[ra][B.value] = cmake((lane == (p & 31) && ra == (p >> 5)) ? 1.0 : 0.0, 0.0);
-            });
+        if (k > 0 && warp != k % NW) {
+            if (par) asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         }
-        __syncthreads();
         // ---- 2. every thread: multipliers f r of its rows, the pivot-row entries of its columns by shuffle from
         //         lane p % 32 (unscaled: the scaling rides on the multipliers), then a pure-FMA tile update.
         //         Pivot row: its entries restart from 0 with multiplier -r  ->  r v exactly.
@@ -306,16 +330,29 @@ __global__ void __launch_bounds__(32 * NW, (RA * CB <= 16) ? 2 : 1) k_reg_gj(con
         cplx f[RA];
 #pragma unroll
         for (int ra = 0; ra < RA; ra++) f[ra] = cmul(colbuf[par * NR + lane + 32 * ra], r);
+        const bool next_owner = (k + 1 < N) && warp == (k + 1) % NW;
+        const int kb1 = (k + 1) / NW;
         static_switch<0, RA>(p >> 5, [&](auto PA) {
             if (mine) f[PA.value] = cneg(r);
-#pragma unroll
-            for (int b = 0; b < CB; b++) {
-                cplx v = A[PA.value][b];
+            auto column = [&](auto B) {
+                cplx v = A[PA.value][B.value];
                 v.x = __shfl_sync(0xffffffffu, v.x, psrc);
                 v.y = __shfl_sync(0xffffffffu, v.y, psrc);
-                if (mine) A[PA.value][b] = cmake(0.0, 0.0);
+                if (mine) A[PA.value][B.value] = cmake(0.0, 0.0);
 #pragma unroll
-                for (int ra = 0; ra < RA; ra++) A[ra][b] = cfnma(A[ra][b], f[ra], v);
+                for (int ra = 0; ra < RA; ra++) A[ra][B.value] = cfnma(A[ra][B.value], f[ra], v);
+            };
+            if (next_owner) {
+                static_switch<0, CB>(kb1, column);
+                pivot_search(k + 1);
+                __threadfence_block();
+                if ((k + 1) & 1) asm volatile("bar.arrive 2, %0;" ::"n"(NT) : "memory");
+                else asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
+                static_for<0, CB>([&](auto B) {
+                    if (B.value != kb1) column(B);
+                });
+            } else {
+                static_for<0, CB>(column);
             }
         });
     }
@@ -323,17 +360,28 @@ __global__ void __launch_bounds__(32 * NW, (RA * CB <= 16) ? 2 : 1) k_reg_gj(con
 
     // ---- epilogues: stored[i][m] = G[invp[i]][piv[m]]
     if (a.mode == GNB_SMALL_GREEN) {
+        // 32 rows of G at a time through the slab, so that the global stores are whole rows (the register tiles hold
+        // G scattered by the two pivot maps)
         cplx* G = a.G + (size_t)e * a.strideG;
+        int grow[RA], gcol[CB];
 #pragma unroll
-        for (int ra = 0; ra < RA; ra++) {
-            const int i = lane + 32 * ra;
-            if (i >= N) continue;
-            const size_t row = (size_t)invp[i] * a.ldg;
+        for (int ra = 0; ra < RA; ra++) grow[ra] = (lane + 32 * ra < N) ? invp[lane + 32 * ra] : -1;
 #pragma unroll
-            for (int b = 0; b < CB; b++) {
-                const int m = warp + NW * b;
-                if (m < N) G[row + piv[m]] = A[ra][b];
+        for (int b = 0; b < CB; b++) gcol[b] = (warp + NW * b < N) ? piv[warp + NW * b] : -1;
+        for (int r0 = 0; r0 < N; r0 += 32) {
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++) {
+                const int rr = grow[ra] - r0;
+                if (rr >= 0 && rr < 32) {
+#pragma unroll
+                    for (int b = 0; b < CB; b++)
+                        if (gcol[b] >= 0) slab[rr * ld + gcol[b]] = A[ra][b];
+                }
             }
+            __syncthreads();
+            for (int rr = warp; rr < 32 && r0 + rr < N; rr += NW)
+                for (int j = lane; j < N; j += 32) G[(size_t)(r0 + rr) * a.ldg + j] = slab[rr * ld + j];
+            __syncthreads();
         }
         return;
     }
