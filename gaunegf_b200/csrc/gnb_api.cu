@@ -24,6 +24,7 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
 static int g_mixed_layout = 1;    // transmission: store the real columns as doubles (mixed layout, gnb_rec.cu)
 static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
+static int g_chain_joint = 1;     // chain contacts with equal block size / iteration parameters share one fixed-point batch
 static int g_small = 1;           // N <= gnb_small_max_n(): one CTA per energy, matrix on chip (gnb_small.cu)
 int gnb_small_enabled() { return g_small; }
 static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
@@ -103,6 +104,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
     else if (!strcmp(name, "small_fused")) g_small = value;
+    else if (!strcmp(name, "chain_joint")) g_chain_joint = value;
     else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
@@ -464,11 +466,31 @@ static int resolve_contact(gnb_ctx* c, int idx) {
 
 // Sigma blocks (and Gammas) of every contact for the energies of this chunk
 static int prepare_sigma(gnb_ctx* c, int M, const cplx* dE, int want_gamma) {
+    // 1-D chain contacts that can iterate together (surfG1D.py:260-288 is the same recurrence for each of them)
+    std::vector<Contact*> joint;
+    if (g_chain_joint)
+        for (auto& ct : c->contacts)
+            if (ct.kind == GNB_C_CHAIN1D) {
+                const bool same = joint.empty() || (ct.nc == joint[0]->nc && ct.conv == joint[0]->conv &&
+                                                    ct.relax == joint[0]->relax && ct.max_iter == joint[0]->max_iter);
+                if (same) joint.push_back(&ct);
+            }
+    if (joint.size() >= 2) {
+        int rc = gnb_chain1d_surface_g_multi(c, joint.data(), (int)joint.size(), M, dE);
+        if (rc) return rc;
+    } else {
+        joint.clear();
+    }
+    for (size_t k = 0; k < joint.size(); k++) {          // before any other chain contact reuses c->cg
+        Contact& ct = *joint[k];
+        int rc = gnb_contact_eval(c, ct, M, dE, want_gamma, c->cg.as<cplx>() + (long)k * M * ct.nc * ct.nc);
+        if (rc) return rc;
+    }
     for (auto& ct : c->contacts) {
         if (ct.kind == GNB_C_CONST) {
             ct.blk_ptr = ct.d_const.as<cplx>(); ct.blk_stride = 0;
             ct.gam_ptr = ct.gam.as<cplx>(); ct.gam_stride = 0;
-        } else {
+        } else if (std::find(joint.begin(), joint.end(), &ct) == joint.end()) {
             int rc = gnb_contact_eval(c, ct, M, dE, want_gamma);
             if (rc) return rc;
         }

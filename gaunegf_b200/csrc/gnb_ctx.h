@@ -96,7 +96,8 @@ struct gnb_ctx {
 };
 
 // gnb_sigma.cu
-int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma);
+int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma, const cplx* g_ready = nullptr);
+int gnb_chain1d_surface_g_multi(gnb_ctx* c, Contact* const* cts, int K, int M, const cplx* dE);   // g_k in c->cg + k*M*nc*nc
 int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE);     // leaves g in c->cg
 int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cplx* d_out);
 GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc);

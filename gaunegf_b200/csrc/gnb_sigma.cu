@@ -120,31 +120,40 @@ static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
     return GNB_OK;
 }
 
-// Surface Green's function of every energy of the chunk -> c->cg ; iteration counts -> ct.iters/diffs
-int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE) {
+// Surface Green's functions of K chain contacts (same block size and iteration parameters) for every energy of the
+// chunk, as ONE lock-step batch of K * M fixed-point problems (problem k * M + e): the iteration is a chain of ~30
+// short, latency-bound launches, so two contacts in one batch cost far less than two batches.
+// g of contact k -> c->cg + k * M * nc * nc ; iteration counts -> cts[k]->iters / diffs
+int gnb_chain1d_surface_g_multi(gnb_ctx* c, Contact* const* cts, int K, int M, const cplx* dE) {
+    const Contact& ct = *cts[0];
     const int nc = ct.nc;
     const long nn = (long)nc * nc;
-    const size_t bytes = (size_t)M * nn * sizeof(cplx);
+    const int MT = K * M;
+    const size_t bytes = (size_t)MT * nn * sizeof(cplx);
     GNB_CK(c->cA.ensure(bytes)); GNB_CK(c->cB.ensure(bytes)); GNB_CK(c->cg.ensure(bytes));
     GNB_CK(c->cgn.ensure(bytes)); GNB_CK(c->cT1.ensure(bytes)); GNB_CK(c->cM.ensure(bytes));
-    GNB_CK(c->cflags.ensure((size_t)M * (sizeof(ChainFlags) + sizeof(double)) + 64));
-    GNB_CK(ct.iters.ensure((size_t)M * sizeof(int)));
-    GNB_CK(ct.diffs.ensure((size_t)M * sizeof(double)));
+    GNB_CK(c->cflags.ensure((size_t)MT * (sizeof(ChainFlags) + sizeof(double)) + 64));
     cplx *A = c->cA.as<cplx>(), *B = c->cB.as<cplx>(), *g = c->cg.as<cplx>(), *gn = c->cgn.as<cplx>(),
          *T1 = c->cT1.as<cplx>(), *Mx = c->cM.as<cplx>();
     ChainFlags* flags = c->cflags.as<ChainFlags>();
-    double* diffs = reinterpret_cast<double*>(flags + M);
-    int* d_nact = reinterpret_cast<int*>(diffs + M);
+    double* diffs = reinterpret_cast<double*>(flags + MT);
+    int* d_nact = reinterpret_cast<int*>(diffs + MT);
     cudaStream_t st = c->stream;
 
     dim3 pg(std::min(cdiv_i(nn, 256), 1024), M);
-    k_chain_pencil<<<pg, 256, 0, st>>>((int)nn, dE, ct.eta, ct.Salpha.as<cplx>(), ct.alpha.as<cplx>(), A);
-    k_chain_pencil<<<pg, 256, 0, st>>>((int)nn, dE, ct.eta, ct.Sbeta.as<cplx>(), ct.beta.as<cplx>(), B);
+    for (int k = 0; k < K; k++) {
+        Contact& ck = *cts[k];
+        GNB_CK(ck.iters.ensure((size_t)M * sizeof(int)));
+        GNB_CK(ck.diffs.ensure((size_t)M * sizeof(double)));
+        const long off = (long)k * M * nn;
+        k_chain_pencil<<<pg, 256, 0, st>>>((int)nn, dE, ck.eta, ck.Salpha.as<cplx>(), ck.alpha.as<cplx>(), A + off);
+        k_chain_pencil<<<pg, 256, 0, st>>>((int)nn, dE, ck.eta, ck.Sbeta.as<cplx>(), ck.beta.as<cplx>(), B + off);
+        c->launches += 2;
+    }
     GNB_CK(cudaMemcpyAsync(Mx, A, bytes, cudaMemcpyDeviceToDevice, st));
-    c->launches += 2;
-    int rc = chain_invert(c, M, nc, Mx, g);                         // g0 = inv(A)   (surfG1D.py:287)
+    int rc = chain_invert(c, MT, nc, Mx, g);                        // g0 = inv(A)   (surfG1D.py:287)
     if (rc) return rc;
-    k_chain_init_flags<<<cdiv_i(M, 256), 256, 0, st>>>(flags, diffs, M, ct.max_iter);
+    k_chain_init_flags<<<cdiv_i(MT, 256), 256, 0, st>>>(flags, diffs, MT, ct.max_iter);
     c->launches++;
 
     GnbGemmArgs ga{};
@@ -153,27 +162,36 @@ int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE) {
     const int check_every = 16;
     for (int it = 0; it < ct.max_iter; it++) {
         ga.C = T1; ga.P = B; ga.W = g; ga.zero_init = 1; ga.plus = 1;        // T1 = B g
-        gnb_launch_gemm(st, ga, M, false, false);
+        gnb_launch_gemm(st, ga, MT, false, false);
         GNB_CK(cudaMemcpyAsync(Mx, A, bytes, cudaMemcpyDeviceToDevice, st));
         ga.C = Mx; ga.P = T1; ga.W = B; ga.zero_init = 0; ga.plus = 0;       // Mx = A - T1 B^H
-        gnb_launch_gemm(st, ga, M, true, false);
+        gnb_launch_gemm(st, ga, MT, true, false);
         c->launches += 2;
-        if ((rc = chain_invert(c, M, nc, Mx, gn))) return rc;               // g_new = inv(A - B g B^H)
-        k_chain_mix<<<M, 256, 0, st>>>((int)nn, g, gn, flags, diffs, ct.conv, ct.relax, ct.max_iter);
+        if ((rc = chain_invert(c, MT, nc, Mx, gn))) return rc;              // g_new = inv(A - B g B^H)
+        k_chain_mix<<<MT, 256, 0, st>>>((int)nn, g, gn, flags, diffs, ct.conv, ct.relax, ct.max_iter);
         c->launches++;
         if ((it + 1) % check_every == 0 || it + 1 == ct.max_iter) {
             int nact = 0;
-            k_chain_count_active<<<1, 256, 0, st>>>(flags, M, d_nact);
+            k_chain_count_active<<<1, 256, 0, st>>>(flags, MT, d_nact);
             c->launches++;
             GNB_CK(cudaMemcpyAsync(&nact, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
             GNB_CK(cudaStreamSynchronize(st));
             if (nact == 0) break;
         }
     }
-    k_chain_export<<<cdiv_i(M, 256), 256, 0, st>>>(flags, diffs, M, ct.iters.as<int>(), ct.diffs.as<double>());
-    c->launches++;
+    for (int k = 0; k < K; k++) {
+        k_chain_export<<<cdiv_i(M, 256), 256, 0, st>>>(flags + (long)k * M, diffs + (long)k * M, M, cts[k]->iters.as<int>(),
+                                                       cts[k]->diffs.as<double>());
+        c->launches++;
+    }
     GNB_CK(cudaGetLastError());
     return GNB_OK;
+}
+
+// one contact: leaves g in c->cg
+int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE) {
+    Contact* one = &ct;
+    return gnb_chain1d_surface_g_multi(c, &one, 1, M, dE);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -425,14 +443,17 @@ int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cpl
 // ------------------------------------------------------------------------------------------
 // Contact self-energy blocks of a chunk (+ Gamma)
 // ------------------------------------------------------------------------------------------
-int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma) {
+int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma, const cplx* g_ready) {
     const int nc = ct.nc;
     const long nn = (long)nc * nc;
     GNB_CK(ct.blk.ensure((size_t)M * nn * sizeof(cplx)));
     cudaStream_t st = c->stream;
     if (ct.kind == GNB_C_CHAIN1D) {
-        int rc = gnb_chain1d_surface_g(c, ct, M, dE);
-        if (rc) return rc;
+        if (!g_ready) {                                   // not part of a joint batch (gnb_chain1d_surface_g_multi)
+            int rc = gnb_chain1d_surface_g(c, ct, M, dE);
+            if (rc) return rc;
+            g_ready = c->cg.as<cplx>();
+        }
         GNB_CK(c->ct.ensure((size_t)M * nn * sizeof(cplx)));
         cplx* tmat = c->ct.as<cplx>();
         dim3 pg(std::min(cdiv_i(nn, 256), 1024), M);
@@ -441,7 +462,7 @@ int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_ga
         ga.ilo = 0; ga.ihi = nc; ga.jlo = 0; ga.jhi = nc; ga.kdim = nc; ga.skip_lo = ga.skip_hi = -1;
         ga.strideC = ga.strideP = ga.strideW = nn; ga.ldc = ga.ldp = ga.ldw = nc;
         ga.zero_init = 1; ga.plus = 1;
-        ga.C = c->cT1.as<cplx>(); ga.P = tmat; ga.W = c->cg.as<cplx>();           // T1 = t g
+        ga.C = c->cT1.as<cplx>(); ga.P = tmat; ga.W = g_ready;                    // T1 = t g
         gnb_launch_gemm(st, ga, M, false, false);
         ga.C = ct.blk.as<cplx>(); ga.P = c->cT1.as<cplx>(); ga.W = tmat;          // Sigma = T1 t^H
         gnb_launch_gemm(st, ga, M, true, false);
