@@ -28,24 +28,34 @@ __device__ __forceinline__ const double* gnb_real_view(const cplx* A, int mixr) 
     return reinterpret_cast<const double*>(reinterpret_cast<const char*>(A) + (size_t)mixr * 8);
 }
 
+// One CTA = one matrix row x ASM_EB energies: F, S (and Sigma0) of the row are read ONCE into registers and reused
+// for every energy of the group, so the kernel is bound by its HBM writes (16 N ld B per energy), not by L2 reads of
+// F and S per energy or by index arithmetic.
+#define ASM_EB 16
 __global__ void __launch_bounds__(256) k_assemble(cplx* __restrict__ A, long strideA, int ld, int N,
                                                   const cplx* __restrict__ F, const cplx* __restrict__ S,
                                                   const cplx* __restrict__ Sig0,
                                                   const cplx* __restrict__ SigB, long strideSigB,
-                                                  const cplx* __restrict__ E, const int* __restrict__ pi, int mixr) {
-    const int b = blockIdx.y;
-    const cplx e = E[b];
-    cplx* Ab = A + (long)b * strideA;
-    double* Ar = gnb_real_view(A, mixr) + (long)b * 2 * strideA;
-    const long total = (long)N * N;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int i = (int)(idx / N), j = (int)(idx - (long)i * N);
-        const long src = pi ? (long)pi[i] * N + pi[j] : idx;      // symmetric orbital reordering (contacts last)
-        cplx v = csub(cmul(e, S[src]), F[src]);
-        if (Sig0) v = csub(v, Sig0[src]);
-        if (SigB) v = csub(v, SigB[(long)b * strideSigB + src]);
-        if (j < mixr) Ar[(long)i * 2 * ld + j] = v.x;
-        else Ab[(long)i * ld + j] = v;
+                                                  const cplx* __restrict__ E, const int* __restrict__ pi, int mixr, int M) {
+    __shared__ cplx sE[ASM_EB];
+    const int i = blockIdx.x, b0 = blockIdx.y * ASM_EB, nb = min(ASM_EB, M - b0), t = threadIdx.x;
+    if (t < nb) sE[t] = E[b0 + t];
+    __syncthreads();
+    const long rowsrc = (long)(pi ? pi[i] : i) * N;              // symmetric orbital reordering (contacts last)
+    double* Ar = gnb_real_view(A, mixr);
+    for (int j = t; j < N; j += 256) {
+        const long src = rowsrc + (pi ? pi[j] : j);
+        const cplx s = S[src], f = F[src];
+        const cplx s0 = Sig0 ? Sig0[src] : cmake(0.0, 0.0);
+        const bool real_slot = j < mixr;
+        for (int bb = 0; bb < nb; bb++) {
+            const long b = b0 + bb;
+            cplx v = csub(cmul(sE[bb], s), f);
+            if (Sig0) v = csub(v, s0);
+            if (SigB) v = csub(v, SigB[b * strideSigB + src]);
+            if (real_slot) Ar[b * 2 * strideA + (long)i * 2 * ld + j] = v.x;
+            else A[b * strideA + (long)i * ld + j] = v;
+        }
     }
 }
 
@@ -838,8 +848,8 @@ void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, 
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E,
                          const int* pi, int mixr) {
     if (M <= 0) return;
-    dim3 grid(min(cdiv_i((long)N * N, 256 * 4), 4096), M);
-    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E, pi, mixr);
+    dim3 grid(N, cdiv_i(M, ASM_EB));
+    k_assemble<<<grid, 256, 0, st>>>(A, strideA, ld, N, F, S, Sig0, SigB, strideSigB, E, pi, mixr, M);
 }
 
 void gnb_launch_scatter_sub(cudaStream_t st, int M, cplx* A, long strideA, int ld, const int* inds, int nc,

@@ -450,34 +450,40 @@ __global__ void __launch_bounds__(288, WR ? 2 : 1) k_rk_gemm_rp(RkGemmRpArgs g, 
 // ------------------------------------------------------------------------------------------------
 // Phase 1: Ppk[r][K] = A[src(r)][K] for rows r in [rlo, N) (src = row move of this block), zero for the pivot
 // rows.  Reads A only and writes Ppk only, so the row moves need no separate pass over the panel.
+#define PS_ROWS 128
 __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ A, long strideA, int ld, int N, int c0,
                                                        int rlo, const int* __restrict__ moves, cplx* __restrict__ Ppk,
                                                        long stridePk, int nrb, int mixr, double* __restrict__ PpkR,
                                                        long stridePkR) {
-    __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
-    __shared__ int s_nm;
+    // one CTA = PS_ROWS consecutive rows: their sources are resolved once into shared memory (identity, then the
+    // moves that land in the range), so the copy loop is address arithmetic + one load + one store per element
+    __shared__ int s_map[PS_ROWS];
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, wrp = t >> 5;
     const int* mv = moves + (long)b * GNB_MOVES_STRIDE;
-    if (t == 0) s_nm = mv[0];
-    if (t < 2 * GNB_NB) { s_dst[t] = mv[1 + 2 * t]; s_src[t] = mv[2 + 2 * t]; }
+    const int r0 = rlo + blockIdx.x * PS_ROWS;
+    if (t < PS_ROWS) s_map[t] = r0 + t;
     __syncthreads();
-    const int nm = s_nm;
+    const int nm = mv[0];
+    if (t < nm) {
+        const int d = mv[1 + 2 * t] - r0;
+        if (d >= 0 && d < PS_ROWS) s_map[d] = mv[2 + 2 * t];
+    }
+    __syncthreads();
     const cplx* Ab = A + (long)b * strideA;
     cplx* Pb = Ppk + (long)b * stridePk;
     const int kc = c0 / 16 + (lane >> 4), kk = lane & 15;
-    for (int r = rlo + blockIdx.x * 8 + wrp; r < N; r += gridDim.x * 8) {
-        int src = r;
-        for (int m = lane; m < nm; m += 32)
-            if (s_dst[m] == r) src = s_src[m];
-        src = __reduce_max_sync(0xffffffffu, src == r ? -1 : src);
-        if (src < 0) src = r;
+    const bool realp = c0 < mixr;                            // real-stored panel -> real-packed copy
+    const double* Arv = rk_real_view(Ab, mixr);
+    double* PRb = PpkR + (long)b * stridePkR;
+#pragma unroll 4
+    for (int q = wrp; q < PS_ROWS; q += 8) {
+        const int r = r0 + q;
+        if (r >= N) break;
+        const int src = s_map[q];
         const bool piv = (r >= c0 && r < c0 + GNB_NB);
         const long off = ((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk;
-        if (c0 < mixr) {                                     // real-stored panel -> real-packed copy
-            PpkR[(long)b * stridePkR + off] = piv ? 0.0 : rk_real_view(Ab, mixr)[(long)src * 2 * ld + c0 + lane];
-        } else {
-            Pb[off] = piv ? cmake(0.0, 0.0) : Ab[(long)src * ld + c0 + lane];
-        }
+        if (realp) PRb[off] = piv ? 0.0 : Arv[(long)src * 2 * ld + c0 + lane];
+        else Pb[off] = piv ? cmake(0.0, 0.0) : Ab[(long)src * ld + c0 + lane];
     }
 }
 
@@ -1037,7 +1043,7 @@ struct Rec {
         }
         const int rlo = jordan ? 0 : c0 + GNB_NB;
         if (rlo < N) {
-            dim3 grid(std::min(cdiv_i(N - rlo, 8), 128), M);
+            dim3 grid(cdiv_i(N - rlo, PS_ROWS), M);
             k_rk_panel_save<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, rlo, mv(c0), ws.Ppk, ws.stridePk, nrb, mixr, ws.PpkR,
                                                   ws.stridePkR);
             launches++;
