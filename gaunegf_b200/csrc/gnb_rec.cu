@@ -539,6 +539,24 @@ __global__ void __launch_bounds__(128) k_rk_panel_fin(cplx* __restrict__ A, long
     }
 }
 
+// Phase 2 on the tensor pipe (JORDAN): A[:, K] = 0 with inv in the pivot rows, and inv as the packed W operand of
+// K's own rows / column block (a slot no far update reads).  The rank-32 strip update A[:, K] -= P[:, K] inv of the
+// packed DMMA kernel then produces exactly what k_rk_panel_fin computes with FP64 FMAs (P has zero pivot rows).
+__global__ void __launch_bounds__(256) k_rk_panel_prep(cplx* __restrict__ A, long strideA, int ld, int N, int c0,
+                                                       const cplx* __restrict__ inv, cplx* __restrict__ Wpk, long strideWk,
+                                                       int ncb) {
+    const int b = blockIdx.y, t = threadIdx.x, col = t & 31;
+    cplx* Ab = A + (long)b * strideA;
+    const cplx* ib = inv + (long)b * GNB_NB * GNB_NB;
+    for (int r = blockIdx.x * 8 + (t >> 5); r < N; r += gridDim.x * 8) {
+        const bool piv = (r >= c0 && r < c0 + GNB_NB);
+        const cplx v = piv ? ib[(r - c0) * GNB_NB + col] : cmake(0.0, 0.0);
+        Ab[(long)r * ld + c0 + col] = v;
+        if (piv)
+            Wpk[(long)b * strideWk + ((long)(r >> 4) * ncb + (c0 >> 5)) * RK_WBLK + (r & 15) * RK_WPS + col] = v;
+    }
+}
+
 // Row moves of blocks [blk_lo, blk_hi) applied, in order, to a 32-column tile of A.
 template <typename ET>
 __device__ __forceinline__ void rk_moves_tile(ET* __restrict__ Xb, long ldx, int col, bool colok, const int* __restrict__ moves,
@@ -858,6 +876,7 @@ static int g_rk_sms = 148;
 static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
 static const size_t kWmSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WM_BS) * sizeof(cplx);
 static int g_rk_wsolve_mma = 1;  // leaf forward-W products on the FP64 tensor pipe
+static int g_rk_fin_mma = 1;     // JORDAN pivot-column update A[:,K] = -P inv as a rank-32 strip update on the tensor pipe
 static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
 
 cudaError_t gnb_rec_init() {
@@ -886,6 +905,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_strip")) g_rk_strip = value;
     else if (!strcmp(name, "rk_real")) g_rk_real = value;
     else if (!strcmp(name, "rk_wsolve_mma")) g_rk_wsolve_mma = value;
+    else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
 }
 
 // Developer trace: CUDA events around every launch of the engine, per stream (tools/trace_elim.py).
@@ -1048,7 +1068,12 @@ struct Rec {
                                                   ws.stridePkR);
             launches++;
         }
-        if (jordan) {
+        if (jordan && g_rk_fin_mma && N >= 128) {
+            dim3 grid(std::min(cdiv_i(N, 8), 64), M);
+            k_rk_panel_prep<<<grid, 256, 0, st>>>(A, strideA, ld, N, c0, inv(c0), ws.Wpk, ws.strideWk, ncb);
+            launches++;
+            gemm(0, N, c0, c0 + GNB_NB, c0, c0 + GNB_NB, ws.Ppk, 0);
+        } else if (jordan) {
             dim3 grid(cdiv_i(N, PF_ROWS), M);
             k_rk_panel_fin<<<grid, 128, kPfSmem, st>>>(A, strideA, ld, N, c0, inv(c0), ws.Ppk, ws.stridePk, nrb);
             launches++;

@@ -196,7 +196,7 @@ def _set(ctx, **opts):
 
 
 DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=2,
-                rk_real=1, mixed_layout=1, rk_strip=1, rk_wsolve_mma=1)
+                rk_real=1, mixed_layout=1, rk_strip=1, rk_wsolve_mma=1, rk_fin_mma=1)
 
 
 @pytest.mark.parametrize("N,nc", [(96, 8), (100, 7), (256, 16), (416, 33), (600, 40)])
@@ -226,7 +226,7 @@ def test_recursive_engine_matches_two_level_engine_and_numpy(ctx, N, nc):
 
 
 @pytest.mark.parametrize("opt", ["rk_m3", "rk_kskip", "contacts_last", "tourn_fp32", "rec_streams", "rk_real",
-                                 "mixed_layout", "rk_strip", "rk_wsolve_mma"])
+                                 "mixed_layout", "rk_strip", "rk_wsolve_mma", "rk_fin_mma"])
 def test_recursive_engine_switches_do_not_change_results(ctx, opt):
     """3M arithmetic, block-upper K skipping, contacts-last ordering, FP32 nominating rounds and sub-batch streams
     are performance switches: results must stay within the parity tolerance of the plain path."""
