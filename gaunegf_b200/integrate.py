@@ -34,7 +34,12 @@ def _device_of(ctx):
     return torch.device("cuda", ctx.device)
 
 
-def _gr_partial(ctx, plan, N):
+def _reinstall(ctx, F, S):
+    ctx.set_system(F, S)
+    ctx.sigma_clear()
+
+
+def _gr_partial(ctx, plan, N, F, S):
     def run(E, w, out):
         ptr_ = out.data_ptr() if out is not None else None
         if plan.kind == DESC:
@@ -45,7 +50,9 @@ def _gr_partial(ctx, plan, N):
         step = max(1, _DENSE_STAGE_BYTES // (16 * N * N))
         acc = np.zeros((N, N), dtype=complex)
         for k in range(0, E.size, step):
-            acc += ctx.gr_int_dense(E[k:k + step], w[k:k + step], plan.sigma_total_batch(E[k:k + step]))
+            st = plan.sigma_total_batch(E[k:k + step])
+            _reinstall(ctx, F, S)          # g.sigmaTot may itself have used this context (e.g. a surfGBAt)
+            acc += ctx.gr_int_dense(E[k:k + step], w[k:k + step], st)
         if out is not None:
             import torch
             out.copy_(torch.from_numpy(acc))
@@ -63,7 +70,7 @@ def GrInt(F, S, g, Elist, weights):
     plan = ObjectPlan(g, N)
     plan.install(ctx)
     parallel_logger.info("Calculating G^R with GInt on B200: %dx%d, %d energies", N, N, Elist.size)
-    run = _gr_partial(ctx, plan, N)
+    run = _gr_partial(ctx, plan, N, F, S)
     _, world = parallel.dist_info()
     return parallel.sharded_matrix_sum(N, Elist, weights, run, device=_device_of(ctx) if world > 1 else None)
 
@@ -95,6 +102,7 @@ def GrLessInt(F, S, g, Elist, weights, ind=None):
             st = plan.sigma_total_batch(Ek)
             sg = st if ind is None else plan.sigma_batch(Ek, ind)
             gam = 1j * (sg - sg.conj().transpose(0, 2, 1))
+            _reinstall(ctx, F, S)
             acc += ctx.gless_int_dense(Ek, w[k:k + step], st, gam)
         if out is not None:
             import torch
@@ -104,3 +112,21 @@ def GrLessInt(F, S, g, Elist, weights, ind=None):
 
     _, world = parallel.dist_info()
     return parallel.sharded_matrix_sum(N, Elist, weights, run, device=_device_of(ctx) if world > 1 else None)
+
+
+# ---- the reference's per-point matrix functions (integrate.py:67-82), same names and signatures ----------------
+def _gr_matrix_ops(sigTot, E, F, S):
+    """G^R(E) = (E S - F - Sigma)^-1 at one energy (integrate.py:67-71)."""
+    ctx = default_context()
+    ctx.set_system(np.asarray(F), np.asarray(S))
+    ctx.sigma_clear()
+    return ctx.green_dense(np.array([E], dtype=complex), np.asarray(sigTot, dtype=complex))[0]
+
+
+def _gless_matrix_ops(sig, sigTot, E, F, S):
+    """G^R i(sig - sig^H) G^A at one energy (integrate.py:74-82)."""
+    ctx = default_context()
+    ctx.set_system(np.asarray(F), np.asarray(S))
+    ctx.sigma_clear()
+    return ctx.gless_int_dense(np.array([E], dtype=complex), np.ones(1, dtype=complex), np.asarray(sigTot, dtype=complex),
+                               gamma_of(np.asarray(sig, dtype=complex)))

@@ -112,6 +112,8 @@ class ObjectPlan:
         return 2
 
     def sigma_total_batch(self, Elist):
+        if self.full is None and getattr(self.g, "_gnb_batched", False):      # provider evaluates the batch in one call
+            return np.asarray(self.g.sigmaTot(np.asarray(Elist)), dtype=complex)
         return np.stack([self.sigma_total(E) for E in Elist])
 
     def sigma_batch(self, Elist, i):

@@ -9,7 +9,8 @@ the reference (or any Slater-Koster code) and hand them to surfGBAt / surfGB.fro
 import numpy as np
 
 from ._native import default_context
-from .config import ETA, TEMPERATURE, SURFACE_GREEN_CONVERGENCE, BETHE_MAX_ITER, BETHE_MIXING
+from .config import (ETA, TEMPERATURE, SURFACE_GREEN_CONVERGENCE, BETHE_MAX_ITER, BETHE_MIXING, ENERGY_MIN,
+                     FERMI_CALCULATION_TOL)
 
 dim = 9
 
@@ -74,14 +75,26 @@ class surfGBAt:
     def setF(self, F, mu1, mu2):
         pass
 
+    _gnb_batched = True        # sigmaTot accepts an array of energies (one GPU call for the whole batch)
+
     def sigmaTot(self, E, conv=SURFACE_GREEN_CONVERGENCE):
-        sigK = np.asarray(self.sigmaK(E, conv))
+        """self-energy of the 13-site extended system (surfGBethe.py:1110-1136): every neighbour site carries the
+        bulk total minus the direction pointing back at the centre; the centre itself carries none"""
+        Es = np.atleast_1d(np.asarray(E, dtype=complex))
+        sigK = np.asarray(self.sigmaK(Es, conv))                  # (M, 12, 9, 9)
         n = self.NN
-        sig = np.zeros(((n + 1) * dim, (n + 1) * dim), dtype=complex)
-        tot = np.sum(sigK, axis=0)
+        sig = np.zeros((len(Es), (n + 1) * dim, (n + 1) * dim), dtype=complex)
+        tot = np.sum(sigK, axis=1)
         for k in range(n):
-            sig[k * dim:(k + 1) * dim, k * dim:(k + 1) * dim] = tot - sigK[(k + 6) % 12]
-        return sig
+            sig[:, k * dim:(k + 1) * dim, k * dim:(k + 1) * dim] = tot - sigK[:, (k + 6) % 12]
+        return sig[0] if np.ndim(E) == 0 else sig
+
+    def calcFermi(self, ne, fGuess=5, tol=FERMI_CALCULATION_TOL):
+        """Fermi level of the Bethe lattice holding `ne` electrons on the centre atom's 9 orbitals
+        (surfGBethe.py:1159-1186): density.getFermiContact on the extended system F, S"""
+        from .density import getFermiContact
+        self.fermi = getFermiContact(self, ne, tol, ENERGY_MIN, 1000, T=self.T, nOrbs=dim)
+        return self.fermi
 
     def DOS(self, E):
         """bulk DOS of the Bethe lattice (surfGBethe.py:1139-1155); the 9x9 inverse runs on the GPU"""

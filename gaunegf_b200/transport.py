@@ -114,9 +114,10 @@ def _transmission_batch(F, S, calc, energies, spin):
             step = max(1, (1 << 30) // (48 * n * n))
             for k in range(0, E.size, step):
                 Ek = E[k:k + step]
-                out[k:k + step] = ctx.transmission_dense(Ek, _batched_sigma(calc, Ek, spin, n, 'tot'),
-                                                         _batched_sigma(calc, Ek, spin, n, 0),
-                                                         _batched_sigma(calc, Ek, spin, n, -1))
+                st, g1, g2 = (_batched_sigma(calc, Ek, spin, n, which) for which in ('tot', 0, -1))
+                ctx.set_system(F, S)       # the provider's sigma() may itself have used this context
+                ctx.sigma_clear()
+                out[k:k + step] = ctx.transmission_dense(Ek, st, g1, g2)
             return out
         return parallel.sharded_per_energy(energies, generic)
 
@@ -143,6 +144,8 @@ def _transmission_batch(F, S, calc, energies, spin):
             st, g1, g2 = (a[:, perm][:, :, perm] for a in (st, g1, g2))
         if const:
             st, g1, g2 = st[0], g1[0], g2[0]
+        ctx.set_system(Fm, Sm)
+        ctx.sigma_clear()
         return ctx.transmission_spin(E, st, g1, g2)
 
     T4 = parallel.sharded_per_energy(energies, spin_fn, width=4)
@@ -165,6 +168,13 @@ def _dos_batch(F, S, calc, energies, spin):
     if spin not in _SPINS:
         raise ValueError(f"Unknown spin configuration '{spin}'. Use 'r', 'u', 'ro', or 'g'")
     ctx.set_system(F, S)
+
+    def _host_sigma_dos(E):        # Sigma(E) from the provider on the host, inverse and reduction on the GPU
+        st = _batched_sigma(calc, E, spin, n, 'tot')
+        ctx.set_system(F, S)       # the provider's sigmaTot() may itself have used this context
+        ctx.sigma_clear()
+        return np.column_stack(ctx.dos_dense(E, st)[::-1])
+
     if spin == 'r':
         plan = calc._plan(n)
         plan.install(ctx)
@@ -174,11 +184,11 @@ def _dos_batch(F, S, calc, energies, spin):
             st = plan.sigma_total()
             fn = lambda E: np.column_stack(ctx.dos_dense(E, st)[::-1])        # noqa: E731
         else:
-            fn = lambda E: np.column_stack(ctx.dos_dense(E, _batched_sigma(calc, E, spin, n, 'tot'))[::-1])  # noqa: E731
+            fn = _host_sigma_dos
     else:
         ctx.sigma_clear()
         if calc.energy_dependent:
-            fn = lambda E: np.column_stack(ctx.dos_dense(E, _batched_sigma(calc, E, spin, n, 'tot'))[::-1])  # noqa: E731
+            fn = _host_sigma_dos
         else:
             st = calc.get_sigma_total(None, spin, n).astype(complex)
             fn = lambda E: np.column_stack(ctx.dos_dense(E, st)[::-1])        # noqa: E731
@@ -441,3 +451,34 @@ def DOSE(Elist, F, S, g):
     for E, dos in zip(Elist, dos_values):
         print("Energy:", E, "eV, DOS=", dos)
     return dos_values.tolist(), dos_per_site_list
+
+
+# ---- the reference's single-point kernels (transport.py:150-190), same names and signatures -------------------
+# One energy per call, like the reference's jitted functions; the batched drivers above are the fast path.
+def _one_energy_system(F, S):
+    ctx = default_context()
+    ctx.set_system(np.asarray(F), np.asarray(S))
+    ctx.sigma_clear()
+    return ctx
+
+
+def _transmission_kernel_restricted(E, F, S, sigma_total, gamma1, gamma2):
+    """Re Tr[Gamma1 G Gamma2 G^H] at one energy (transport.py:150-157)."""
+    ctx = _one_energy_system(F, S)
+    return float(ctx.transmission_dense(np.array([E]), np.asarray(sigma_total, dtype=complex),
+                                        np.asarray(gamma1, dtype=complex), np.asarray(gamma2, dtype=complex))[0])
+
+
+def _transmission_kernel_spin_block(E, F, S, sigma_total, gamma1, gamma2):
+    """(total, [uu, ud, du, dd]) spin-block transmissions of a 2N x 2N system (transport.py:159-181)."""
+    ctx = _one_energy_system(F, S)
+    T4 = ctx.transmission_spin(np.array([E]), np.asarray(sigma_total, dtype=complex),
+                               np.asarray(gamma1, dtype=complex), np.asarray(gamma2, dtype=complex))[0]
+    return float(np.sum(T4)), np.asarray(T4)
+
+
+def _dos_kernel(E, F, S, sigma_total):
+    """(total, per-orbital) -Im diag(G)/pi at one energy (transport.py:183-190)."""
+    ctx = _one_energy_system(F, S)
+    tot, per = ctx.dos_dense(np.array([E]), np.asarray(sigma_total, dtype=complex))
+    return float(tot[0]), per[0]

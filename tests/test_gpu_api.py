@@ -265,3 +265,41 @@ def test_n2_fermi_searches(golden):
     from gaunegf_b200.surfG1D import surfG
     from n2_cases import run_cases, compare
     compare(run_cases(D, surfGTest, surfG), golden("n2_fermi"), 1e-8)
+
+
+def test_single_point_kernels():
+    """the reference's per-energy kernels under their own names (transport.py:150-190, integrate.py:67-82)"""
+    from gaunegf_b200 import transport as tr, integrate as it
+    N = 40
+    F, S = sy.hermitian_pair(N, seed=21)
+    rng = np.random.default_rng(3)
+    def sig(n0, n1, im):
+        s = np.zeros((N, N), complex)
+        b = rng.standard_normal((n1 - n0, n1 - n0)) * 0.03
+        s[n0:n1, n0:n1] = (b + b.T) / 2 - 1j * im * np.eye(n1 - n0)
+        return s
+    s1, s2 = sig(0, 6, 0.1), sig(N - 6, N, 0.2)
+    st, g1, g2 = s1 + s2, 1j * (s1 - s1.conj().T), 1j * (s2 - s2.conj().T)
+    E = 0.37
+    assert abs(tr._transmission_kernel_restricted(E, F, S, st, g1, g2) - O.transmission_restricted(E, F, S, st, g1, g2)) < 1e-10
+    tot, per = tr._dos_kernel(E, F, S, st)
+    rt, rp = O.dos_kernel(E, F, S, st)
+    assert abs(tot - rt) < 1e-10 * abs(rt) and relerr(per, rp) < TOL
+    assert relerr(it._gr_matrix_ops(st, E + 0.1j, F, S), O.gr_matrix(st, E + 0.1j, F, S)) < TOL
+    assert relerr(it._gless_matrix_ops(s1, st, E, F, S), O.gless_matrix(s1, st, E, F, S)) < TOL
+    k = np.kron
+    F2, S2, st2 = k(np.eye(2), F) + 0.01 * k(np.array([[0, 1], [1, 0]]), np.eye(N)), k(np.eye(2), S), k(np.eye(2), st)
+    tt, t4 = tr._transmission_kernel_spin_block(E, F2, S2, st2, k(np.eye(2), g1), k(np.eye(2), g2))
+    rtt, rt4 = O.transmission_spin_block(E, F2, S2, st2, k(np.eye(2), g1), k(np.eye(2), g2))
+    assert relerr(t4, rt4) < TOL and abs(tt - rtt) < 1e-10 * abs(rtt)
+
+
+def test_bethe_atom_calcFermi(golden):
+    """surfGBAt.calcFermi (surfGBethe.py:1159-1186): the Fermi level the reference's surfGB constructor finds for the
+    Au Bethe lattice (ne/2 = 5.5 electrons on the 9 centre orbitals) is stored with the cfg 5 goldens"""
+    from gaunegf_b200.surfGBethe import surfGBAt
+    G = golden("cfg5_bethe")
+    at = surfGBAt(G["H"][0], G["Slist"][0], G["Vlist"][0], float(G["eta"]))
+    mu = quiet(at.calcFermi, 5.5)
+    assert abs(mu - float(G["fermi"])) < 1e-6
+    assert at.fermi == mu
