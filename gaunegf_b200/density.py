@@ -644,3 +644,16 @@ def bisectFermi(V, Vc, D, Gam, Nexp, conv=FERMI_CALCULATION_TOL, Eminf=ENERGY_MI
         print('Warning: Bisection search timed out after 1000 iterations!')
     print(f'Bisection fermi search converged to {dN:.2E} in {Niter} iterations.')
     return fermi_level
+
+
+def integratePoints(computePointFunc, numPoints, parallel=False, numWorkers=None, chunkSize=None, debug=False):
+    """sum_i computePointFunc(i), i = 0 .. numPoints-1 (density.py:121-208).  The reference's process-pool branch
+    exists to spread CPU solves over cores; here every point function already runs its linear algebra on the GPU
+    (batch the points through GrInt / GrLessInt instead), so the points are simply accumulated in order and
+    `parallel`, `numWorkers`, `chunkSize` are accepted for signature compatibility only."""
+    if debug:
+        print(f'Number of points to integrate: {numPoints}')
+    result = np.zeros_like(computePointFunc(0))
+    for i in range(int(numPoints)):
+        result += computePointFunc(i)
+    return result

@@ -17,3 +17,14 @@ def fractional_matrix_power(S, power):
     w, v = np.linalg.eigh(np.asarray(S))
     w = np.maximum(w, 1e-16)
     return v @ np.diag(np.power(w, power)) @ v.conj().T
+
+
+def eig(A):
+    """eigenvalues / right eigenvectors of a general matrix (utils.py:56-58).  Setup-time host linear algebra
+    (Fermi-level guesses of density.getFermiContact); nothing on the energy grid calls it."""
+    return np.linalg.eig(np.asarray(A))
+
+
+def eigh(A):
+    """eigh as the reference calls it (utils.py:60-62): lower triangle of A, ascending eigenvalues."""
+    return np.linalg.eigh(np.asarray(A))
