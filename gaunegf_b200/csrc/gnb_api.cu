@@ -66,7 +66,7 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     DevBuf* bufs[] = {&c->dF, &c->dS, &c->dSig0, &c->A, &c->Pws, &c->LU, &c->moves, &c->cand0, &c->cand1,
                       &c->perm, &c->invperm, &c->info, &c->dE, &c->dW, &c->G, &c->Y, &c->Z, &c->Xr, &c->out,
                       &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
-                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->PpkR, &c->WpkR, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct};
+                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->PpkR, &c->WpkR, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct, &c->cgw, &c->cA2, &c->cB2, &c->cgw2};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < GNB_MAX_SUBSTREAMS; i++) {
         if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
@@ -105,6 +105,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
     else if (!strcmp(name, "small_fused")) g_small = value;
     else if (!strcmp(name, "chain_joint")) g_chain_joint = value;
+    else if (!strcmp(name, "chain_compact")) gnb_chain_set_compact(value);
     else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;

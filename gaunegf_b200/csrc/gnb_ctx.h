@@ -89,7 +89,7 @@ struct gnb_ctx {
     DevBuf A, Pws, LU, moves, cand0, cand1, perm, invperm, info, dE, dW, G, Y, Z, Xr, out, dT, dDosT, dDosP,
         sigB, gam1B, gam2B, cols, rows, in_stage, Ppk, Lpk, Wpk, PpkR, WpkR;
     // chain1d fixed-point workspaces
-    DevBuf cA, cB, cg, cgn, cT1, cM, cflags, ct;
+    DevBuf cA, cB, cg, cgn, cT1, cM, cflags, ct, cgw, cA2, cB2, cgw2;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double elim_ms = 0.0;
     bool timing = false;
@@ -97,6 +97,7 @@ struct gnb_ctx {
 
 // gnb_sigma.cu
 int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma, const cplx* g_ready = nullptr);
+void gnb_chain_set_compact(int on);
 int gnb_chain1d_surface_g_multi(gnb_ctx* c, Contact* const* cts, int K, int M, const cplx* dE);   // g_k in c->cg + k*M*nc*nc
 int gnb_chain1d_surface_g(gnb_ctx* c, Contact& ct, int M, const cplx* dE);     // leaves g in c->cg
 int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cplx* d_out);

@@ -906,6 +906,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_real")) g_rk_real = value;
     else if (!strcmp(name, "rk_wsolve_mma")) g_rk_wsolve_mma = value;
     else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
+    else if (!strcmp(name, "rk_sms") && value > 0) g_rk_sms = value;      // CTAs of the persistent rank-K kernels
 }
 
 // Developer trace: CUDA events around every launch of the engine, per stream (tools/trace_elim.py).

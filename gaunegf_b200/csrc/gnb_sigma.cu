@@ -98,6 +98,9 @@ __global__ void k_chain_export(const ChainFlags* f, const double* diffs, int M, 
     if (b < M) { iters[b] = f[b].count; dout[b] = diffs[b]; }
 }
 
+static int g_chain_compact = 1;        // developer switch "chain_compact"
+void gnb_chain_set_compact(int on) { g_chain_compact = on; }
+
 static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
     int rc;
     if (gnb_small_enabled() && nc <= gnb_small_max_n()) {    // one CTA per matrix, on chip (gnb_small.cu)
@@ -124,20 +127,58 @@ static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
 // chunk, as ONE lock-step batch of K * M fixed-point problems (problem k * M + e): the iteration is a chain of ~30
 // short, latency-bound launches, so two contacts in one batch cost far less than two batches.
 // g of contact k -> c->cg + k * M * nc * nc ; iteration counts -> cts[k]->iters / diffs
+// Active-set compaction: every `check_every` iterations the host reads the per-problem flags; when enough problems
+// have converged, the live ones (A, B, g, flags) are gathered into a dense prefix of a second buffer set and the
+// lock-step batch shrinks (converged problems are frozen by the reference's while_loop anyway, so retiring them
+// changes nothing).  c->cg / fin_flags / fin_diffs hold the results in the ORIGINAL problem order.
+__global__ void __launch_bounds__(256) k_chain_gather(int nn, const int* __restrict__ src_slot, const cplx* __restrict__ A0,
+                                                      const cplx* __restrict__ B0, const cplx* __restrict__ g0,
+                                                      cplx* __restrict__ A1, cplx* __restrict__ B1, cplx* __restrict__ g1) {
+    const long s = (long)src_slot[blockIdx.y] * nn, d = (long)blockIdx.y * nn;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
+        A1[d + i] = A0[s + i]; B1[d + i] = B0[s + i]; g1[d + i] = g0[s + i];
+    }
+}
+// results of the current slots -> original problem order
+__global__ void __launch_bounds__(256) k_chain_scatter(int nn, const int* __restrict__ slot_prob, const cplx* __restrict__ g,
+                                                       const ChainFlags* __restrict__ f, const double* __restrict__ diffs,
+                                                       cplx* __restrict__ g_fin, ChainFlags* __restrict__ f_fin,
+                                                       double* __restrict__ d_fin) {
+    const int slot = blockIdx.y, prob = slot_prob[slot];
+    const long s = (long)slot * nn, d = (long)prob * nn;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) g_fin[d + i] = g[s + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { f_fin[prob] = f[slot]; d_fin[prob] = diffs[slot]; }
+}
+__global__ void k_chain_gather_flags(int n, const int* __restrict__ src_slot, const ChainFlags* __restrict__ f0,
+                                     const double* __restrict__ d0, ChainFlags* __restrict__ f1, double* __restrict__ d1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { f1[i] = f0[src_slot[i]]; d1[i] = d0[src_slot[i]]; }
+}
+
 int gnb_chain1d_surface_g_multi(gnb_ctx* c, Contact* const* cts, int K, int M, const cplx* dE) {
     const Contact& ct = *cts[0];
     const int nc = ct.nc;
     const long nn = (long)nc * nc;
     const int MT = K * M;
     const size_t bytes = (size_t)MT * nn * sizeof(cplx);
+    const size_t fbytes = (size_t)MT * (sizeof(ChainFlags) + sizeof(double)) + 64;
     GNB_CK(c->cA.ensure(bytes)); GNB_CK(c->cB.ensure(bytes)); GNB_CK(c->cg.ensure(bytes));
     GNB_CK(c->cgn.ensure(bytes)); GNB_CK(c->cT1.ensure(bytes)); GNB_CK(c->cM.ensure(bytes));
-    GNB_CK(c->cflags.ensure((size_t)MT * (sizeof(ChainFlags) + sizeof(double)) + 64));
-    cplx *A = c->cA.as<cplx>(), *B = c->cB.as<cplx>(), *g = c->cg.as<cplx>(), *gn = c->cgn.as<cplx>(),
-         *T1 = c->cT1.as<cplx>(), *Mx = c->cM.as<cplx>();
-    ChainFlags* flags = c->cflags.as<ChainFlags>();
+    GNB_CK(c->cgw.ensure(bytes));
+    GNB_CK(c->cflags.ensure(3 * fbytes + 2 * (size_t)MT * sizeof(int)));
+    // buffer set 0: cA, cB, cgw ; set 1 (allocated at the first compaction): cA2, cB2, cgw2
+    cplx *A = c->cA.as<cplx>(), *B = c->cB.as<cplx>(), *g = c->cgw.as<cplx>(), *gn = c->cgn.as<cplx>(),
+         *T1 = c->cT1.as<cplx>(), *Mx = c->cM.as<cplx>(), *g_fin = c->cg.as<cplx>();
+    char* fb = c->cflags.as<char>();
+    ChainFlags* flags = reinterpret_cast<ChainFlags*>(fb);
     double* diffs = reinterpret_cast<double*>(flags + MT);
     int* d_nact = reinterpret_cast<int*>(diffs + MT);
+    ChainFlags* flags2 = reinterpret_cast<ChainFlags*>(fb + fbytes);
+    double* diffs2 = reinterpret_cast<double*>(flags2 + MT);
+    ChainFlags* fin_flags = reinterpret_cast<ChainFlags*>(fb + 2 * fbytes);
+    double* fin_diffs = reinterpret_cast<double*>(fin_flags + MT);
+    int* d_slot_prob = reinterpret_cast<int*>(fb + 3 * fbytes);
+    int* d_src_slot = d_slot_prob + MT;
     cudaStream_t st = c->stream;
 
     dim3 pg(std::min(cdiv_i(nn, 256), 1024), M);
@@ -156,32 +197,69 @@ int gnb_chain1d_surface_g_multi(gnb_ctx* c, Contact* const* cts, int K, int M, c
     k_chain_init_flags<<<cdiv_i(MT, 256), 256, 0, st>>>(flags, diffs, MT, ct.max_iter);
     c->launches++;
 
+    std::vector<int> slot_prob(MT), src_slot;
+    for (int i = 0; i < MT; i++) slot_prob[i] = i;
+    std::vector<ChainFlags> hflags(MT);
+    bool prob_uploaded = false;
+    int Mcur = MT;
+    const dim3 cp_grid_x(std::min(cdiv_i(nn, 256), 64));
+    auto scatter_current = [&]() -> int {                           // current slots -> original order
+        if (!prob_uploaded)
+            GNB_CK(cudaMemcpyAsync(d_slot_prob, slot_prob.data(), (size_t)Mcur * sizeof(int), cudaMemcpyHostToDevice, st));
+        prob_uploaded = true;
+        k_chain_scatter<<<dim3(cp_grid_x.x, Mcur), 256, 0, st>>>((int)nn, d_slot_prob, g, flags, diffs, g_fin, fin_flags,
+                                                                 fin_diffs);
+        c->launches++;
+        return GNB_OK;
+    };
+
     GnbGemmArgs ga{};
     ga.ilo = 0; ga.ihi = nc; ga.jlo = 0; ga.jhi = nc; ga.kdim = nc; ga.skip_lo = ga.skip_hi = -1;
     ga.strideC = ga.strideP = ga.strideW = nn; ga.ldc = ga.ldp = ga.ldw = nc;
     const int check_every = 16;
-    for (int it = 0; it < ct.max_iter; it++) {
+    for (int it = 0; it < ct.max_iter && Mcur > 0; it++) {
+        const size_t cur_bytes = (size_t)Mcur * nn * sizeof(cplx);
         ga.C = T1; ga.P = B; ga.W = g; ga.zero_init = 1; ga.plus = 1;        // T1 = B g
-        gnb_launch_gemm(st, ga, MT, false, false);
-        GNB_CK(cudaMemcpyAsync(Mx, A, bytes, cudaMemcpyDeviceToDevice, st));
+        gnb_launch_gemm(st, ga, Mcur, false, false);
+        GNB_CK(cudaMemcpyAsync(Mx, A, cur_bytes, cudaMemcpyDeviceToDevice, st));
         ga.C = Mx; ga.P = T1; ga.W = B; ga.zero_init = 0; ga.plus = 0;       // Mx = A - T1 B^H
-        gnb_launch_gemm(st, ga, MT, true, false);
+        gnb_launch_gemm(st, ga, Mcur, true, false);
         c->launches += 2;
-        if ((rc = chain_invert(c, MT, nc, Mx, gn))) return rc;              // g_new = inv(A - B g B^H)
-        k_chain_mix<<<MT, 256, 0, st>>>((int)nn, g, gn, flags, diffs, ct.conv, ct.relax, ct.max_iter);
+        if ((rc = chain_invert(c, Mcur, nc, Mx, gn))) return rc;            // g_new = inv(A - B g B^H)
+        k_chain_mix<<<Mcur, 256, 0, st>>>((int)nn, g, gn, flags, diffs, ct.conv, ct.relax, ct.max_iter);
         c->launches++;
         if ((it + 1) % check_every == 0 || it + 1 == ct.max_iter) {
-            int nact = 0;
-            k_chain_count_active<<<1, 256, 0, st>>>(flags, MT, d_nact);
-            c->launches++;
-            GNB_CK(cudaMemcpyAsync(&nact, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GNB_CK(cudaMemcpyAsync(hflags.data(), flags, (size_t)Mcur * sizeof(ChainFlags), cudaMemcpyDeviceToHost, st));
             GNB_CK(cudaStreamSynchronize(st));
+            src_slot.clear();
+            for (int i = 0; i < Mcur; i++)
+                if (hflags[i].active) src_slot.push_back(i);
+            const int nact = (int)src_slot.size();
             if (nact == 0) break;
+            if (g_chain_compact && nact <= Mcur - std::max(8, Mcur / 8) && it + 1 < ct.max_iter) {
+                if ((rc = scatter_current())) return rc;                     // retire: results of every current slot
+                GNB_CK(c->cA2.ensure(bytes)); GNB_CK(c->cB2.ensure(bytes)); GNB_CK(c->cgw2.ensure(bytes));
+                const bool on0 = (A == c->cA.as<cplx>());
+                cplx *A1 = on0 ? c->cA2.as<cplx>() : c->cA.as<cplx>(), *B1 = on0 ? c->cB2.as<cplx>() : c->cB.as<cplx>(),
+                     *g1 = on0 ? c->cgw2.as<cplx>() : c->cgw.as<cplx>();
+                GNB_CK(cudaMemcpyAsync(d_src_slot, src_slot.data(), (size_t)nact * sizeof(int), cudaMemcpyHostToDevice, st));
+                k_chain_gather<<<dim3(cp_grid_x.x, nact), 256, 0, st>>>((int)nn, d_src_slot, A, B, g, A1, B1, g1);
+                k_chain_gather_flags<<<cdiv_i(nact, 256), 256, 0, st>>>(nact, d_src_slot, flags, diffs, flags2, diffs2);
+                c->launches += 2;
+                GNB_CK(cudaStreamSynchronize(st));                           // src_slot / slot_prob are reused on the host
+                for (int i = 0; i < nact; i++) slot_prob[i] = slot_prob[src_slot[i]];
+                A = A1; B = B1; g = g1;
+                std::swap(flags, flags2); std::swap(diffs, diffs2);
+                Mcur = nact;
+                prob_uploaded = false;
+            }
         }
     }
+    (void)d_nact;
+    if ((rc = scatter_current())) return rc;
     for (int k = 0; k < K; k++) {
-        k_chain_export<<<cdiv_i(M, 256), 256, 0, st>>>(flags + (long)k * M, diffs + (long)k * M, M, cts[k]->iters.as<int>(),
-                                                       cts[k]->diffs.as<double>());
+        k_chain_export<<<cdiv_i(M, 256), 256, 0, st>>>(fin_flags + (long)k * M, fin_diffs + (long)k * M, M,
+                                                       cts[k]->iters.as<int>(), cts[k]->diffs.as<double>());
         c->launches++;
     }
     GNB_CK(cudaGetLastError());

@@ -303,14 +303,15 @@ def test_real_structure_shortcut_matches_complex_path(ctx):
 
 @pytest.mark.parametrize("n,nE", [(24, 37), (104, 7)])
 def test_chain_contacts_joint_batch_equals_separate(ctx, n, nE):
-    """two 1-D chain contacts with the same block size iterate as ONE lock-step batch (developer switch chain_joint):
-    per-problem arithmetic is unchanged, so transmission, iteration counts and GrLessInt must agree exactly"""
+    """two 1-D chain contacts with the same block size iterate as ONE lock-step batch (developer switch chain_joint)
+    whose converged problems retire (chain_compact): per-problem arithmetic is unchanged, so transmission, iteration
+    counts and GrLessInt must agree exactly"""
     F, S, li, taus = sy.lead_device_lead(n, 2 * n, seed=5, s_off=0.04)
     E = np.linspace(-0.8, 0.9, nE)
     res = {}
     try:
-        for joint in (1, 0):
-            _set(ctx, chain_joint=joint)
+        for joint, compact in ((1, 1), (0, 0), (1, 0)):
+            _set(ctx, chain_joint=joint, chain_compact=compact)
             ctx.set_system(F, S)
             ctx.sigma_clear()
             for k in range(2):
@@ -320,11 +321,12 @@ def test_chain_contacts_joint_batch_equals_separate(ctx, n, nE):
             T = ctx.transmission(E, 0, -1)
             its = [ctx.sigma_eval(k, 1, E.astype(complex), (n, n))[1] for k in range(2)]
             P = ctx.gless_int(E, np.full(E.size, 0.05), -1)
-            res[joint] = (T, its[0], its[1], P)
+            res[joint + compact] = (T, its[0], its[1], P)
     finally:
-        _set(ctx, chain_joint=1)
-    for a, b in zip(res[1], res[0]):
-        assert np.array_equal(a, b)
+        _set(ctx, chain_joint=1, chain_compact=1)
+    for a, b, c_ in zip(res[2], res[1], res[0]):          # joint + compacted / joint / separate
+        assert np.array_equal(a, b) and np.array_equal(a, c_)
+    res[1] = res[2]
     og = O.surfG1D(F, S, li, taus, eta=0.03)
     Tref = O.calculate_transmission(F, S, O.SigmaCalculator(og, energy_dependent=True), E)
     assert relerr(res[1][0], Tref) < TOL
