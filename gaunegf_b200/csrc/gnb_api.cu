@@ -107,6 +107,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "chain_joint")) g_chain_joint = value;
     else if (!strcmp(name, "chain_compact")) gnb_chain_set_compact(value);
     else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
+    else if (!strcmp(name, "small_cluster")) gnb_small_set_cluster(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
@@ -1014,7 +1015,7 @@ extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, do
         cplx* G;
         if (loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(Aout) + (size_t)k0 * nn;
         else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
-        if (g_small && n <= gnb_small_max_n()) {          // one CTA per matrix, on chip (gnb_small.cu)
+        if (g_small && n <= gnb_small_inverse_max_n()) {  // one CTA (or 2-CTA cluster) per matrix, on chip (gnb_small.cu)
             const cplx* Araw = reinterpret_cast<const cplx*>(Ain) + (size_t)k0 * nn;
             if (loc == GNB_HOST) {
                 if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;

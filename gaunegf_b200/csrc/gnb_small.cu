@@ -464,6 +464,203 @@ void launch_reg(cudaStream_t st, const GnbSmallArgs& a) {
     k_reg_gj<RA, CB, NW><<<a.M, 32 * NW, reg_smem<RA, CB, NW>(a), st>>>(a);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Cluster variant of the register-resident inverse (96 < N <= 128): the matrix columns are spread over the warps of
+// a thread-block CLUSTER of CL CTAs (global warp gw = rank * NW + warp owns columns gw + CL NW b), rows over lanes as
+// before.  The owning warp publishes the multiplier column, the pivot row index and the reciprocal pivot into the
+// shared memory of EVERY CTA of the cluster (st.shared::cluster through mapa), and the per-column barrier is the
+// cluster barrier, split into arrive (by the look-ahead owner, right after publishing) and wait (by everybody at the
+// top of the next step).  GREEN mode only (inverse written out).  Measured (tools/cluster_probe.py,
+// profiles/r01_cluster_probe.json): one launch instead of ~25 latency-bound ones makes utils.inv 1.3-1.6x faster for
+// up to ~64 matrices of n = 128; at the 512-problem lock-step batches of the 1-D chain fixed point (BASELINE cfg 4)
+// the block engine is 7 % faster (3.44 s vs 3.67 s), so only gnb_inverse_batch dispatches here.
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned remote_addr(const void* p, unsigned rank) {
+    unsigned l = (unsigned)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_remote(unsigned addr, cplx v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_remote(unsigned addr, int v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+template <int RA, int CB, int NW, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(32 * NW, 1) k_reg_gj_cl(const GnbSmallArgs a) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    constexpr int NT = 32 * NW, NR = 32 * RA, GW = CL * NW;
+    const int N = a.N, ld = N | 1;
+    cplx* colbuf = reinterpret_cast<cplx*>(sm_raw);                  // [2][NR]
+    cplx* rinfo = colbuf + 2 * NR;                                   // [2]
+    int* piv = reinterpret_cast<int*>(rinfo + 2);                    // [NR]
+    int* invp = piv + NR;                                            // [NR]
+    cplx* slab = reinterpret_cast<cplx*>(invp + NR);                 // [32][ld]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned rank = cluster_rank();
+    const int gw = (int)rank * NW + warp;
+    const int e = blockIdx.x / CL;
+    cplx A[RA][CB];
+
+    {   // ---- assemble: every CTA stages whole 32-row slabs and keeps its own columns
+        const cplx E = a.Araw ? cmake(0.0, 0.0) : a.E[e];
+        const cplx* SB = a.SigB ? a.SigB + (size_t)e * a.strideSigB : nullptr;
+        const cplx* Ar = a.Araw ? a.Araw + (size_t)e * N * N : nullptr;
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int r0 = 32 * ra;
+            for (int rr = warp; rr < 32 && r0 + rr < N; rr += NW)
+                for (int j = lane; j < N; j += 32) {
+                    const size_t g = (size_t)(r0 + rr) * N + j;
+                    cplx v;
+                    if (Ar) v = Ar[g];
+                    else {
+                        v = csub(cmul(E, a.S[g]), a.F[g]);
+                        if (a.Sig0) v = csub(v, a.Sig0[g]);
+                        if (SB) v = csub(v, SB[g]);
+                    }
+                    slab[rr * ld + j] = v;
+                }
+            __syncthreads();
+            for (int cidx = 0; cidx < a.ncontacts; cidx++) {
+                const GnbSmallContact& ct = a.ct[cidx];
+                const cplx* blk = ct.blk + (size_t)e * ct.blk_stride;
+                for (int idx = t; idx < ct.nc * ct.nc; idx += NT) {
+                    const int r = idx / ct.nc, cc = idx - r * ct.nc;
+                    const int row = ct.inds[r] - r0;
+                    if (row >= 0 && row < 32) {
+                        cplx* p = &slab[row * ld + ct.inds[cc]];
+                        *p = csub(*p, blk[idx]);
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                const int j = gw + GW * b;
+                A[ra][b] = (r0 + lane < N && j < N) ? slab[lane * ld + j] : cmake(0.0, 0.0);
+            }
+            __syncthreads();
+        }
+    }
+
+    unsigned used = 0;
+    auto pivot_search = [&](int kk) {
+        const int pr = kk & 1;
+        cplx colv[RA];
+        static_switch<0, CB>(kk / GW, [&](auto B) {
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++) colv[ra] = A[ra][B.value];
+        });
+        int bk = -1, bi = 0x7fffffff;
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) {
+            const int i = lane + 32 * ra;
+            const int key = __float_as_int(__double2float_rn(fma(colv[ra].x, colv[ra].x, colv[ra].y * colv[ra].y))) &
+                            0x7fffffff;
+            if (!((used >> ra) & 1) && i < N && key > bk) { bk = key; bi = i; }
+        }
+        const int kmax = __reduce_max_sync(0xffffffffu, bk);
+        const int p = __reduce_min_sync(0xffffffffu, bk == kmax ? bi : 0x7fffffff);
+        cplx pv = colv[0];
+#pragma unroll
+        for (int ra = 1; ra < RA; ra++)
+            if (ra == (p >> 5)) pv = colv[ra];
+        pv.x = __shfl_sync(0xffffffffu, pv.x, p & 31);
+        pv.y = __shfl_sync(0xffffffffu, pv.y, p & 31);
+        const cplx rcp = crcp_fast(pv);
+#pragma unroll
+        for (unsigned rk = 0; rk < (unsigned)CL; rk++) {             // publish into every CTA of the cluster
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++) st_remote(remote_addr(&colbuf[pr * NR + lane + 32 * ra], rk), colv[ra]);
+            if (lane == 0) {
+                st_remote(remote_addr(&rinfo[pr], rk), rcp);
+                st_remote(remote_addr(&piv[kk], rk), p);
+                st_remote(remote_addr(&invp[p], rk), kk);
+            }
+        }
+        if (lane == 0 && pv.x == 0.0 && pv.y == 0.0) *a.info = 1;
+        static_switch<0, CB>(kk / GW, [&](auto B) {
+#pragma unroll
+            for (int ra = 0; ra < RA; ra++)
+                A[ra][B.value] = cmake((lane == (p & 31) && ra == (p >> 5)) ? 1.0 : 0.0, 0.0);
+        });
+    };
+
+    cluster_arrive();                                                // every CTA of the cluster is resident before
+    cluster_wait();                                                  // anybody addresses a peer's shared memory
+    if (gw == 0) pivot_search(0);
+    cluster_arrive();
+    cluster_wait();
+    for (int k = 0; k < N; k++) {
+        const int par = k & 1;
+        if (k > 0) {
+            if (gw != k % GW) cluster_arrive();                      // the owner of column k arrived when it published
+            cluster_wait();
+        }
+        const int p = piv[k];
+        const cplx r = rinfo[par];
+        const int psrc = p & 31;
+        const bool mine = lane == psrc;
+        if (mine) used |= 1u << (p >> 5);
+        cplx f[RA];
+#pragma unroll
+        for (int ra = 0; ra < RA; ra++) f[ra] = cmul(colbuf[par * NR + lane + 32 * ra], r);
+        const bool next_owner = (k + 1 < N) && gw == (k + 1) % GW;
+        const int kb1 = (k + 1) / GW;
+        static_switch<0, RA>(p >> 5, [&](auto PA) {
+            if (mine) f[PA.value] = cneg(r);
+            auto column = [&](auto B) {
+                cplx v = A[PA.value][B.value];
+                v.x = __shfl_sync(0xffffffffu, v.x, psrc);
+                v.y = __shfl_sync(0xffffffffu, v.y, psrc);
+                if (mine) A[PA.value][B.value] = cmake(0.0, 0.0);
+#pragma unroll
+                for (int ra = 0; ra < RA; ra++) A[ra][B.value] = cfnma(A[ra][B.value], f[ra], v);
+            };
+            if (next_owner) {
+                static_switch<0, CB>(kb1, column);
+                pivot_search(k + 1);
+                cluster_arrive();
+                static_for<0, CB>([&](auto B) {
+                    if (B.value != kb1) column(B);
+                });
+            } else {
+                static_for<0, CB>(column);
+            }
+        });
+    }
+    cluster_arrive();                                                // nobody leaves while a peer may still address it
+    cluster_wait();
+
+    // ---- G[invp[i]][piv[m]] = stored[i][m]
+    cplx* G = a.G + (size_t)e * a.strideG;
+#pragma unroll
+    for (int ra = 0; ra < RA; ra++) {
+        const int i = lane + 32 * ra;
+        if (i >= N) continue;
+        const size_t row = (size_t)invp[i] * a.ldg;
+#pragma unroll
+        for (int b = 0; b < CB; b++) {
+            const int m = gw + GW * b;
+            if (m < N) G[row + piv[m]] = A[ra][b];
+        }
+    }
+}
+
+template <int RA, int CB, int NW, int CL>
+void launch_reg_cl(cudaStream_t st, const GnbSmallArgs& a) {
+    const size_t smem = (size_t)(2 * 32 * RA + 2 + 32 * (a.N | 1)) * sizeof(cplx) + (size_t)2 * 32 * RA * sizeof(int);
+    k_reg_gj_cl<RA, CB, NW, CL><<<a.M * CL, 32 * NW, smem, st>>>(a);
+}
+
 size_t small_smem(int N, int nt) {
     const int ld = N | 1;
     return (size_t)N * ld * sizeof(cplx) + (size_t)(2 * N) * sizeof(int) + (size_t)(nt / 32) * sizeof(double);
@@ -485,12 +682,22 @@ cudaError_t gnb_small_init() {
     if ((e = cudaFuncSetAttribute(k_small_gj<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
-    return cudaFuncSetAttribute(k_reg_gj<3, 6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if ((e = cudaFuncSetAttribute(k_reg_gj<3, 6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    return cudaFuncSetAttribute(k_reg_gj_cl<4, 4, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
+
+static int g_cluster = 1;               // developer switch "small_cluster"
+void gnb_small_set_cluster(int on) { g_cluster = on; }
+// largest n for which a plain inverse (GREEN mode from given matrices) runs on chip
+int gnb_small_inverse_max_n() { return (g_reg_resident && g_cluster) ? GNB_SMALL_CLUSTER_MAX_N : gnb_small_max_n(); }
 
 void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a) {
     if (a.M <= 0) return;
     const int N = a.N;
+    if (g_reg_resident && g_cluster && N > GNB_SMALL_REG_MAX_N && N <= GNB_SMALL_CLUSTER_MAX_N && a.mode == GNB_SMALL_GREEN) {
+        launch_reg_cl<4, 4, 16, 2>(st, a);
+        return;
+    }
     if (g_reg_resident && N <= GNB_SMALL_REG_MAX_N) {
         if (N <= 32) launch_reg<1, 8, 4>(st, a);
         else if (N <= 64) launch_reg<2, 8, 8>(st, a);

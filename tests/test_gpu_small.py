@@ -19,9 +19,10 @@ def _small(ctx, on, reg=1):
 
 
 @pytest.mark.parametrize("reg", [1, 0])
-@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 96, 97, 118, 119, 120])
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 96, 97, 118, 119, 120, 127, 128, 129])
 def test_small_inverse_batch(ctx, n, reg):
-    """utils.inv (utils.py:52-54): reg=1: n <= 96 in registers, above on the block engine; reg=0: n <= 119 in shared memory"""
+    """utils.inv (utils.py:52-54): reg=1: n <= 96 in the registers of one CTA, n <= 128 in those of a 2-CTA cluster, above
+    on the block engine; reg=0: n <= 119 in shared memory"""
     rng = np.random.default_rng(n)
     A = rng.standard_normal((9, n, n)) + 1j * rng.standard_normal((9, n, n))
     A[3] = np.triu(A[3]) + np.eye(n) * 1e-3          # forces row exchanges to matter little / much
@@ -35,6 +36,22 @@ def test_small_inverse_batch(ctx, n, reg):
     ref = np.linalg.inv(A)
     for k in range(9):
         assert relerr(Ai[k], ref[k]) < 1e-11 * max(1.0, np.linalg.cond(A[k]) / 100)
+
+
+def test_cluster_inverse_matches_block_engine(ctx):
+    """96 < n <= 128: 2-CTA-cluster kernel (DSMEM publishing, cluster barrier) vs the block engine"""
+    rng = np.random.default_rng(5)
+    for n in (100, 128):
+        A = rng.standard_normal((300, n, n)) + 1j * rng.standard_normal((300, n, n))
+        res = {}
+        try:
+            for cl in (1, 0):
+                ctx.lib.gnb_dev_set_option(b"small_cluster", cl)
+                res[cl] = ctx.inverse_batch(A)
+        finally:
+            ctx.lib.gnb_dev_set_option(b"small_cluster", 1)
+        assert relerr(res[1], res[0]) < 1e-10
+        assert relerr(res[1][7] @ A[7], np.eye(n)) < 1e-10
 
 
 def test_small_singular_raises(ctx):
