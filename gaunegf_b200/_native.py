@@ -101,6 +101,9 @@ class Context:
         self.h = h
         self.device = device
         self.N = 0
+        # workspace limit in GiB (default 48 GiB inside the library): GNB_WS_GIB=100
+        if os.environ.get("GNB_WS_GIB"):
+            self.lib.gnb_set_workspace_limit(self.h, C.c_size_t(int(float(os.environ["GNB_WS_GIB"]) * (1 << 30))))
         # developer A/B switches: GNB_DEV_OPTS="rk_m3=1,tourn_group=256"
         for kv in filter(None, os.environ.get("GNB_DEV_OPTS", "").split(",")):
             k, v = kv.split("=")
