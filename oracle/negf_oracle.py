@@ -5,9 +5,9 @@ TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's c
 fails loudly when its CUDA library is missing.
 
 Every function cites the reference file:line (under /root/reference/gauNEGF/) whose arithmetic
-it restates.  Parity is PINNED: tests/test_oracle_vs_reference.py checks this module against
+it restates.  Parity is PINNED: tests/test_oracle_golden.py checks this module against
 (a) golden vectors produced by running the unmodified reference under the jax→numpy shim
-(tests/golden/make_golden.py, fixtures committed under tests/golden/) and (b) the live reference
+(tests/golden/make_golden.py, make_golden_n2.py; fixtures committed under tests/golden/) and (b) the live reference
 when /root/reference is present.  Arithmetic is numpy + LAPACK (zgesv), float64/complex128 — the
 same algorithm family the reference's JAX-CPU path dispatches to (the reference ships no golden
 values of its own: SURVEY.md §4).

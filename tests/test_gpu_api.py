@@ -303,3 +303,36 @@ def test_bethe_atom_calcFermi(golden):
     mu = quiet(at.calcFermi, 5.5)
     assert abs(mu - float(G["fermi"])) < 1e-6
     assert at.fermi == mu
+
+
+def test_edge_cases_empty_single_and_mismatched_inputs():
+    """empty energy lists, one energy, a 1-orbital system, mismatched lengths / shapes (integrate.py:85-87 asserts)"""
+    from gaunegf_b200 import transport as tr, integrate as it
+    from gaunegf_b200.surfGTester import surfGTest
+    N = 12
+    F, S = sy.hermitian_pair(N, seed=2)
+    s1, s2 = sy.block_sigma_vectors(N, 2, 0.1)
+    calc = tr.SigmaCalculator(s1, s2)
+    T0 = tr.calculate_transmission(F, S, calc, [])
+    assert np.shape(T0) == (0,)
+    d0, p0 = tr.calculate_dos(F, S, calc, np.array([]))
+    assert np.shape(d0) == (0,) and np.shape(p0) == (0, N)
+    g = surfGTest(F, S, sy.end_contacts(N, 2), -0.1j, -0.1j)
+    og = O.surfGTest(F, S, sy.end_contacts(N, 2), -0.1j, -0.1j)
+    Z = it.GrInt(F, S, g, np.array([]), np.array([]))
+    assert Z.shape == (N, N) and not np.any(Z)
+    assert not np.any(it.GrLessInt(F, S, g, np.array([]), np.array([]), -1))
+    E1 = np.array([0.2])
+    assert relerr(tr.calculate_transmission(F, S, calc, E1), O.calculate_transmission(F, S, O.SigmaCalculator(s1, s2), E1)) < TOL
+    assert relerr(it.GrInt(F, S, g, E1 + 0.3j, np.array([2.0 - 1j])), O.GrInt(F, S, og, E1 + 0.3j, np.array([2.0 - 1j]))) < TOL
+    with pytest.raises(AssertionError):
+        it.GrInt(F, S, g, np.array([0.1, 0.2]), np.array([1.0]))
+    with pytest.raises(AssertionError):
+        it.GrInt(F[:, :-1], S[:, :-1], g, E1, E1)
+    # one orbital: A is a 1 x 1 matrix, both contacts on the same orbital
+    F1, S1 = np.array([[0.3]]), np.array([[1.0]])
+    v = np.array([-0.1j])
+    E = np.linspace(-1, 1, 5)
+    T = quiet(tr.cohTrans, E, F1, S1, v, v)
+    Tref = O.calculate_transmission(F1, S1, O.SigmaCalculator(v, v), E)
+    assert relerr(T, Tref) < TOL
