@@ -104,6 +104,25 @@ def fp64_peak():
         return 37.0, "fallback: B200 nominal FP64 37 TFLOP/s"
 
 
+def host_info():
+    """CPU model and BLAS build the cpu_baseline numbers were measured with"""
+    model, blas = "unknown", "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        cfg = np.show_config(mode="dicts")
+        b = cfg.get("Build Dependencies", {}).get("blas", {})
+        blas = f"{b.get('name', '?')} {b.get('version', '')}".strip()
+    except Exception:
+        pass
+    return {"cpu_model": model, "blas": blas, "threads": "BLAS default = all host cores, one Python process"}
+
+
 def cpu_reference_step(F, S, s1, s2, energies):
     from oracle import negf_oracle as O
     calc = O.SigmaCalculator(s1, s2, energy_dependent=False)
@@ -132,7 +151,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{CPU_SAMPLE} energies of the same N={N_ORB} workload per step: the reference's algorithm "
                                        "(full solve(A, I) + Gamma1 G Gamma2 G^H, transport.py:150-157) restated in numpy/LAPACK "
-                                       "(oracle/negf_oracle.py), BLAS threads = all host cores"},
+                                       "(oracle/negf_oracle.py), BLAS threads = all host cores", **host_info()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -320,7 +339,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": CPU_SAMPLE / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{CPU_SAMPLE} energies of the same workload (numpy/LAPACK port of the reference "
                                               f"algorithm, oracle/negf_oracle.py), BLAS threads = all host cores",
-                                    "max_rel_diff_vs_gpu": float(np.max(np.abs(Tg - Tc)) / np.max(np.abs(Tc)))}
+                                    "max_rel_diff_vs_gpu": float(np.max(np.abs(Tg - Tc)) / np.max(np.abs(Tc))), **host_info()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
