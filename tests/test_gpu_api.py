@@ -336,3 +336,19 @@ def test_edge_cases_empty_single_and_mismatched_inputs():
     T = quiet(tr.cohTrans, E, F1, S1, v, v)
     Tref = O.calculate_transmission(F1, S1, O.SigmaCalculator(v, v), E)
     assert relerr(T, Tref) < TOL
+
+
+def test_legacy_wrappers_and_option_branches(golden):
+    """currentSpin / currentE / currentF(.mat) / cohTransSpinE, densityGridTrap, T > 0 windows, 'legendre' and midpoint
+    contours, adaptive densityGrid / densityReal: against the unmodified reference (tests/golden/make_golden_legacy.py)"""
+    import tempfile
+    import scipy.io as sio
+    from gaunegf_b200 import transport as tr, density as de
+    from gaunegf_b200.surfGTester import surfGTest
+    from legacy_cases import run_cases
+    G = golden("legacy_api")
+    out = run_cases(tr, de, surfGTest, sio, tempfile)
+    assert set(out) == set(G.files)
+    for k, v in out.items():
+        assert np.shape(v) == G[k].shape, k
+        assert relerr(v, G[k]) < TOL, (k, relerr(v, G[k]))
