@@ -108,6 +108,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "chain_compact")) gnb_chain_set_compact(value);
     else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
     else if (!strcmp(name, "small_cluster")) gnb_small_set_cluster(value);
+    else if (!strcmp(name, "small_wide")) gnb_small_set_wide(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);

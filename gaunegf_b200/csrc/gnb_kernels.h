@@ -118,6 +118,7 @@ cudaError_t gnb_small_init();
 void gnb_small_set_reg(int on);        // developer switch "small_reg": register-resident (1) or shared-memory (0) kernel
 int gnb_small_max_n();                 // 96 (register-resident kernel, default) or 119 (small_reg=0)
 int gnb_small_inverse_max_n();         // largest n whose plain inverse runs on chip (128 with the cluster kernel)
+void gnb_small_set_wide(int on);       // developer switch "small_wide"
 void gnb_small_set_cluster(int on);    // developer switch "small_cluster"
 int gnb_small_enabled();               // developer switch "small_fused" (gnb_api.cu)
 void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a);

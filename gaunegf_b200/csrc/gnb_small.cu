@@ -202,7 +202,7 @@ __device__ __forceinline__ void static_for(F&& fn) {
 // write of every matrix element (the shared-memory-resident kernel above is bound by exactly that).  Without row exchanges the in-place result is stored[i][m] = G[invp[i]][piv[m]] (piv[k] = pivot row
 // of step k); the epilogues address G through these two maps.
 template <int RA, int CB, int NW>
-__global__ void __launch_bounds__(32 * NW, (RA * CB <= 16) ? 2 : 1) k_reg_gj(const GnbSmallArgs a) {
+__global__ void __launch_bounds__(32 * NW, (RA * CB <= 8 && NW == 16) ? 2 : (RA * CB <= 16) ? 2 : 1) k_reg_gj(const GnbSmallArgs a) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int NT = 32 * NW, NR = 32 * RA;
     const int N = a.N, ld = N | 1;
@@ -669,6 +669,8 @@ size_t small_smem(int N, int nt) {
 }  // namespace
 
 static int g_reg_resident = 1;          // developer switch "small_reg"
+static int g_reg_wide = 0;              // developer switch "small_wide": N <= 64 on 16 warps x (2 x 4) tiles
+void gnb_small_set_wide(int on) { g_reg_wide = on; }
 void gnb_small_set_reg(int on) { g_reg_resident = on; }
 // Largest N the one-CTA-per-energy path takes.  Measured on B200 (tools/small_probe.py, profiles/r01_small_probe.json):
 // the register-resident kernel beats the lock-step block engine up to its limit of 96; the shared-memory-resident
@@ -682,6 +684,7 @@ cudaError_t gnb_small_init() {
     if ((e = cudaFuncSetAttribute(k_small_gj<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_reg_gj<2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<3, 6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     return cudaFuncSetAttribute(k_reg_gj_cl<4, 4, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
@@ -700,6 +703,7 @@ void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a) {
     }
     if (g_reg_resident && N <= GNB_SMALL_REG_MAX_N) {
         if (N <= 32) launch_reg<1, 8, 4>(st, a);
+        else if (N <= 64 && g_reg_wide) launch_reg<2, 4, 16>(st, a);
         else if (N <= 64) launch_reg<2, 8, 8>(st, a);
         else launch_reg<3, 6, 16>(st, a);
         return;

@@ -26,7 +26,10 @@ def timed(f, reps=5):
     return float(np.median(ts))
 
 
-for N, nc, M in ((64, 1, 1000), (64, 1, 20000), (32, 4, 20000), (96, 16, 20000), (119, 32, 20000), (64, 1, 12), (96, 16, 12), (119, 32, 12), (119, 32, 108)):
+CASES = ((64, 1, 1000), (64, 1, 20000), (32, 4, 20000), (96, 16, 20000), (119, 32, 20000), (64, 1, 12), (96, 16, 12), (119, 32, 12), (119, 32, 108))
+if len(sys.argv) > 1:
+    CASES = CASES[:int(sys.argv[1])]
+for N, nc, M in CASES:
     if nc == 1:
         F, S, s1, s2 = sy.chain(N)
         blocks = [([0], [[s1[0]]]), ([N - 1], [[s2[N - 1]]])]
