@@ -58,11 +58,40 @@ static void release_contact(Contact& ct) {
     for (DevBuf* b : bufs) b->release();
 }
 
+// Contact descriptions are rebuilt for every driver call (sigma_clear + add_*): their device buffers are recycled
+// through a small pool instead of cudaFree / cudaMalloc each time (6 + 6 calls per cohTrans / GrInt call otherwise).
+static void retire_contacts(gnb_ctx* c) {
+    for (auto& ct : c->contacts) {
+        if (c->contact_pool.size() < 16) c->contact_pool.push_back(ct);      // DevBufs are plain pointers: moved, not freed
+        else release_contact(ct);
+    }
+    c->contacts.clear();
+}
+static Contact& new_contact(gnb_ctx* c) {
+    if (!c->contact_pool.empty()) {
+        Contact old = c->contact_pool.back();
+        c->contact_pool.pop_back();
+        Contact fresh;                                   // defaults for every scalar / host field ...
+        DevBuf* src[] = {&old.d_inds, &old.d_const, &old.alpha, &old.Salpha, &old.beta, &old.Sbeta, &old.tau, &old.stau,
+                         &old.d_nb_off, &old.d_nb_dirs, &old.H, &old.Slist, &old.Vlist, &old.blk, &old.gam, &old.iters,
+                         &old.diffs, &old.surf};
+        DevBuf* dst[] = {&fresh.d_inds, &fresh.d_const, &fresh.alpha, &fresh.Salpha, &fresh.beta, &fresh.Sbeta, &fresh.tau,
+                         &fresh.stau, &fresh.d_nb_off, &fresh.d_nb_dirs, &fresh.H, &fresh.Slist, &fresh.Vlist, &fresh.blk,
+                         &fresh.gam, &fresh.iters, &fresh.diffs, &fresh.surf};
+        for (size_t i = 0; i < sizeof(src) / sizeof(src[0]); i++) *dst[i] = *src[i];   // ... and the recycled buffers
+        c->contacts.push_back(fresh);
+    } else {
+        c->contacts.emplace_back();
+    }
+    return c->contacts.back();
+}
+
 extern "C" int gnb_destroy(gnb_ctx* c) {
     if (!c) return GNB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& ct : c->contacts) release_contact(ct);
+    for (auto& ct : c->contact_pool) release_contact(ct);
     DevBuf* bufs[] = {&c->dF, &c->dS, &c->dSig0, &c->A, &c->Pws, &c->LU, &c->moves, &c->cand0, &c->cand1,
                       &c->perm, &c->invperm, &c->info, &c->dE, &c->dW, &c->G, &c->Y, &c->Z, &c->Xr, &c->out,
                       &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
@@ -133,8 +162,7 @@ extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* 
     if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
     cudaSetDevice(c->device);
     if (N != c->N) {                      // a new size invalidates the self-energy description
-        for (auto& ct : c->contacts) release_contact(ct);
-        c->contacts.clear();
+        retire_contacts(c);
         c->has_sig0 = false;
     }
     c->N = N;
@@ -156,8 +184,7 @@ extern "C" int gnb_sigma_clear(gnb_ctx* c) {
     if (!c) return GNB_ERR_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& ct : c->contacts) release_contact(ct);
-    c->contacts.clear();
+    retire_contacts(c);
     c->has_sig0 = false;
     return GNB_OK;
 }
@@ -184,8 +211,7 @@ extern "C" int gnb_sigma_add_const_block(gnb_ctx* c, int nc, const int32_t* inds
     cudaSetDevice(c->device);
     int rc = check_inds(c, nc, inds);
     if (rc) return rc;
-    c->contacts.emplace_back();
-    Contact& ct = c->contacts.back();
+    Contact& ct = new_contact(c);
     ct.kind = GNB_C_CONST;
     ct.nc = nc;
     ct.h_inds.assign(inds, inds + nc);
@@ -207,8 +233,7 @@ extern "C" int gnb_sigma_add_chain1d(gnb_ctx* c, int nc, const int32_t* inds, co
     cudaSetDevice(c->device);
     int rc = check_inds(c, nc, inds);
     if (rc) return rc;
-    c->contacts.emplace_back();
-    Contact& ct = c->contacts.back();
+    Contact& ct = new_contact(c);
     ct.kind = GNB_C_CHAIN1D;
     ct.nc = nc;
     ct.h_inds.assign(inds, inds + nc);
@@ -233,8 +258,7 @@ extern "C" int gnb_sigma_add_bethe(gnb_ctx* c, int natoms, const int32_t* inds, 
     if (rc) return rc;
     for (int i = 0; i < nb_off[natoms]; i++)
         if (nb_dirs[i] < 0 || nb_dirs[i] >= 9) return gnb_fail(c, GNB_ERR_ARG, "bethe: neighbour direction must be in 0..8");
-    c->contacts.emplace_back();
-    Contact& ct = c->contacts.back();
+    Contact& ct = new_contact(c);
     ct.kind = GNB_C_BETHE;
     ct.natoms = natoms;
     ct.nc = natoms * 9;

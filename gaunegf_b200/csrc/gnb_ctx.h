@@ -85,6 +85,7 @@ struct gnb_ctx {
     bool has_sig0 = false;
     bool real_FS = false;          // F and S given with zero imaginary parts (host arrays only)
     std::vector<Contact> contacts;
+    std::vector<Contact> contact_pool;  // retired descriptions whose device buffers are reused (gnb_api.cu)
     // workspaces
     DevBuf A, Pws, LU, moves, cand0, cand1, perm, invperm, info, dE, dW, G, Y, Z, Xr, out, dT, dDosT, dDosP,
         sigB, gam1B, gam2B, cols, rows, in_stage, Ppk, Lpk, Wpk, PpkR, WpkR;
