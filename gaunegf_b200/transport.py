@@ -397,11 +397,22 @@ def currentF(fn, dE=ENERGY_STEP, T=TEMPERATURE):
                    matfile["fermi"][0, 0], matfile["qV"][0, 0], T, matfile["spin"][0], dE=dE)
 
 
+def _plain(seq):
+    """float64 arrays as Python floats: str() gives the same text as for numpy scalars, several times faster"""
+    return seq.tolist() if isinstance(seq, np.ndarray) and seq.dtype == np.float64 and seq.ndim == 1 else seq
+
+
+def _report(Elist, label, values):
+    """the reference prints one line per energy (transport.py:910-911, 1031-1032, 1104-1105); same text, one write"""
+    lines = [f"Energy: {E} eV, {label}= {v}" for E, v in zip(_plain(Elist), _plain(values))]
+    if lines:
+        print("\n".join(lines))
+
+
 def cohTrans(Elist, F, S, sig1, sig2):
     sigma_calc = SigmaCalculator(sig1, sig2, energy_dependent=False)
     transmissions = calculate_transmission(F, S, sigma_calc, Elist, spin='r')
-    for E, T in zip(Elist, transmissions):
-        print("Energy:", E, "eV, Transmission=", T)
+    _report(Elist, "Transmission", transmissions)
     return transmissions.tolist()
 
 
@@ -413,8 +424,7 @@ def cohTransSpin(Elist, F, S, sig1, sig2, spin='u'):
         for i, E in enumerate(Elist):
             print("Energy:", E, "eV, Transmission=", transmissions[i], ", Tspin=", spin_transmissions[i])
         return (transmissions.tolist(), spin_transmissions)
-    for E, T in zip(Elist, result):
-        print("Energy:", E, "eV, Transmission=", T)
+    _report(Elist, "Transmission", result)
     return (result.tolist(), np.zeros((len(Elist), 4)))
 
 
@@ -427,8 +437,7 @@ def DOS(Elist, F, S, sig1, sig2):
 def cohTransE(Elist, F, S, g):
     sigma_calc = SigmaCalculator(g, energy_dependent=True)
     transmissions = calculate_transmission(F, S, sigma_calc, Elist, spin='r')
-    for E, T in zip(Elist, transmissions):
-        print("Energy:", E, "eV, Transmission=", T)
+    _report(Elist, "Transmission", transmissions)
     return transmissions.tolist()
 
 
@@ -440,16 +449,14 @@ def cohTransSpinE(Elist, F, S, g, spin='u'):
         for i, E in enumerate(Elist):
             print("Energy:", E, "eV, Transmission=", transmissions[i], ", Tspin=", spin_transmissions[i])
         return transmissions, spin_transmissions
-    for E, T in zip(Elist, result):
-        print("Energy:", E, "eV, Transmission=", T)
+    _report(Elist, "Transmission", result)
     return result, np.zeros((len(Elist), 4))
 
 
 def DOSE(Elist, F, S, g):
     sigma_calc = SigmaCalculator(g, energy_dependent=True)
     dos_values, dos_per_site_list = calculate_dos(F, S, sigma_calc, Elist, spin='r')
-    for E, dos in zip(Elist, dos_values):
-        print("Energy:", E, "eV, DOS=", dos)
+    _report(Elist, "DOS", dos_values)
     return dos_values.tolist(), dos_per_site_list
 
 
