@@ -9,13 +9,21 @@ per-GPU work fixed).  A "step" is one pass of the hot path over one such batch.
   python bench.py [--gpus N --steps K --warmup W]            our arm (one process per GPU)
   python bench.py --impl reference [...]                     the reference algorithm on the host CPU
 
-Output: ONE JSON line (rank 0).  `value` = whole-job energy points/s with F, S and the contact blocks
-resident in HBM; `e2e` = the same metric through the public API (transport.calculate_transmission)
-with host buffers, H2D/D2H inside the timed region; `roofline` = the rank-K update kernel (the
-dominant kernel) against the measured FP64 tensor-pipe peak; `cpu_baseline` = the numpy/LAPACK
-port of the reference (oracle/) on this box's host cores, bounded sample.
+Output: ONE JSON line (rank 0).
+  value      whole-job energy points/s with F, S and the contact blocks resident in HBM
+  e2e        the same metric through the public API (transport.calculate_transmission) with host buffers; F changes
+             every step, so F, S travel host -> device inside the timed region every step
+  roofline   the rank-K update kernel family (the dominant kernel) against the FP64 tensor-pipe ceiling MEASURED IN
+             THIS RUN (gnb_dev_fp64_peak), plus step_frac = executed flops of all elimination launches / step time / peak
+  parity     max relative deviation of the GPU results of THIS run (at this world size) from the CPU port on a sample
+  secondary* density-matrix integration (GrInt, one NCCL all-reduce per call; cfg5 densityGridN at N=2048), complex-F
+             T(E), N=512
+  cpu_baseline  the numpy/LAPACK port of the reference (oracle/) on this box's host cores, bounded sample, two variants:
+             as shipped (one process, all BLAS threads) and best effort (process pool, 1 BLAS thread per worker)
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -30,25 +38,27 @@ sys.path.insert(0, ROOT)
 
 N_ORB = 1024
 N_CONTACT = 64
+SEED = 1
 E_PER_GPU = 1250          # 10 000 energies over 8 GPUs
-CPU_SAMPLE = 8            # energies per CPU-reference step (about 0.5 s each on 16 cores)
+CPU_SAMPLE = 8            # energies per as-shipped CPU step (about 1 s on 16 cores)
+POOL_PER_WORKER = 2       # energies per worker per best-effort CPU step
 METRIC = "Green's-function energy points/sec at N=1024"
 UNIT = "energy points/s"
 
 
 def workload_desc(n_gpus):
     return {
-        "workload": f"cfg3 transmission T(E): synthetic N={N_ORB} junction (seed 1), {N_CONTACT}-orbital constant "
+        "workload": f"cfg3 transmission T(E): synthetic N={N_ORB} junction (seed {SEED}), {N_CONTACT}-orbital constant "
                     f"contacts, {E_PER_GPU} energy points per GPU per step ({E_PER_GPU * n_gpus} total), grid [-0.5, 0.5] eV",
         "N": N_ORB, "contact_orbitals": N_CONTACT, "energies_per_gpu_per_step": E_PER_GPU,
         "parallelism": f"energy-grid sharding x{n_gpus} (no data-path collective; all-gather of T)",
-        "l2": "per-step working set (1250 x 16.8 MB matrices) exceeds the 126 MB L2; no flush needed",
+        "l2": "per-step working set (1250 x 10.5 MB matrices) exceeds the 126 MB L2; no flush needed",
     }
 
 
 def make_inputs():
     from gaunegf_b200 import synthetic as sy
-    F, S = sy.hermitian_pair(N_ORB, seed=1)
+    F, S = sy.hermitian_pair(N_ORB, seed=SEED)
     s1, s2 = sy.block_sigma_vectors(N_ORB, N_CONTACT, 0.1)
     return F, S, s1, s2
 
@@ -93,17 +103,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def fp64_peak():
-    """FP64 tensor-pipe peak: MEASURED_PEAKS.json holds only bf16/HBM, so the denominator is the
-    DMMA.8x8x4 issue-rate ceiling measured on this pool's B200 by tools/fp64_peak.cu
-    (profiles/r01_fp64_peak_dmma_dfma.json)."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak_dmma_dfma.json")))
-        return max(v for k, v in d.items() if k.startswith("dmma884")), "measured DMMA.8x8x4 ceiling (tools/fp64_peak.cu, this pool)"
-    except Exception:
-        return 37.0, "fallback: B200 nominal FP64 37 TFLOP/s"
-
-
 def host_info():
     """CPU model and BLAS build the cpu_baseline numbers were measured with"""
     model, blas = "unknown", "unknown"
@@ -120,7 +119,19 @@ def host_info():
         blas = f"{b.get('name', '?')} {b.get('version', '')}".strip()
     except Exception:
         pass
-    return {"cpu_model": model, "blas": blas, "threads": "BLAS default = all host cores, one Python process"}
+    return {"cpu_model": model, "blas": blas}
+
+
+@contextlib.contextmanager
+def all_blas_threads():
+    """torchrun exports OMP_NUM_THREADS=1, which would starve the CPU arm: set the BLAS thread count explicitly"""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=n):
+            yield n
+    except ImportError:
+        yield n
 
 
 def cpu_reference_step(F, S, s1, s2, energies):
@@ -131,29 +142,85 @@ def cpu_reference_step(F, S, s1, s2, energies):
     return time.perf_counter() - t, T
 
 
+def cpu_arms(F, S, s1, s2, steps, warmup, rng):
+    """both CPU variants of the reference algorithm on bounded samples of the bench workload.
+    Returns (as_shipped dict, best_effort dict, last as-shipped energies, their T)."""
+    from oracle.cpu_pool import TransmissionPool
+    cores = os.cpu_count() or 1
+    with all_blas_threads():
+        for _ in range(max(1, warmup)):
+            cpu_reference_step(F, S, s1, s2, rng.uniform(-0.5, 0.5, 2))
+        tot, Es, Tc = 0.0, None, None
+        for _ in range(steps):
+            Es = np.sort(rng.uniform(-0.5, 0.5, CPU_SAMPLE))
+            dt, Tc = cpu_reference_step(F, S, s1, s2, Es)
+            tot += dt
+    shipped = {"value": CPU_SAMPLE * steps / tot, "unit": UNIT, "cores": cores, "threads": cores, "processes": 1,
+               "ms_per_step": 1e3 * tot / steps,
+               "sample": f"{CPU_SAMPLE} energies of the N={N_ORB} workload per step, one Python process, BLAS threads = {cores}"}
+    pool = TransmissionPool(N_ORB, N_CONTACT, SEED, workers=cores)
+    try:
+        n_pool = POOL_PER_WORKER * cores
+        for _ in range(max(1, min(warmup, 2))):
+            pool.run(rng.uniform(-0.5, 0.5, cores))
+        ptot = 0.0
+        for _ in range(steps):
+            dt, _ = pool.run(np.sort(rng.uniform(-0.5, 0.5, n_pool)))
+            ptot += dt
+    finally:
+        pool.close()
+    best = {"value": n_pool * steps / ptot, "unit": UNIT, "cores": cores, "threads": 1, "processes": cores,
+            "ms_per_step": 1e3 * ptot / steps,
+            "sample": f"{n_pool} energies per step over a pool of {cores} processes, 1 BLAS thread each (the reference's "
+                      "own recipe: tests/benchmark_sigma_parallelization.py:27-30, 178-212)"}
+    return shipped, best, Es, Tc
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     F, S, s1, s2 = make_inputs()
     rng = np.random.default_rng(0)
-    for _ in range(args.warmup):
-        cpu_reference_step(F, S, s1, s2, rng.uniform(-0.5, 0.5, 2))
-    tot = 0.0
-    for _ in range(args.steps):
-        dt, _ = cpu_reference_step(F, S, s1, s2, np.sort(rng.uniform(-0.5, 0.5, CPU_SAMPLE)))
-        tot += dt
-    val = CPU_SAMPLE * args.steps / tot
-    cores = os.cpu_count()
+    shipped, best, _, _ = cpu_arms(F, S, s1, s2, args.steps, args.warmup, rng)
+    top = best if best["value"] >= shipped["value"] else shipped
+    val = top["value"]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic", "config": workload_desc(args.gpus),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{CPU_SAMPLE} energies of the same N={N_ORB} workload per step: the reference's algorithm "
-                                       "(full solve(A, I) + Gamma1 G Gamma2 G^H, transport.py:150-157) restated in numpy/LAPACK "
-                                       "(oracle/negf_oracle.py), BLAS threads = all host cores", **host_info()},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": top["cores"], "kind": "port",
+                             "sample": top["sample"] + "; the reference's algorithm (full solve(A, I) + Gamma1 G Gamma2 G^H, "
+                                       "transport.py:150-157) restated in numpy/LAPACK (oracle/negf_oracle.py). value = the "
+                                       "faster of the two variants below",
+                             "variant": "best_effort" if top is best else "as_shipped",
+                             "as_shipped": shipped, "best_effort": best, **host_info()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def cfg5_system():
+    """BASELINE cfg 5: N = 2048 device with two 3-atom Bethe-lattice (Au) contacts; contact parameters as produced by the
+    reference's own constructor (tests/golden/cfg5_full.npz, committed fixture)."""
+    from gaunegf_b200 import synthetic as sy
+    from gaunegf_b200.surfGBethe import surfGB, surfGBAt
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cfg5_full.npz"))
+    N = int(G["N"])
+    F, S = sy.hermitian_pair(N, seed=3)
+    gl = [surfGBAt(G["H"][i], G["Slist"][i], G["Vlist"][i], float(G["eta"])) for i in range(2)]
+    lens, flat = G["nInd_len"], list(G["nInd_flat"])
+    nil, p = [], 0
+    for c in lens:
+        cl = []
+        for n in c:
+            cl.append([int(v) for v in flat[p:p + n]])
+            p += n
+        nil.append(cl)
+    return G, F, S, surfGB.from_parts(F, S, gl, G["indsLists"], nil, eta=float(G["eta"]))
 
 
 def run_ours(args):
@@ -165,7 +232,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from gaunegf_b200 import transport as tr
+    from gaunegf_b200 import transport as tr, integrate as it, density as de, parallel, synthetic as sy
     from gaunegf_b200._native import default_context
 
     F, S, s1, s2 = make_inputs()
@@ -184,8 +251,8 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        for k in range(steps):
+            fn(k)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
@@ -194,24 +261,29 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def install_t1024(Fm=F):
+        ctx.set_system(Fm, S)
+        ctx.sigma_clear()
+        ctx.sigma_add_const_block(np.arange(nc), np.diag(s1[:nc]))
+        ctx.sigma_add_const_block(np.arange(N_ORB - nc, N_ORB), np.diag(s2[N_ORB - nc:]))
+
     # ---- device-resident leg: F, S, contact blocks already in HBM ---------------------------
-    ctx.set_system(F, S)
-    ctx.sigma_clear()
-    ctx.sigma_add_const_block(np.arange(nc), np.diag(s1[:nc]))
-    ctx.sigma_add_const_block(np.arange(N_ORB - nc, N_ORB), np.diag(s2[N_ORB - nc:]))
+    install_t1024()
     T_last = [None]
 
-    def step_dev():
+    def step_dev(_k):
         T_last[0] = ctx.transmission(E_loc, 0, -1)
 
-    for _ in range(args.warmup):
-        step_dev()
-    l0 = ctx.launches
+    for k in range(args.warmup):
+        step_dev(k)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    peak = ctx.fp64_peak(300.0)            # FP64 tensor-pipe ceiling of this GPU, now (clocks sampled alongside)
+    l0 = ctx.launches
     ms = timed(step_dev, args.steps)
     launches = ctx.launches - l0
+    elim_flops_step = ctx.last_elim_flops
     value = M_total * args.steps / (ms * 1e-3)
     # roofline leg: the same steps again with a CUDA-event pair around every launch of the rank-K update kernel
     # (on the stream the kernel is launched on); kept out of `value` because the per-launch events cost time.
@@ -224,24 +296,32 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end leg: public API, host buffers, H2D + D2H inside the timed region ---------
-    Fp = torch.from_numpy(F.astype(np.complex128)).pin_memory().numpy()
+    # F changes every step (an SCF loop hands a new Fock matrix to every call), so F and S are uploaded every step
+    Fv = []
+    for d in (0.0, 1e-13):
+        Fx = F.astype(np.complex128)
+        Fx[0, 0] += d
+        Fv.append(torch.from_numpy(Fx).pin_memory().numpy())
     Sp = torch.from_numpy(S.astype(np.complex128)).pin_memory().numpy()
     calc = tr.SigmaCalculator(s1, s2, energy_dependent=False)
     T_e2e = [None]
 
-    def step_e2e():
-        T_e2e[0] = tr.calculate_transmission(Fp, Sp, calc, E_all)
+    def step_e2e(k):
+        T_e2e[0] = tr.calculate_transmission(Fv[k % 2], Sp, calc, E_all)
 
-    step_e2e()
-    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e(1)
+    e2e_steps = max(2, min(args.steps, 6))
+    skipped0 = ctx.system_uploads_skipped
     ms_e2e = timed(step_e2e, e2e_steps)
+    assert ctx.system_uploads_skipped == skipped0, "e2e leg must upload F, S every step"
     e2e_val = M_total * e2e_steps / (ms_e2e * 1e-3)
     h2d = 2 * N_ORB * N_ORB * 16 + 2 * (nc * nc * 16 + nc * 4) + E_loc.size * 16
     d2h = E_loc.size * 8
+    step_e2e(0)
+    ms_e2e_res = timed(lambda k: step_e2e(0), 3)          # unchanged F, S: they stay resident, nothing is re-sent
+    T_full = T_e2e[0].copy()                              # T(E_all) with F = Fv[0], gathered from every rank
 
     # ---- secondary: density-matrix contour integration (GrInt, full G + on-device reduction + all-reduce)
-    from gaunegf_b200 import integrate as it, synthetic as sy
-    from gaunegf_b200.sigma_plan import ArrayPlan
     Mg = 296
     z, w = sy.contour_points(Mg * world, -30.0, 0.0)
 
@@ -256,13 +336,34 @@ def run_ours(args):
             return np.diag(s1 if i == 0 else s2)
     gobj = ConstG()
     P = [None]
+    brk = []
 
-    def step_grint():
-        P[0] = it.GrInt(Fp, Sp, gobj, z, w)
+    def step_grint(_k):
+        P[0] = it.GrInt(Fv[0], Sp, gobj, z, w)
+        if world > 1:
+            brk.append(dict(parallel.last_breakdown))
 
-    step_grint()
-    ms_g = timed(step_grint, 2)
-    grint_val = Mg * world * 2 / (ms_g * 1e-3)
+    step_grint(0)
+    brk.clear()
+    g_steps = 4
+    ms_g = timed(step_grint, g_steps)
+    grint_val = Mg * world * g_steps / (ms_g * 1e-3)
+    # parity of the sharded integral at this world size: 8 contour points split over the ranks vs the CPU port
+    z8, w8 = sy.contour_points(8, -30.0, 0.0)
+    P8 = it.GrInt(Fv[0], Sp, gobj, z8, w8)
+
+    # ---- secondary: complex F (spin-orbit-like Hermitian F): no real-structure shortcut anywhere, device-resident
+    Fc, _ = sy.hermitian_pair(N_ORB, seed=SEED, complex_F=True)
+    install_t1024(Fc)
+
+    def step_cplx(_k):
+        T_last[0] = ctx.transmission(E_loc, 0, -1)
+
+    step_cplx(0)
+    c_steps = max(1, min(args.steps, 3))
+    ms_c = timed(step_cplx, c_steps)
+    cplx_val = M_total * c_steps / (ms_c * 1e-3)
+    cplx_flops_step = ctx.last_elim_flops
 
     # ---- secondary: the same T(E) path at N = 512 (BASELINE metric names N = 512 / 1024), device-resident
     N5, nc5, M5 = 512, 32, 2500
@@ -274,34 +375,54 @@ def run_ours(args):
     ctx.sigma_add_const_block(np.arange(nc5), np.diag(s15[:nc5]))
     ctx.sigma_add_const_block(np.arange(N5 - nc5, N5), np.diag(s25[N5 - nc5:]))
 
-    def step_n512():
+    def step_n512(_k):
         T_last[0] = ctx.transmission(E5, 0, -1)
 
-    step_n512()
+    step_n512(0)
     n512_steps = max(1, min(args.steps, 5))
     ms_5 = timed(step_n512, n512_steps)
     n512_val = M5 * world * n512_steps / (ms_5 * 1e-3)
-    ctx.set_system(F, S)                       # back to the N = 1024 system (the CPU leg below compares against it)
-    ctx.sigma_clear()
-    ctx.sigma_add_const_block(np.arange(nc), np.diag(s1[:nc]))
-    ctx.sigma_add_const_block(np.arange(N_ORB - nc, N_ORB), np.diag(s2[N_ORB - nc:]))
+
+    # ---- secondary: BASELINE cfg 5, densityGridN at N = 2048 with Bethe-lattice contacts, sharded + one all-reduce
+    G5, Fb, Sb, gB = cfg5_system()
+    mu = float(G5["fermi"])
+    NG = 96 * world
+
+    def quiet(f, *a):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return f(*a)
+
+    def step_cfg5(_k):
+        P[0] = quiet(de.densityGridN, Fb, Sb, gB, mu - 0.25, mu + 0.25, -1, NG, 0.0, False)
+
+    step_cfg5(0)
+    ms_b = timed(step_cfg5, 2)
+    cfg5_val = NG * 2 / (ms_b * 1e-3)
+    Pg8 = quiet(de.densityGridN, Fb, Sb, gB, mu - 0.25, mu + 0.25, -1, 8, 0.0, False)    # the golden's 8-point grid
+    cfg5_par = max(rel(Pg8[G5["ii"], G5["jj"]], G5["PgN_samp"]), rel(np.diag(Pg8), G5["PgN_diag"]))
 
     if rank == 0:
-        peak, peak_src = fp64_peak()
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01c_rk_gemm_ncu.json"))).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        traffic, traffic_src = None, None
+        for name in ("r02_rk_gemm_ncu.json", "r01c_rk_gemm_ncu.json"):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", name))).get("dram_bytes_per_launch")
+                traffic_src = f"profiles/{name} (ncu --set full capture of this kernel; static, not re-measured in this run)"
+                break
+            except Exception:
+                pass
+        W_T = 8 / 3 * N_ORB ** 3 + 8 * N_ORB ** 2 * nc
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "complex128 (f64)", "data": "synthetic", "config": workload_desc(world),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "gaunegf_b200.transport.calculate_transmission (pinned numpy in, numpy out)",
-                    "ms_per_step": ms_e2e / e2e_steps},
+                    "api": "gaunegf_b200.transport.calculate_transmission (pinned numpy in, numpy out); F differs from the "
+                           "previous call every step, so F and S are uploaded every step",
+                    "ms_per_step": ms_e2e / e2e_steps,
+                    "resident_value": M_total * 3 / (ms_e2e_res * 1e-3),
+                    "resident_note": "same call with F, S unchanged since the previous call: they stay in HBM (h2d = energies only)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor",
                          "kernel": "k_rk_gemm / k_rk_gemm_rp (rank-K update C -= P W of the complex128 elimination, K = 32..512, packed "
@@ -309,40 +430,88 @@ def run_ours(args):
                                    "achieved counts EXECUTED arithmetic in 4-multiplication-equivalent flops: 8 per complex "
                                    "MAC, 4 where the panel is real, 2 where panel and pivot rows are real (real F, S, E with "
                                    "the contact orbitals ordered last keep every column left of the contacts exactly real); "
-                                   "complex tiles with K >= 64 use 3M arithmetic (3 DMMAs for an 8-flop MAC), so the rate can "
-                                   "exceed the DMMA ceiling",
+                                   "complex tiles with K >= 64 use 3M arithmetic (3 DMMAs for an 8-flop MAC)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "peak_source": peak_src, "launches_timed": int(gemm_n),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "measured in this run: gnb_dev_fp64_peak (register-resident DMMA.8x8x4 issue loop on every "
+                                        "SM, best of ~0.3 s of launches), clocks as in `clocks`",
+                         "launches_timed": int(gemm_n),
                          "algorithmic_flops_per_launch_avg": gemm_flops / gemm_n if gemm_n else None,
                          "kernel_share_of_step": gemm_ms / ms_roof if ms_roof > 0 else None,
                          "roofline_leg_ms_per_step": ms_roof / roof_steps,
-                         "step_algorithmic_tflops": (8 / 3 * N_ORB ** 3 + 8 * N_ORB ** 2 * nc) * E_loc.size * args.steps
-                                                    / (ms * 1e-3) / 1e12,
+                         "step_frac": elim_flops_step / (ms / args.steps * 1e-3) / 1e12 / peak,
+                         "step_executed_tflops": elim_flops_step / (ms / args.steps * 1e-3) / 1e12,
+                         "step_frac_note": "executed flops of ALL rank-K, forward-W and back-substitution launches of one step "
+                                           "(host-counted, gnb_last_elim_flops) / device step time / peak; tournament pivoting "
+                                           "(< 1 % of the flops, mostly FP32) is not counted",
+                         "step_algorithmic_tflops": W_T * E_loc.size * args.steps / (ms * 1e-3) / 1e12,
                          "step_algorithmic_note": "complex128 flop count of the contact-column algorithm (SURVEY 8d: 8/3 N^3 "
-                                                  "+ 8 N^2 n2 per energy); the executed count is lower because real columns "
-                                                  "are updated with real arithmetic"},
+                                                  "+ 8 N^2 n2 per energy) - NOT a roofline fraction: real columns run real "
+                                                  "arithmetic, so fewer flops are executed"},
             "secondary": {"what": f"integrate.GrInt contour integration N={N_ORB}: full G(E) per point + on-device weighted "
-                                  f"reduction + one NCCL all-reduce per call, {Mg} points per GPU per call (public API, host buffers)",
-                          "value": grint_val, "unit": UNIT,
-                          "algorithmic_tflops_per_gpu": 8 * N_ORB ** 3 * grint_val / world / 1e12},
+                                  f"reduction + one NCCL all-reduce per call, {Mg} points per GPU per call (public API, host buffers, "
+                                  "F and S resident)",
+                          "value": grint_val, "unit": UNIT, "ms_per_call": ms_g / g_steps,
+                          "algorithmic_tflops_per_gpu": 8 * N_ORB ** 3 * grint_val / world / 1e12,
+                          "frac_of_fp64_peak": 8 * N_ORB ** 3 * grint_val / world / 1e12 / peak,
+                          "frac_note": "algorithmic 8 N^3 per point / measured peak; the update runs 3M arithmetic (6 executed flops "
+                                       "per 8 algorithmic), so this can approach 1.33",
+                          "rank0_breakdown_ms": ({k: float(np.mean([b[k] for b in brk])) for k in ("partial_ms", "allreduce_ms", "d2h_ms")}
+                                                 if brk else None)},
+            "secondary_complex_F": {"what": f"T(E) at N={N_ORB} with a complex Hermitian F (no real-structure shortcut), "
+                                            f"{E_PER_GPU} energy points per GPU per step, device-resident",
+                                    "value": cplx_val, "unit": UNIT, "ms_per_step": ms_c / c_steps,
+                                    "step_frac": cplx_flops_step / (ms_c / c_steps * 1e-3) / 1e12 / peak,
+                                    "step_algorithmic_tflops": W_T * cplx_val / world / 1e12},
             "secondary_n512": {"what": f"T(E) at N={N5}, {nc5}-orbital constant contacts, {M5} energy points per GPU per step, "
                                        f"device-resident (same path and kernels as the headline value)",
                                "value": n512_val, "unit": UNIT,
-                               "step_algorithmic_tflops": (8 / 3 * N5 ** 3 + 8 * N5 ** 2 * nc5) * n512_val / 1e12},
+                               "step_algorithmic_tflops": (8 / 3 * N5 ** 3 + 8 * N5 ** 2 * nc5) * n512_val / world / 1e12},
+            "secondary_cfg5": {"what": "BASELINE cfg 5: density.densityGridN (GrLessInt, ind=-1) at N=2048 with two 27-orbital "
+                                       "Bethe-lattice contacts, 96 grid points per GPU per call, one NCCL all-reduce per call "
+                                       "(public API, host buffers)",
+                               "value": cfg5_val, "unit": UNIT, "ms_per_call": ms_b / 2,
+                               "algorithmic_tflops_per_gpu": (8 / 3 * 2048 ** 3 + 16 * 2048 ** 2 * 54) * cfg5_val / world / 1e12,
+                               "parity_vs_reference_golden": cfg5_par,
+                               "parity_note": "8-point densityGridN computed at THIS world size vs the unmodified reference's "
+                                              "result (tests/golden/cfg5_full.npz: 512 sampled entries + diagonal)"},
         }
+        # ---- parity at this world size + CPU baseline -------------------------------------------------
+        from oracle import negf_oracle as O
+        rng = np.random.default_rng(0)
+        idx = np.sort(rng.choice(M_total, CPU_SAMPLE, replace=False))      # spread over every rank's shard
+        with all_blas_threads():
+            _, Tc = cpu_reference_step(F, S, s1, s2, E_all[idx])
+            P8c = O.GrInt(F, S, _ConstOracle(s1, s2), z8, w8)
+        line["parity"] = {"T_max_rel_diff_vs_cpu": rel(T_full[idx], Tc),
+                          "T_sample": f"{CPU_SAMPLE} random energies of the {M_total}-point grid (shards of all {world} ranks), "
+                                      "GPU values from the e2e call of this run",
+                          "GrInt_max_rel_diff_vs_cpu": rel(P8, P8c),
+                          "GrInt_sample": f"8-point contour integral sharded over {world} rank(s) vs numpy/LAPACK",
+                          "cfg5_max_rel_diff_vs_reference": cfg5_par, "tolerance": 1e-10}
         if world == 1 and not args.no_cpu:
-            rng = np.random.default_rng(0)
-            Es = np.sort(rng.uniform(-0.5, 0.5, CPU_SAMPLE))
-            cpu_reference_step(F, S, s1, s2, Es[:2])
-            dt, Tc = cpu_reference_step(F, S, s1, s2, Es)
-            Tg = ctx.transmission(Es, 0, -1)
-            line["cpu_baseline"] = {"value": CPU_SAMPLE / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{CPU_SAMPLE} energies of the same workload (numpy/LAPACK port of the reference "
-                                              f"algorithm, oracle/negf_oracle.py), BLAS threads = all host cores",
-                                    "max_rel_diff_vs_gpu": float(np.max(np.abs(Tg - Tc)) / np.max(np.abs(Tc))), **host_info()}
+            shipped, best, _, _ = cpu_arms(F, S, s1, s2, 2, 1, rng)
+            top = best if best["value"] >= shipped["value"] else shipped
+            line["cpu_baseline"] = {"value": top["value"], "unit": UNIT, "cores": top["cores"], "kind": "port",
+                                    "sample": top["sample"] + " (numpy/LAPACK port of the reference algorithm, "
+                                                              "oracle/negf_oracle.py); value = the faster variant",
+                                    "variant": "best_effort" if top is best else "as_shipped",
+                                    "as_shipped": shipped, "best_effort": best,
+                                    "max_rel_diff_vs_gpu": line["parity"]["T_max_rel_diff_vs_cpu"], **host_info()}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+class _ConstOracle:
+    """constant diagonal contacts for the oracle's GrInt (surfG protocol)"""
+
+    def __init__(self, s1, s2):
+        self.tot = np.diag(s1 + s2)
+
+    def sigmaTot(self, E):
+        return self.tot
 
 
 def main():
@@ -351,7 +520,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline timing legs (parity is still checked)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,7 +41,7 @@ extern "C" int gnb_create(gnb_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GNB_ERR_CUDA; }
     gnb_ctx* c = new gnb_ctx();
     c->device = device;
-    if (gnb_kernels_init() != cudaSuccess || gnb_rec_init() != cudaSuccess || gnb_small_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+    if (gnb_kernels_init() != cudaSuccess || gnb_rec_init() != cudaSuccess || gnb_small_init() != cudaSuccess || gnb_sigma_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
         cudaEventCreate(&c->ev1) != cudaSuccess) {
         cudaGetLastError();
         delete c;
@@ -54,7 +54,7 @@ extern "C" int gnb_create(gnb_ctx** out, int device) {
 static void release_contact(Contact& ct) {
     DevBuf* bufs[] = {&ct.d_inds, &ct.d_const, &ct.alpha, &ct.Salpha, &ct.beta, &ct.Sbeta, &ct.tau, &ct.stau,
                       &ct.d_nb_off, &ct.d_nb_dirs, &ct.H, &ct.Slist, &ct.Vlist, &ct.blk, &ct.gam, &ct.iters,
-                      &ct.diffs, &ct.surf};
+                      &ct.diffs, &ct.surf, &ct.xiU, &ct.xiV};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -74,10 +74,10 @@ static Contact& new_contact(gnb_ctx* c) {
         Contact fresh;                                   // defaults for every scalar / host field ...
         DevBuf* src[] = {&old.d_inds, &old.d_const, &old.alpha, &old.Salpha, &old.beta, &old.Sbeta, &old.tau, &old.stau,
                          &old.d_nb_off, &old.d_nb_dirs, &old.H, &old.Slist, &old.Vlist, &old.blk, &old.gam, &old.iters,
-                         &old.diffs, &old.surf};
+                         &old.diffs, &old.surf, &old.xiU, &old.xiV};
         DevBuf* dst[] = {&fresh.d_inds, &fresh.d_const, &fresh.alpha, &fresh.Salpha, &fresh.beta, &fresh.Sbeta, &fresh.tau,
                          &fresh.stau, &fresh.d_nb_off, &fresh.d_nb_dirs, &fresh.H, &fresh.Slist, &fresh.Vlist, &fresh.blk,
-                         &fresh.gam, &fresh.iters, &fresh.diffs, &fresh.surf};
+                         &fresh.gam, &fresh.iters, &fresh.diffs, &fresh.surf, &fresh.xiU, &fresh.xiV};
         for (size_t i = 0; i < sizeof(src) / sizeof(src[0]); i++) *dst[i] = *src[i];   // ... and the recycled buffers
         c->contacts.push_back(fresh);
     } else {
@@ -95,7 +95,7 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     DevBuf* bufs[] = {&c->dF, &c->dS, &c->dSig0, &c->A, &c->Pws, &c->LU, &c->moves, &c->cand0, &c->cand1,
                       &c->perm, &c->invperm, &c->info, &c->dE, &c->dW, &c->G, &c->Y, &c->Z, &c->Xr, &c->out,
                       &c->dT, &c->dDosT, &c->dDosP, &c->sigB, &c->gam1B, &c->gam2B, &c->cols, &c->rows,
-                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->PpkR, &c->WpkR, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct, &c->cgw, &c->cA2, &c->cB2, &c->cgw2};
+                      &c->in_stage, &c->Ppk, &c->Lpk, &c->Wpk, &c->PpkR, &c->WpkR, &c->cA, &c->cB, &c->cg, &c->cgn, &c->cT1, &c->cM, &c->cflags, &c->ct, &c->cgw, &c->cA2, &c->cB2, &c->cgw2, &c->dXi, &c->sigN, &c->xiY};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < GNB_MAX_SUBSTREAMS; i++) {
         if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
@@ -104,6 +104,7 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
     delete c;
     return GNB_OK;
 }
@@ -117,6 +118,7 @@ extern "C" int gnb_set_workspace_limit(gnb_ctx* c, size_t bytes) {
 }
 extern "C" int64_t gnb_launch_count(const gnb_ctx* c) { return c ? c->launches : 0; }
 extern "C" double gnb_last_elim_ms(const gnb_ctx* c) { return c ? c->elim_ms : 0.0; }
+extern "C" double gnb_last_elim_flops(const gnb_ctx* c) { return c ? c->elim_flops : 0.0; }
 extern "C" int gnb_gemm_stats(gnb_ctx* c, double* ms, double* flops, int64_t* launches, int reset) {
     if (!c) return GNB_ERR_ARG;
     if (ms) *ms = c->gemm_timer.total_ms;
@@ -164,6 +166,7 @@ extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* 
     if (N != c->N) {                      // a new size invalidates the self-energy description
         retire_contacts(c);
         c->has_sig0 = false;
+        c->sig_n = 0; c->sig_spin = 0; c->has_xi = false;
     }
     c->N = N;
     const size_t bytes = (size_t)N * N * sizeof(cplx);
@@ -186,8 +189,28 @@ extern "C" int gnb_sigma_clear(gnb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     retire_contacts(c);
     c->has_sig0 = false;
+    c->sig_n = 0; c->sig_spin = 0; c->has_xi = false;
     return GNB_OK;
 }
+
+// Sigma_tot(E) = expand(Xi [sum_c scatter(inds_c, blk_c(E))] Xi): de-orthonormalisation and spin expansion of
+// surfGBethe.py:529-539.  Contacts added afterwards index an n-dimensional space (n = N, or N/2 with a spin mode).
+extern "C" int gnb_sigma_set_transform(gnb_ctx* c, int n, const double* Xi, int spin_mode, int loc) {
+    if (!c || c->N <= 0) return gnb_fail(c, GNB_ERR_ARG, "sigma_set_transform: set_system first");
+    if (spin_mode < 0 || spin_mode > 2) return gnb_fail(c, GNB_ERR_ARG, "sigma_set_transform: spin_mode must be 0, 1 or 2");
+    if (n * (spin_mode ? 2 : 1) != c->N)
+        return gnb_fail(c, GNB_ERR_ARG, "sigma_set_transform: n (x2 with a spin mode) must equal the system size");
+    if (!c->contacts.empty()) return gnb_fail(c, GNB_ERR_ARG, "sigma_set_transform: call after sigma_clear, before adding contacts");
+    cudaSetDevice(c->device);
+    c->sig_n = n; c->sig_spin = spin_mode; c->has_xi = Xi != nullptr;
+    if (Xi) {
+        int rc = put(c, c->dXi, Xi, (size_t)n * n * sizeof(cplx), loc);
+        if (rc) return rc;
+        GNB_CK(cudaStreamSynchronize(c->stream));
+    }
+    return GNB_OK;
+}
+static inline bool transformed(const gnb_ctx* c) { return c->sig_n > 0 && (c->sig_spin != 0 || c->has_xi); }
 
 extern "C" int gnb_sigma_set_dense0(gnb_ctx* c, const double* sig0, int loc) {
     if (!c || c->N <= 0 || !sig0) return gnb_fail(c, GNB_ERR_ARG, "sigma_set_dense0: set_system first");
@@ -201,8 +224,13 @@ extern "C" int gnb_sigma_set_dense0(gnb_ctx* c, const double* sig0, int loc) {
 
 static int check_inds(gnb_ctx* c, int n, const int32_t* inds) {
     if (n <= 0 || !inds) return gnb_fail(c, GNB_ERR_ARG, "contact: empty index list");
-    for (int i = 0; i < n; i++)
-        if (inds[i] < 0 || inds[i] >= c->N) return gnb_fail(c, GNB_ERR_ARG, "contact: orbital index out of range");
+    const int dim = c->sig_n > 0 ? c->sig_n : c->N;
+    std::vector<char> seen(dim, 0);
+    for (int i = 0; i < n; i++) {
+        if (inds[i] < 0 || inds[i] >= dim) return gnb_fail(c, GNB_ERR_ARG, "contact: orbital index out of range");
+        if (seen[inds[i]]) return gnb_fail(c, GNB_ERR_ARG, "contact: duplicate orbital index");   // the scatter is not atomic
+        seen[inds[i]] = 1;
+    }
     return GNB_OK;
 }
 
@@ -305,17 +333,39 @@ GnbElimWork gnb_elim_work(gnb_ctx* c, int M, int N, bool jordan, int* rc) {
 static int begin_call(gnb_ctx* c) {
     cudaSetDevice(c->device);
     c->elim_ms = 0.0;
+    c->elim_flops = 0.0;
+    c->pend_dst = nullptr; c->pend_bytes = 0;
     c->gemm_timer.used = 0; c->gemm_timer.flops.clear();
     GNB_CK(c->info.ensure(sizeof(int) * 4));
     GNB_CK(cudaMemsetAsync(c->info.p, 0, sizeof(int) * 4, c->stream));
     return GNB_OK;
 }
 
+// device -> caller's host memory for the N x N results (see gnb_ctx::h_pin); completed by end_call
+static int result_to_host(gnb_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes > c->h_pin_cap) {
+        if (c->h_pin) cudaFreeHost(c->h_pin);
+        c->h_pin = nullptr; c->h_pin_cap = 0;
+        if (cudaHostAlloc(&c->h_pin, bytes, cudaHostAllocDefault) == cudaSuccess) c->h_pin_cap = bytes;
+        else cudaGetLastError();
+    }
+    if (!c->h_pin) {                              // no pinned memory available: plain pageable copy
+        GNB_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return GNB_OK;
+    }
+    GNB_CK(cudaMemcpyAsync(c->h_pin, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->pend_dst = dst; c->pend_bytes = bytes;
+    return GNB_OK;
+}
+
 static int end_call(gnb_ctx* c) {
     int info = 0;
+    void* pend_dst = c->pend_dst; const size_t pend_bytes = c->pend_bytes;
+    c->pend_dst = nullptr; c->pend_bytes = 0;
     GNB_CK(cudaMemcpyAsync(&info, c->info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     GNB_CK(cudaStreamSynchronize(c->stream));
     GNB_CK(cudaGetLastError());
+    if (pend_dst) memcpy(pend_dst, c->h_pin, pend_bytes);
     if (c->timing) c->gemm_timer.resolve();
     if (info) return gnb_fail(c, GNB_ERR_SINGULAR, "Singular matrix");
     return GNB_OK;
@@ -411,6 +461,7 @@ GnbRecWork gnb_rec_work(gnb_ctx* c, int M, int Np, int ld, bool jordan, int* rc,
     w.Wpk = c->Wpk.as<cplx>(); w.strideWk = (long)wk;
     w.info = c->info.as<int>();
     w.timer = c->timing ? &c->gemm_timer : nullptr;
+    w.flops_acc = &c->elim_flops;
     return w;
 }
 
@@ -502,6 +553,7 @@ static int prepare_sigma(gnb_ctx* c, int M, const cplx* dE, int want_gamma) {
                                                     ct.relax == joint[0]->relax && ct.max_iter == joint[0]->max_iter);
                 if (same) joint.push_back(&ct);
             }
+    if (joint.size() * (size_t)M > 65535) joint.clear();      // gridDim.y of the joint batch
     if (joint.size() >= 2) {
         int rc = gnb_chain1d_surface_g_multi(c, joint.data(), (int)joint.size(), M, dE);
         if (rc) return rc;
@@ -522,6 +574,57 @@ static int prepare_sigma(gnb_ctx* c, int M, const cplx* dE, int want_gamma) {
             if (rc) return rc;
         }
     }
+    return GNB_OK;
+}
+
+// Transformed description (gnb_sigma_set_transform): dense N x N Sigma of contact `sel` (-1: all contacts) for the m
+// energies of the chunk, into `out` ([m][N][N]).  prepare_sigma() must have run.
+static int build_dense_sigma(gnb_ctx* c, int m, int sel, DevBuf& out) {
+    const int n = c->sig_n, N = c->N;
+    const long nn = (long)n * n;
+    GNB_CK(out.ensure((size_t)m * N * N * sizeof(cplx)));
+    cplx* sigN = out.as<cplx>();
+    if (c->sig_spin) { GNB_CK(c->sigN.ensure((size_t)m * nn * sizeof(cplx))); sigN = c->sigN.as<cplx>(); }
+    GNB_CK(cudaMemsetAsync(sigN, 0, (size_t)m * nn * sizeof(cplx), c->stream));
+    for (int ci = 0; ci < (int)c->contacts.size(); ci++) {
+        if (sel >= 0 && ci != sel) continue;
+        Contact& ct = c->contacts[ci];
+        const int nc = ct.nc;
+        if (!c->has_xi) {
+            gnb_launch_scatter_add(c->stream, m, sigN, nn, n, ct.d_inds.as<int>(), nc, ct.blk_ptr, ct.blk_stride);
+            c->launches++;
+            continue;
+        }
+        GNB_CK(ct.xiU.ensure((size_t)n * nc * sizeof(cplx)));
+        GNB_CK(ct.xiV.ensure((size_t)n * nc * sizeof(cplx)));
+        GNB_CK(c->xiY.ensure((size_t)m * nc * n * sizeof(cplx)));
+        gnb_launch_xi_gather(c->stream, n, c->dXi.as<cplx>(), ct.d_inds.as<int>(), nc, ct.xiU.as<cplx>(), ct.xiV.as<cplx>());
+        GnbGemmArgs g{};
+        g.skip_lo = g.skip_hi = -1; g.plus = 1;
+        g.ilo = 0; g.ihi = nc; g.jlo = 0; g.jhi = n; g.kdim = nc; g.zero_init = 1;      // Y = blk Xi[C, :]
+        g.C = c->xiY.as<cplx>(); g.strideC = (long)nc * n; g.ldc = n;
+        g.P = ct.blk_ptr; g.strideP = ct.blk_stride; g.ldp = nc;
+        g.W = ct.xiV.as<cplx>(); g.strideW = 0; g.ldw = n;
+        gnb_launch_gemm(c->stream, g, m, false, false);
+        g.ihi = n; g.zero_init = 0;                                                        // Sigma += Xi[:, C] Y
+        g.C = sigN; g.strideC = nn; g.ldc = n;
+        g.P = ct.xiU.as<cplx>(); g.strideP = 0; g.ldp = nc;
+        g.W = c->xiY.as<cplx>(); g.strideW = (long)nc * n; g.ldw = n;
+        gnb_launch_gemm(c->stream, g, m, false, false);
+        c->launches += 3;
+    }
+    if (c->sig_spin) { gnb_launch_kron_expand(c->stream, m, n, c->sig_spin, sigN, out.as<cplx>()); c->launches++; }
+    GNB_CK(cudaGetLastError());
+    return GNB_OK;
+}
+// Gamma = i (Sigma - Sigma^H) of contact `sel` as dense N x N matrices in `out`; `tmp` receives the dense Sigma
+static int build_dense_gamma(gnb_ctx* c, int m, int sel, DevBuf& tmp, DevBuf& out) {
+    int rc = build_dense_sigma(c, m, sel, tmp);
+    if (rc) return rc;
+    const long NN = (long)c->N * c->N;
+    GNB_CK(out.ensure((size_t)m * NN * sizeof(cplx)));
+    gnb_launch_gamma_from_sigma(c->stream, m, tmp.as<cplx>(), NN, c->N, out.as<cplx>());
+    c->launches++;
     return GNB_OK;
 }
 
@@ -606,8 +709,11 @@ static GnbSmallArgs small_args(gnb_ctx* c, int m, const cplx* dE, bool use_desc,
 // ---------------------------------------------------------------------------------------------
 enum { MODE_GREEN = 0, MODE_DOS = 1, MODE_GRINT = 2, MODE_T_DENSE = 3, MODE_GLESS_DENSE = 4, MODE_T_SPIN = 5 };
 
+// xa / xb: contacts whose Gammas a transformed description (gnb_sigma_set_transform) builds on the device for the
+// T / G< modes (xa = -1 in MODE_GLESS_DENSE: Gamma of Sigma_tot)
 static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double* w, bool use_desc,
-                      DenseSrc sig, DenseSrc g1, DenseSrc g2, double* out0, double* out1, int loc) {
+                      DenseSrc sig, DenseSrc g1, DenseSrc g2, double* out0, double* out1, int loc, int xa = 0,
+                      int xb = 0) {
     if (!c || c->N <= 0) return gnb_fail(c, GNB_ERR_ARG, "set_system first");
     if (M < 0 || (M > 0 && !E)) return gnb_fail(c, GNB_ERR_ARG, "bad energy list");
     int rc = begin_call(c);
@@ -624,8 +730,10 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     if (sig.p && sig.stride) per += nn * 16;
     if (g1.p && g1.stride) per += nn * 16;
     if (g2.p && g2.stride) per += nn * 16;
-    const bool small = small_ok(c, use_desc);
-    if (small) per = (size_t)(2 + (sig.p && sig.stride) + 2 * (g1.p && g1.stride) + 2) * nn * 16 + (size_t)N * 16 + 64;
+    const bool xform = use_desc && transformed(c);       // dense Sigma (and Gammas) built on the device per chunk
+    if (xform) per += nn * 16 * (mode == MODE_T_DENSE || mode == MODE_T_SPIN ? 4 : mode == MODE_GLESS_DENSE ? 3 : 2);
+    const bool small = small_ok(c, use_desc && !xform);
+    if (small) per = (size_t)(2 + (sig.p && sig.stride) + 2 * (g1.p && g1.stride) + 2 + (xform ? 4 : 0)) * nn * 16 + (size_t)N * 16 + 64;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     cplx* d_out = nullptr;
     if (mode == MODE_GRINT || mode == MODE_GLESS_DENSE) {
@@ -639,7 +747,12 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         const cplx *sc = nullptr, *sb = nullptr;
         if (use_desc) {
             if ((rc = prepare_sigma(c, m, dE, 0))) return rc;
+            if (xform) {
+                if ((rc = build_dense_sigma(c, m, -1, c->sigB))) return rc;
+                sb = c->sigB.as<cplx>();
+            }
         } else if ((rc = stage_dense(c, c->sigB, sig, k0, m, &sc, &sb))) return rc;
+        const bool desc_asm = use_desc && !xform;   // contact blocks scattered at assembly (else Sigma is dense in sb)
         cplx* A = nullptr;                       // where the consumers below find (P A)^-1 ...
         long strideA = (long)Np * ld;
         int lda = ld;
@@ -652,7 +765,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         }
         if (small) {
             // one CTA per energy: assembly, pivoted Gauss-Jordan and (for DOS) the reduction stay in shared memory
-            GnbSmallArgs sa = small_args(c, m, dE, use_desc, sc, sb);
+            GnbSmallArgs sa = small_args(c, m, dE, desc_asm, sc, sb);
             if (mode == MODE_DOS) {
                 GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
                 if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
@@ -670,7 +783,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
             GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
             A = c->A.as<cplx>();
             if ((rc = pad_chunk(c, m, L, A))) return rc;
-            if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, use_desc, sc, sb))) return rc;
+            if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, desc_asm, sc, sb))) return rc;
             if ((rc = run_eliminate(c, m, L, A, 1))) return rc;
             gnb_launch_invperm(c->stream, m, c->perm.as<int>(), c->invperm.as<int>(), Np, Np);
             c->launches++;
@@ -700,9 +813,15 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
             gnb_launch_weighted_sum(c->stream, m, N, A, strideA, lda, inv, pst, c->dW.as<cplx>(), d_out, k0 > 0);
             c->launches++;
         } else if (mode == MODE_T_DENSE) {
-            const cplx *g1c, *g1b, *g2c, *g2b;
-            if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &g1c, &g1b))) return rc;
-            if ((rc = stage_dense(c, c->gam2B, g2, k0, m, &g2c, &g2b))) return rc;
+            const cplx *g1c = nullptr, *g1b = nullptr, *g2c = nullptr, *g2b = nullptr;
+            if (xform) {
+                if ((rc = build_dense_gamma(c, m, xa, c->Y, c->gam1B))) return rc;
+                if ((rc = build_dense_gamma(c, m, xb, c->Y, c->gam2B))) return rc;
+                g1b = c->gam1B.as<cplx>(); g2b = c->gam2B.as<cplx>();
+            } else {
+                if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &g1c, &g1b))) return rc;
+                if ((rc = stage_dense(c, c->gam2B, g2, k0, m, &g2c, &g2b))) return rc;
+            }
             GNB_CK(c->Y.ensure((size_t)m * nn * sizeof(cplx)));
             GNB_CK(c->Z.ensure((size_t)m * nn * sizeof(cplx)));
             GNB_CK(c->dT.ensure((size_t)m * sizeof(double)));
@@ -723,9 +842,15 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         } else if (mode == MODE_T_SPIN) {
             // four spin-block traces of one 2N x 2N inverse (transport.py:159-181):
             // T_i = Re sum_ij (Gamma1[r,r] G[r,c] Gamma2[c,c])[i,j] conj(G[c,r][i,j])
-            const cplx *g1c, *g1b, *g2c, *g2b;
-            if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &g1c, &g1b))) return rc;
-            if ((rc = stage_dense(c, c->gam2B, g2, k0, m, &g2c, &g2b))) return rc;
+            const cplx *g1c = nullptr, *g1b = nullptr, *g2c = nullptr, *g2b = nullptr;
+            if (xform) {
+                if ((rc = build_dense_gamma(c, m, xa, c->Z, c->gam1B))) return rc;
+                if ((rc = build_dense_gamma(c, m, xb, c->Z, c->gam2B))) return rc;
+                g1b = c->gam1B.as<cplx>(); g2b = c->gam2B.as<cplx>();
+            } else {
+                if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &g1c, &g1b))) return rc;
+                if ((rc = stage_dense(c, c->gam2B, g2, k0, m, &g2c, &g2b))) return rc;
+            }
             const int h = N / 2;
             const long hh = (long)h * h;
             GNB_CK(c->Y.ensure((size_t)m * hh * sizeof(cplx)));
@@ -753,8 +878,11 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
             GNB_CK(cudaMemcpyAsync(out0 + (size_t)k0 * 4, c->dT.p, (size_t)m * 4 * sizeof(double),
                                    cudaMemcpyDeviceToHost, c->stream));
         } else if (mode == MODE_GLESS_DENSE) {
-            const cplx *gc, *gb;
-            if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &gc, &gb))) return rc;
+            const cplx *gc = nullptr, *gb = nullptr;
+            if (xform) {
+                if ((rc = build_dense_gamma(c, m, xa, c->Y, c->gam1B))) return rc;
+                gb = c->gam1B.as<cplx>();
+            } else if ((rc = stage_dense(c, c->gam1B, g1, k0, m, &gc, &gb))) return rc;
             GNB_CK(c->Y.ensure((size_t)m * nn * sizeof(cplx)));
             GnbGemmArgs g{};
             g.ilo = 0; g.ihi = N; g.jlo = 0; g.jhi = N; g.kdim = N; g.skip_lo = g.skip_hi = -1;
@@ -774,7 +902,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));   // staging buffers are reused per chunk
     }
     if ((mode == MODE_GRINT || mode == MODE_GLESS_DENSE) && loc == GNB_HOST)
-        GNB_CK(cudaMemcpyAsync(out0, d_out, nn * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = result_to_host(c, out0, d_out, nn * sizeof(cplx)))) return rc;
     return end_call(c);
 }
 
@@ -806,8 +934,15 @@ extern "C" int gnb_transmission_dense(gnb_ctx* c, int M, const double* E, const 
 }
 extern "C" int gnb_transmission_spin(gnb_ctx* c, int M, const double* E, const double* sig, long ss,
                                      const double* gam1, long s1, const double* gam2, long s2, double* T4) {
-    if (!gam1 || !gam2) return gnb_fail(c, GNB_ERR_ARG, "gamma matrices required");
     if (c && (c->N % 2)) return gnb_fail(c, GNB_ERR_ARG, "spin-resolved transmission needs an even (2N) dimension");
+    if (c && !sig && !gam1 && !gam2) {       // described (transformed) self-energies: contacts 0 and -1, as the reference
+        const int ca = resolve_contact(c, 0), cb = resolve_contact(c, -1);
+        if (!transformed(c) || ca < 0 || cb < 0)
+            return gnb_fail(c, GNB_ERR_ARG, "transmission_spin without matrices needs a spin-expanded description (gnb_sigma_set_transform)");
+        return run_jordan(c, MODE_T_SPIN, M, E, nullptr, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, T4, nullptr,
+                          GNB_HOST, ca, cb);
+    }
+    if (!gam1 || !gam2) return gnb_fail(c, GNB_ERR_ARG, "gamma matrices required");
     return run_jordan(c, MODE_T_SPIN, M, E, nullptr, false, {sig, ss}, {gam1, s1}, {gam2, s2}, T4, nullptr, GNB_HOST);
 }
 extern "C" int gnb_gless_int_dense(gnb_ctx* c, int M, const double* E, const double* w, const double* sig, long ss,
@@ -824,6 +959,9 @@ extern "C" int gnb_transmission(gnb_ctx* c, int M, const double* E, int ca_, int
     const int ca = resolve_contact(c, ca_), cb = resolve_contact(c, cb_);
     if (ca < 0 || cb < 0) return gnb_fail(c, GNB_ERR_ARG, "transmission: invalid contact index");
     if (M < 0 || (M > 0 && (!E || !T))) return gnb_fail(c, GNB_ERR_ARG, "bad energy list");
+    if (transformed(c))      // Xi Sigma Xi / spin-expanded contacts: dense Gammas, built on the device
+        return run_jordan(c, MODE_T_DENSE, M, E, nullptr, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, T, nullptr,
+                          GNB_HOST, ca, cb);
     int rc = begin_call(c);
     if (rc) return rc;
     const int N = c->N;
@@ -935,6 +1073,9 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         if (contact < 0 || contact >= (int)c->contacts.size()) return gnb_fail(c, GNB_ERR_ARG, "gless_int: invalid contact");
         use.push_back(contact);
     }
+    if (transformed(c))
+        return run_jordan(c, MODE_GLESS_DENSE, M, E, w, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, out, nullptr, loc,
+                          contact, 0);
     int rc = begin_call(c);
     if (rc) return rc;
     const int N = c->N;
@@ -1021,7 +1162,7 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         c->launches++;
     }
     if (loc == GNB_HOST)
-        GNB_CK(cudaMemcpyAsync(out, d_out, (size_t)N * N * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = result_to_host(c, out, d_out, (size_t)N * N * sizeof(cplx)))) return rc;
     return end_call(c);
 }
 
@@ -1097,5 +1238,51 @@ extern "C" int gnb_dev_gemm_bench(gnb_ctx* c, int M, int n, int k, int bm, int i
     *ms_out = ms / iters;
     gnb_set_gemm_bm(32);
     gnb_set_gemm_pipe(1);
+    return GNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Developer hook (bench.py's roofline denominator): the FP64 tensor-pipe ceiling of THIS GPU, measured in the run.
+// A register-resident DMMA.8x8x4 issue loop (8 independent accumulator pairs per warp, 8 warps per CTA, 2 CTAs per
+// SM: the configuration tools/fp64_peak.cu found to saturate the pipe) repeated until about ms_target has elapsed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double seed) {
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = seed * i; acc[i][1] = seed; }
+    const double a = seed + threadIdx.x * 1e-9, b = seed - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[i][0]), "+d"(acc[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i][0] + acc[i][1];
+    if (s == 123.456) out[0] = s;
+}
+extern "C" int gnb_dev_fp64_peak(gnb_ctx* c, double ms_target, double* tflops) {
+    if (!c || !tflops || ms_target <= 0) return gnb_fail(c, GNB_ERR_ARG, "fp64_peak: bad arguments");
+    cudaSetDevice(c->device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    GNB_CK(c->dT.ensure(64));
+    const int iters = 20000, grid = sms * 2;
+    const double flops_per_launch = (double)grid * 8 /*warps*/ * iters * 8 /*accumulators*/ * 512.0;
+    k_fp64_peak<<<grid, 256, 0, c->stream>>>(c->dT.as<double>(), iters, 1.0);      // warm-up
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    double best = 0.0, spent = 0.0;
+    while (spent < ms_target) {
+        GNB_CK(cudaEventRecord(c->ev0, c->stream));
+        k_fp64_peak<<<grid, 256, 0, c->stream>>>(c->dT.as<double>(), iters, 1.0);
+        GNB_CK(cudaEventRecord(c->ev1, c->stream));
+        GNB_CK(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        GNB_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        spent += ms;
+        best = std::max(best, flops_per_launch / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
     return GNB_OK;
 }

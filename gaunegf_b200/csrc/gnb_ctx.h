@@ -40,6 +40,7 @@ struct Contact {
     DevBuf d_nb_off, d_nb_dirs, H, Slist, Vlist;
     // per-chunk products
     DevBuf blk, gam, iters, diffs, surf;
+    DevBuf xiU, xiV;                // Xi[:, inds] (n x nc) and Xi[inds, :] (nc x n) when a transform is set
     const cplx* blk_ptr = nullptr; long blk_stride = 0;   // valid after prepare
     const cplx* gam_ptr = nullptr; long gam_stride = 0;
 };
@@ -84,6 +85,11 @@ struct gnb_ctx {
     DevBuf dF, dS, dSig0;
     bool has_sig0 = false;
     bool real_FS = false;          // F and S given with zero imaginary parts (host arrays only)
+    // Sigma transform (gnb_sigma_set_transform): contact indices refer to an n-dimensional space,
+    // Sigma_tot = expand(Xi Sigma Xi); sig_n = 0 means none
+    int sig_n = 0, sig_spin = 0;
+    bool has_xi = false;
+    DevBuf dXi, sigN, xiY;
     std::vector<Contact> contacts;
     std::vector<Contact> contact_pool;  // retired descriptions whose device buffers are reused (gnb_api.cu)
     // workspaces
@@ -91,12 +97,18 @@ struct gnb_ctx {
         sigB, gam1B, gam2B, cols, rows, in_stage, Ppk, Lpk, Wpk, PpkR, WpkR;
     // chain1d fixed-point workspaces
     DevBuf cA, cB, cg, cgn, cT1, cM, cflags, ct, cgw, cA2, cB2, cgw2;
+    // pinned landing buffer for N x N results going to (pageable) caller memory: one DMA at PCIe rate + a host
+    // memcpy after the synchronisation in end_call, instead of the driver's chunked pageable staging
+    void* h_pin = nullptr; size_t h_pin_cap = 0;
+    void* pend_dst = nullptr; size_t pend_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double elim_ms = 0.0;
+    double elim_flops = 0.0;        // executed FP64 flops of the elimination launches of the last compute call
     bool timing = false;
 };
 
 // gnb_sigma.cu
+cudaError_t gnb_sigma_init();
 int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_gamma, const cplx* g_ready = nullptr);
 void gnb_chain_set_compact(int on);
 int gnb_chain1d_surface_g_multi(gnb_ctx* c, Contact* const* cts, int K, int M, const cplx* dE);   // g_k in c->cg + k*M*nc*nc

@@ -83,6 +83,8 @@ struct GnbRecWork {
     int back_row_lo;                   // FORWARD: only rows >= back_row_lo of the solution are needed
     int nreal;                         // FORWARD: columns [0, nreal) of the matrices are real (0 = unknown / complex)
     int mixr;                          // mixed layout: columns [0, mixr) stored as real doubles (0 or == nreal)
+    double* flops_acc;                 // host accumulator: executed real FP64 flops of the rank-K / forward-W /
+                                       // back-substitution launches (4-multiplication equivalents; may be null)
 };
 size_t gnb_rec_pk_elems(int N);               // cplx elements per matrix of Ppk / Lpk (incl. slack)
 size_t gnb_rec_wk_elems(int N, int ld);       // cplx elements per matrix of Wpk (incl. slack)
@@ -137,5 +139,9 @@ void gnb_launch_trace_dot(cudaStream_t st, int M, const cplx* Z, const cplx* X, 
 void gnb_launch_gamma_from_sigma(cudaStream_t st, int M, const cplx* sig, long stride, int n, cplx* gam);
 void gnb_launch_unpermute_sym(cudaStream_t st, int N, const cplx* in, const int* pi, cplx* out);
 void gnb_launch_scale_cols(cudaStream_t st, int M, cplx* X, long stride, int n, const cplx* w);
+void gnb_launch_xi_gather(cudaStream_t st, int n, const cplx* Xi, const int* inds, int nc, cplx* U, cplx* V);
+void gnb_launch_scatter_add(cudaStream_t st, int M, cplx* dense, long strideD, int n, const int* inds, int nc,
+                            const cplx* blk, long strideBlk);
+void gnb_launch_kron_expand(cudaStream_t st, int M, int n, int mode, const cplx* in, cplx* out);
 void gnb_launch_trace_dot_strided(cudaStream_t st, int M, const cplx* Z, long strideZ, int ldz, const cplx* X,
                                   long strideX, int ldx, int nr, int ncols, double* T, int tstride, int toff);

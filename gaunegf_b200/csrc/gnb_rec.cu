@@ -998,6 +998,7 @@ struct Rec {
                 else k_rk_gemm_rp<2, 2, 0><<<grid, 288, rk_rp_smem<2, 2, 0>(), st>>>(r, nti, ntj, (int)total);
             }
             if (ws.timer) ws.timer->end(st, flops);
+            if (ws.flops_acc) *ws.flops_acc += flops;
             launches++;
             return;
         }
@@ -1035,6 +1036,7 @@ struct Rec {
             else k_rk_gemm<0, 2, 2><<<grid, 288, rk_smem<2, 2>(), st>>>(g, nti, ntj, (int)total);
         }
         if (ws.timer) ws.timer->end(st, flops);
+        if (ws.flops_acc) *ws.flops_acc += flops;
         launches++;
     }
 
@@ -1087,6 +1089,12 @@ struct Rec {
         const cplx* Lsrc = jordan ? ws.Lpk : ws.Ppk;
         if (nb <= 2) {
             TraceScope ts("wsolve", st, M);
+            if (ws.flops_acc) {                             // 1 (nb = 1) or 3 (nb = 2) products 32 x 32 x columns
+                const int nr = g_rk_real ? ws.nreal : 0;
+                const double cr = (c0 + w <= nr) ? std::max(0, std::min(jhi, nr) - jlo) : 0;     // real x real columns
+                const double per = (c0 + w <= nr) ? 2.0 * cr + 4.0 * ((jhi - jlo) - cr) : 8.0 * (jhi - jlo);
+                *ws.flops_acc += (nb == 2 ? 3.0 : 1.0) * 32.0 * 32.0 * per * M;
+            }
             if (g_rk_wsolve_mma || mixr > 0) {             // the FMA kernel does not know the mixed layout
                 const int ntile = (jhi - jlo) / WM_TC;
                 const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
@@ -1157,6 +1165,7 @@ struct Rec {
             if (ws.timer) ws.timer->begin(st);
             gnb_launch_gemm(st, g, M, false, false);
             if (ws.timer) ws.timer->end(st, 8.0 * (double)(c0 + h - ilo) * (double)naug * g.kdim * M);
+            if (ws.flops_acc) *ws.flops_acc += 8.0 * (double)(c0 + h - ilo) * (double)naug * g.kdim * M;
             launches++;
         }
         backsub(c0, h, row_lo);

@@ -181,3 +181,57 @@ __global__ void __launch_bounds__(256) k_unpermute_sym(int N, const cplx* __rest
 void gnb_launch_unpermute_sym(cudaStream_t st, int N, const cplx* in, const int* pi, cplx* out) {
     k_unpermute_sym<<<min(cdiv_i((long)N * N, 256), 4096), 256, 0, st>>>(N, in, pi, out);
 }
+
+// ------------------------------------------------------------------------------------------
+// De-orthonormalisation / spin expansion of contact self-energies (surfGBethe.py:529-539):
+//   Sigma_c -> Xi Sigma_c Xi = Xi[:, C] blk_c Xi[C, :]  and  kron(I2, Sigma) ('u', 'ro') / kron(Sigma, I2) ('g').
+// ------------------------------------------------------------------------------------------
+// U[i][p] = Xi[i][inds[p]] (n x nc),  V[p][j] = Xi[inds[p]][j] (nc x n)
+__global__ void __launch_bounds__(256) k_xi_gather(int n, const cplx* __restrict__ Xi, const int* __restrict__ inds, int nc,
+                                                   cplx* __restrict__ U, cplx* __restrict__ V) {
+    const long total = (long)n * nc;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / nc), p = (int)(idx - (long)i * nc);
+        U[idx] = Xi[(long)i * n + inds[p]];
+        const int q = (int)(idx / n), j = (int)(idx - (long)q * n);
+        V[idx] = Xi[(long)inds[q] * n + j];
+    }
+}
+void gnb_launch_xi_gather(cudaStream_t st, int n, const cplx* Xi, const int* inds, int nc, cplx* U, cplx* V) {
+    k_xi_gather<<<min(cdiv_i((long)n * nc, 256), 2048), 256, 0, st>>>(n, Xi, inds, nc, U, V);
+}
+
+// dense[b][inds[p]][inds[q]] += blk[b][p][q]
+__global__ void __launch_bounds__(256) k_scatter_add(cplx* __restrict__ dense, long strideD, int n, const int* __restrict__ inds,
+                                                     int nc, const cplx* __restrict__ blk, long strideBlk) {
+    const int b = blockIdx.y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nc * nc; idx += gridDim.x * blockDim.x) {
+        const int p = idx / nc, q = idx - p * nc;
+        cplx* d = dense + (long)b * strideD + (long)inds[p] * n + inds[q];
+        *d = cadd(*d, blk[(long)b * strideBlk + idx]);
+    }
+}
+void gnb_launch_scatter_add(cudaStream_t st, int M, cplx* dense, long strideD, int n, const int* inds, int nc,
+                            const cplx* blk, long strideBlk) {
+    if (M <= 0 || nc <= 0) return;
+    dim3 grid(min(cdiv_i((long)nc * nc, 256), 256), M);
+    k_scatter_add<<<grid, 256, 0, st>>>(dense, strideD, n, inds, nc, blk, strideBlk);
+}
+
+// out (2n x 2n) = kron(I2, in) (mode 1) or kron(in, I2) (mode 2); in is n x n
+__global__ void __launch_bounds__(256) k_kron_expand(int n, int mode, const cplx* __restrict__ in, cplx* __restrict__ out) {
+    const int b = blockIdx.y, n2 = 2 * n;
+    const long total = (long)n2 * n2;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / n2), c = (int)(idx - (long)r * n2);
+        int i, j, sr, sc;
+        if (mode == 1) { sr = r / n; i = r - sr * n; sc = c / n; j = c - sc * n; }
+        else { i = r >> 1; sr = r & 1; j = c >> 1; sc = c & 1; }
+        out[(long)b * total + idx] = (sr == sc) ? in[(long)b * n * n + (long)i * n + j] : cmake(0.0, 0.0);
+    }
+}
+void gnb_launch_kron_expand(cudaStream_t st, int M, int n, int mode, const cplx* in, cplx* out) {
+    if (M <= 0) return;
+    dim3 grid(min(cdiv_i(4L * n * n, 256), 1024), M);
+    k_kron_expand<<<grid, 256, 0, st>>>(n, mode, in, out);
+}

@@ -503,12 +503,12 @@ __global__ void __launch_bounds__(128) k_bethe_block(const cplx* __restrict__ su
     }
 }
 
+// per-context (per-device) kernel attributes; called from gnb_create after cudaSetDevice
+cudaError_t gnb_sigma_init() {
+    return cudaFuncSetAttribute(k_bethe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BetheSmem));
+}
+
 int gnb_bethe_raw(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int which, cplx* d_out) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CK(cudaFuncSetAttribute(k_bethe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BetheSmem)));
-        attr_set = true;
-    }
     GNB_CK(ct.iters.ensure((size_t)M * sizeof(int)));
     GNB_CK(ct.diffs.ensure((size_t)M * sizeof(double)));
     k_bethe<<<M, BWARPS * 32, sizeof(BetheSmem), c->stream>>>(dE, ct.eta, ct.H.as<cplx>(), ct.Slist.as<cplx>(),
@@ -567,6 +567,34 @@ int gnb_contact_eval(gnb_ctx* c, Contact& ct, int M, const cplx* dE, int want_ga
     return GNB_OK;
 }
 
+// one chunk of gnb_sigma_eval (m energies already in c->dE)
+static int sigma_eval_chunk(gnb_ctx* c, Contact& ct, int which, int m, double* out_blk, int32_t* iters, double* diffs) {
+    const cplx* dE = c->dE.as<cplx>();
+    const long nn = (long)ct.nc * ct.nc;
+    const cplx* src = nullptr;
+    size_t per = 0;
+    int rc = GNB_OK;
+    if (ct.kind == GNB_C_CHAIN1D) {
+        if (which == 1) { rc = gnb_chain1d_surface_g(c, ct, m, dE); src = c->cg.as<cplx>(); }
+        else { rc = gnb_contact_eval(c, ct, m, dE, 0); src = ct.blk.as<cplx>(); }
+        per = nn;
+    } else {
+        if (which == 0) { rc = gnb_contact_eval(c, ct, m, dE, 0); src = ct.blk.as<cplx>(); per = nn; }
+        else {
+            per = (which == 1 ? 12 : 9) * BSZ;
+            GNB_CK(ct.surf.ensure((size_t)m * 12 * BSZ * sizeof(cplx)));
+            rc = gnb_bethe_raw(c, ct, m, dE, which, ct.surf.as<cplx>());
+            src = ct.surf.as<cplx>();
+        }
+    }
+    if (rc) return rc;
+    GNB_CK(cudaMemcpyAsync(out_blk, src, (size_t)m * per * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    if (iters) GNB_CK(cudaMemcpyAsync(iters, ct.iters.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (diffs) GNB_CK(cudaMemcpyAsync(diffs, ct.diffs.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GNB_CK(cudaStreamSynchronize(c->stream));
+    return GNB_OK;
+}
+
 extern "C" int gnb_sigma_eval(gnb_ctx* c, int contact, int which, int M, const double* E, double* out_blk,
                               int32_t* iters, double* diffs) {
     if (!c || contact < 0 || contact >= (int)c->contacts.size() || M < 0 || (M > 0 && (!E || !out_blk)))
@@ -576,13 +604,7 @@ extern "C" int gnb_sigma_eval(gnb_ctx* c, int contact, int which, int M, const d
     Contact& ct = c->contacts[contact];
     GNB_CK(c->info.ensure(sizeof(int) * 4));
     GNB_CK(cudaMemsetAsync(c->info.p, 0, sizeof(int) * 4, c->stream));
-    GNB_CK(c->dE.ensure((size_t)M * sizeof(cplx)));
-    GNB_CK(cudaMemcpyAsync(c->dE.p, E, (size_t)M * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
-    const cplx* dE = c->dE.as<cplx>();
     const long nn = (long)ct.nc * ct.nc;
-    const cplx* src = nullptr;
-    size_t per = 0;
-    int rc = GNB_OK;
     if (ct.kind == GNB_C_CONST) {
         std::vector<cplx> h(nn);
         GNB_CK(cudaMemcpyAsync(h.data(), ct.d_const.p, nn * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
@@ -591,23 +613,22 @@ extern "C" int gnb_sigma_eval(gnb_ctx* c, int contact, int which, int M, const d
         if (iters) std::fill(iters, iters + M, 0);
         if (diffs) std::fill(diffs, diffs + M, 0.0);
         return GNB_OK;
-    } else if (ct.kind == GNB_C_CHAIN1D) {
-        if (which == 1) { rc = gnb_chain1d_surface_g(c, ct, M, dE); src = c->cg.as<cplx>(); }
-        else { rc = gnb_contact_eval(c, ct, M, dE, 0); src = ct.blk.as<cplx>(); }
-        per = nn;
-    } else {
-        if (which == 0) { rc = gnb_contact_eval(c, ct, M, dE, 0); src = ct.blk.as<cplx>(); per = nn; }
-        else {
-            per = (which == 1 ? 12 : 9) * BSZ;
-            GNB_CK(ct.surf.ensure((size_t)M * 12 * BSZ * sizeof(cplx)));
-            rc = gnb_bethe_raw(c, ct, M, dE, which, ct.surf.as<cplx>());
-            src = ct.surf.as<cplx>();
-        }
     }
-    if (rc) return rc;
-    GNB_CK(cudaMemcpyAsync(out_blk, src, (size_t)M * per * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
-    if (iters) GNB_CK(cudaMemcpyAsync(iters, ct.iters.p, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (diffs) GNB_CK(cudaMemcpyAsync(diffs, ct.diffs.p, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // energies in chunks: bounded workspace (the chain fixed point keeps ~10 n_c x n_c matrices per energy) and
+    // gridDim.y = chunk <= 8192
+    const size_t per_out = ct.kind == GNB_C_CHAIN1D ? (size_t)nn : (which == 0 ? (size_t)nn : (size_t)(which == 1 ? 12 : 9) * BSZ);
+    const size_t per_ws = (ct.kind == GNB_C_CHAIN1D ? 12 * (size_t)nn : (size_t)nn + 12 * BSZ) * sizeof(cplx) + 256;
+    size_t mc = std::max<size_t>(1, std::min<size_t>(c->ws_limit / per_ws, 8192));
+    const size_t nchunks = ((size_t)M + mc - 1) / mc;
+    mc = ((size_t)M + nchunks - 1) / nchunks;
+    for (int k0 = 0; k0 < M; k0 += (int)mc) {
+        const int m = std::min<int>((int)mc, M - k0);
+        GNB_CK(c->dE.ensure((size_t)m * sizeof(cplx)));
+        GNB_CK(cudaMemcpyAsync(c->dE.p, E + 2 * (size_t)k0, (size_t)m * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+        int rc = sigma_eval_chunk(c, ct, which, m, out_blk + (size_t)k0 * per_out * 2, iters ? iters + k0 : nullptr,
+                                  diffs ? diffs + k0 : nullptr);
+        if (rc) return rc;
+    }
     int info = 0;
     GNB_CK(cudaMemcpyAsync(&info, c->info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     GNB_CK(cudaStreamSynchronize(c->stream));

@@ -7,8 +7,15 @@ kernel: energies are independent, so the path shards with weak scaling.
 torch is used for what it is here for: device buffers, streams and torch.distributed.
 """
 import os
+import time
 
 import numpy as np
+
+# wall-clock / device-time breakdown of the last sharded_matrix_sum call on this rank (bench.py, profiles/):
+# partial_ms (device work of the rank's shard incl. its host orchestration), allreduce_ms, d2h_ms
+last_breakdown = {}
+
+_buffers = {}          # (N, device index) -> (device accumulator, pinned host result)
 
 
 def dist_info():
@@ -29,6 +36,29 @@ def shard_indices(M, rank, world):
     return np.arange(rank, M, world)
 
 
+def rank0_value(fn):
+    """fn() evaluated on rank 0 and broadcast, so that every rank continues from the same value (checkpoint contents)"""
+    rank, world = dist_info()
+    if world == 1:
+        return fn()
+    import torch.distributed as dist
+    box = [fn() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def _device_buffers(N, device):
+    """persistent N x N device accumulator + pinned host landing buffer per (N, GPU): no allocation, no pageable copy
+    in the per-call path"""
+    import torch
+    key = (N, device.index)
+    if key not in _buffers:
+        _buffers.clear()                       # one size at a time: 2 x 16 N^2 bytes
+        _buffers[key] = (torch.empty((N, N), dtype=torch.complex128, device=device),
+                         torch.empty((N, N), dtype=torch.complex128).pin_memory())
+    return _buffers[key]
+
+
 def sharded_matrix_sum(N, Elist, weights, partial_fn, device=None):
     """sum_k w_k f(E_k) with the energies split over the ranks.
 
@@ -45,11 +75,19 @@ def sharded_matrix_sum(N, Elist, weights, partial_fn, device=None):
     import torch
     import torch.distributed as dist
     if device is not None:
-        out = torch.zeros((N, N), dtype=torch.complex128, device=device)
-        partial_fn(Elist[idx], weights[idx], out)
-        flat = torch.view_as_real(out)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        return out.cpu().numpy()
+        out, host = _device_buffers(N, device)
+        t0 = time.perf_counter()
+        partial_fn(Elist[idx], weights[idx], out)          # an empty shard writes zeros (gnb_gr_int with M = 0)
+        t1 = time.perf_counter()
+        dist.all_reduce(torch.view_as_real(out), op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize(device)
+        t2 = time.perf_counter()
+        host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(device)
+        t3 = time.perf_counter()
+        last_breakdown.update(partial_ms=1e3 * (t1 - t0), allreduce_ms=1e3 * (t2 - t1), d2h_ms=1e3 * (t3 - t2),
+                              bytes=16 * N * N, world=world)
+        return host.numpy().copy()
     part = np.asarray(partial_fn(Elist[idx], weights[idx], None), dtype=np.complex128)
     t = torch.from_numpy(np.ascontiguousarray(part).view(np.float64).copy())
     dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -10,6 +10,11 @@ from .config import (SURFACE_GREEN_CONVERGENCE, SURFACE_RELAXATION_FACTOR, SURFA
 DESC, DENSE_CONST, DENSE_CALL = "desc", "dense_const", "dense_call"
 
 
+def _is_bethe(g):
+    from .surfGBethe import is_bethe_object
+    return is_bethe_object(g)
+
+
 def support(mat, tol=0.0):
     """orbitals on which a self-energy matrix (or its adjoint) is non-zero"""
     m = np.abs(np.asarray(mat)) > tol
@@ -73,8 +78,11 @@ class ObjectPlan:
         self.g, self.N = g, N
         self.kind = DENSE_CALL
         self.full = None
+        self.spin = getattr(g, "spin", 'r') if hasattr(g, "gList") else 'r'     # spin expansion done by the object itself
         if hasattr(g, "_gnb_install"):                      # our own surfG / surfGB / surfGBAt
             self.kind = DESC
+        elif _is_bethe(g):
+            self.kind = DESC                                 # a surfGB built by the reference's own constructor
         elif all(hasattr(g, a) for a in ("aList", "aSList", "bList", "bSList", "tauList", "stauList", "indsList", "eta")) \
                 and all(np.shape(t)[0] == np.shape(t)[1] == len(i) for t, i in zip(g.tauList, g.indsList)):
             self.kind = DESC                                 # a reference-style surfG1D object
@@ -82,11 +90,15 @@ class ObjectPlan:
             self.kind = DENSE_CONST                          # surfGTest-style constant matrices
             self.full = [np.asarray(s, dtype=complex) for s in g.sig]
 
-    def install(self, ctx):
+    def install(self, ctx, spin_mode=None):
         ctx.sigma_clear()
         if self.kind != DESC:
             return
         g = self.g
+        if _is_bethe(g):
+            from .surfGBethe import install_bethe
+            install_bethe(ctx, g, spin_mode=spin_mode)
+            return
         if hasattr(g, "_gnb_install"):
             g._gnb_install(ctx)
             return

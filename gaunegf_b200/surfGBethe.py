@@ -104,6 +104,36 @@ class surfGBAt:
         return -np.trace(Gr).imag / np.pi
 
 
+_SPIN_MODE = {'r': 0, 'u': 1, 'ro': 1, 'g': 2}
+
+
+def is_bethe_object(g):
+    """a surfGB-shaped object: ours, or one built by the reference's constructor (surfGBethe.py:106-248)"""
+    return (all(hasattr(g, a) for a in ("gList", "indsLists", "nIndLists"))
+            and all(all(hasattr(a, x) for x in ("H", "Slist", "Vlist", "eta")) for a in g.gList))
+
+
+def bethe_orthonormal(g):
+    """the reference decides by its parameter file: Sdict['sss'] == 0 selects Xi Sigma Xi (surfGBethe.py:530-533)"""
+    if hasattr(g, "orthonormal"):
+        return bool(g.orthonormal)
+    return hasattr(g, "Sdict") and g.Sdict.get("sss", 1.0) == 0
+
+
+def install_bethe(ctx, g, conv=SURFACE_GREEN_CONVERGENCE, spin_mode=None):
+    """device description of a surfGB-shaped object: one Bethe contact per contact of g; with an orthonormal
+    parameter set and / or a spin-expanded system also the Sigma -> expand(Xi Sigma Xi) transform
+    (surfGBethe.py:529-539).  spin_mode overrides the object's own (transport's spinor -> block reordering)."""
+    orth = bethe_orthonormal(g)
+    mode = _SPIN_MODE[getattr(g, "spin", 'r')] if spin_mode is None else spin_mode
+    if orth or mode:
+        n = ctx.N // 2 if mode else ctx.N
+        ctx.sigma_set_transform(n, np.asarray(g.Xi) if orth else None, mode)
+    for at, inds, nbs in zip(g.gList, g.indsLists, g.nIndLists):
+        ctx.sigma_add_bethe(np.concatenate([np.asarray(i) for i in inds]), [list(x) for x in nbs], np.asarray(at.H),
+                            np.asarray(at.Slist), np.asarray(at.Vlist), at.eta, conv, BETHE_MIXING, BETHE_MAX_ITER)
+
+
 class surfGB:
     """Device with Bethe-lattice contacts (surfG protocol).  Build with from_parts()."""
 
@@ -123,11 +153,8 @@ class surfGB:
         self.Xi, self.orthonormal, self.spin, self.eta = Xi, orthonormal, spin, eta
         return self
 
-    def _gnb_install(self, ctx, conv=SURFACE_GREEN_CONVERGENCE):
-        if self.orthonormal or self.spin != 'r':
-            raise ValueError("device-side Bethe description supports the non-orthogonal, spin-restricted case")
-        for g, inds, nbs in zip(self.gList, self.indsLists, self.nIndLists):
-            ctx.sigma_add_bethe(np.concatenate(inds), nbs, g.H, g.Slist, g.Vlist, g.eta, conv, BETHE_MIXING, BETHE_MAX_ITER)
+    def _gnb_install(self, ctx, conv=SURFACE_GREEN_CONVERGENCE, spin_mode=None):
+        install_bethe(ctx, self, conv, spin_mode)
 
     def sigma(self, E, i, conv=SURFACE_GREEN_CONVERGENCE):
         """N x N self-energy of contact i (surfGBethe.py:479-542)"""

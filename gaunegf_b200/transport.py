@@ -87,6 +87,19 @@ class SigmaCalculator:
         return ArrayPlan([self.sig1, self.sig2], N)
 
 
+def _described_spin_mode(plan, g, spin, n):
+    """spin mode (1: kron(I2, .), 2: kron(., I2)) when a surfGB-shaped object's spin expansion can run on the
+    device for a 2N x 2N system treated with `spin`; 0 otherwise (host evaluation of g.sigmaTot / g.sigma)"""
+    from .surfGBethe import is_bethe_object
+    if plan.kind != DESC or not is_bethe_object(g) or spin not in ('u', 'ro', 'g'):
+        return 0
+    own = getattr(g, "spin", 'r')
+    want = 1 if spin in ('u', 'ro') else 2
+    if own == 'r':                       # SigmaCalculator expands an N x N Sigma itself (transport.py:92-103)
+        return want if getattr(g, "N", None) is not None and 2 * g.N == n else 0
+    return want if (1 if own in ('u', 'ro') else 2) == want else 0
+
+
 def _batched_sigma(calc, energies, spin, n, which):
     if which == 'tot':
         return np.stack([calc.get_sigma_total(E, spin, n) for E in energies]).astype(complex)
@@ -133,6 +146,15 @@ def _transmission_batch(F, S, calc, energies, spin):
         Fm, Sm = Fm[ix], Sm[ix]
     ctx.set_system(Fm, Sm)
     ctx.sigma_clear()
+    if calc.energy_dependent:
+        plan = calc._plan(n)
+        mode = _described_spin_mode(plan, calc.sig1, spin, n)
+        if mode:
+            # Bethe contacts: Sigma blocks, Xi Sigma Xi and the spin expansion all on the device; after the
+            # spinor -> block reordering above a 'g' expansion kron(Sigma, I2) reads kron(I2, Sigma)
+            plan.install(ctx, spin_mode=1)
+            T4 = parallel.sharded_per_energy(energies, ctx.transmission_spin_described, width=4)
+            return T4.sum(axis=1), T4
 
     def spin_fn(E):
         const = not calc.energy_dependent
@@ -187,7 +209,11 @@ def _dos_batch(F, S, calc, energies, spin):
             fn = _host_sigma_dos
     else:
         ctx.sigma_clear()
-        if calc.energy_dependent:
+        mode = _described_spin_mode(calc._plan(n), calc.sig1, spin, n) if calc.energy_dependent else 0
+        if mode:
+            calc._plan(n).install(ctx, spin_mode=mode)
+            fn = lambda E: np.column_stack(ctx.dos(E)[::-1])                   # noqa: E731
+        elif calc.energy_dependent:
             fn = _host_sigma_dos
         else:
             st = calc.get_sigma_total(None, spin, n).astype(complex)
@@ -222,6 +248,27 @@ def _blocks(remaining, checkpoint_file, checkpoint_interval):
     return [remaining[a:b] for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
+def _load_checkpoint(checkpoint_file):
+    """checkpoint contents as a dict of arrays, identical on every rank: rank 0 reads the file and broadcasts it
+    (ranks that read a file another rank is replacing could disagree on what is left to do)"""
+    def read():
+        if checkpoint_file and os.path.exists(checkpoint_file):
+            with np.load(checkpoint_file, allow_pickle=True) as data:
+                return {k: np.array(data[k]) for k in data.files}
+        return None
+    return parallel.rank0_value(read)
+
+
+def _save_checkpoint(checkpoint_file, **arrays):
+    """rank 0 writes <file>.tmp and renames it over the checkpoint (never a half-written .npz)"""
+    if parallel.dist_info()[0] != 0:
+        return
+    target = checkpoint_file if str(checkpoint_file).endswith(".npz") else str(checkpoint_file) + ".npz"   # np.savez's rule
+    tmp = target + ".tmp.npz"
+    np.savez(tmp, **arrays)
+    os.replace(tmp, target)
+
+
 def calculate_transmission(F, S, sigma_calculator, energy_list,
                            spin=None, checkpoint_file=None,
                            checkpoint_interval=10):
@@ -237,8 +284,8 @@ def calculate_transmission(F, S, sigma_calculator, energy_list,
 
     transmission = -1 * np.ones(n_energies)
     spin_trans = -1 * np.ones((n_energies, 4)) if open_shell else None
-    if checkpoint_file and os.path.exists(checkpoint_file):
-        data = np.load(checkpoint_file, allow_pickle=True)
+    data = _load_checkpoint(checkpoint_file)
+    if data is not None:
         if 'energy_list' in data:
             saved = data['energy_list']
             if np.shape(saved) != np.shape(energy_list) or not np.allclose(saved, energy_list, rtol=1e-10):
@@ -252,10 +299,10 @@ def calculate_transmission(F, S, sigma_calculator, energy_list,
 
     def save():
         if spin_trans is not None:
-            np.savez(checkpoint_file, transmission=transmission, spin_transmission=spin_trans,
-                     energy_list=energy_list)
+            _save_checkpoint(checkpoint_file, transmission=transmission, spin_transmission=spin_trans,
+                             energy_list=energy_list)
         else:
-            np.savez(checkpoint_file, transmission=transmission, energy_list=energy_list)
+            _save_checkpoint(checkpoint_file, transmission=transmission, energy_list=energy_list)
 
     remaining = np.where(transmission == -1)[0]
     for block in _blocks(remaining, checkpoint_file, checkpoint_interval):
@@ -289,8 +336,8 @@ def calculate_dos(F, S, sigma_calculator, energy_list,
     dos_total = -1 * np.ones(n_energies)
     dos_per_site = -1 * np.ones((n_energies, n_sites))
     dos_spin = -1 * np.ones((n_energies, 2)) if open_shell else None
-    if checkpoint_file and os.path.exists(checkpoint_file):
-        data = np.load(checkpoint_file, allow_pickle=True)
+    data = _load_checkpoint(checkpoint_file)
+    if data is not None:
         if 'energy_list' in data:
             saved = data['energy_list']
             if np.shape(saved) != np.shape(energy_list) or not np.allclose(saved, energy_list, rtol=1e-10):
@@ -305,10 +352,10 @@ def calculate_dos(F, S, sigma_calculator, energy_list,
 
     def save():
         if dos_spin is not None:
-            np.savez(checkpoint_file, dos_total=dos_total, dos_per_site=dos_per_site, dos_spin=dos_spin,
-                     energy_list=energy_list)
+            _save_checkpoint(checkpoint_file, dos_total=dos_total, dos_per_site=dos_per_site, dos_spin=dos_spin,
+                             energy_list=energy_list)
         else:
-            np.savez(checkpoint_file, dos_total=dos_total, dos_per_site=dos_per_site, energy_list=energy_list)
+            _save_checkpoint(checkpoint_file, dos_total=dos_total, dos_per_site=dos_per_site, energy_list=energy_list)
 
     remaining = np.where(dos_total == -1)[0]
     for block in _blocks(remaining, checkpoint_file, checkpoint_interval):

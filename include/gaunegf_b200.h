@@ -51,6 +51,10 @@ int64_t gnb_launch_count(const gnb_ctx* ctx);
 /* device-side milliseconds spent inside the elimination launches of the last compute call
  * (CUDA events on the context's stream; bench.py's roofline leg) */
 double gnb_last_elim_ms(const gnb_ctx* ctx);
+/* executed real FP64 flops (4-multiplication equivalents: 8 per complex multiply-add, 4 / 2 where one / both
+ * operands are known to be real) of the rank-K update, forward-W and back-substitution launches of the last
+ * compute call (recursive engine); counted on the host at launch time, no timing needed (bench.py's step_frac) */
+double gnb_last_elim_flops(const gnb_ctx* ctx);
 /* enable/disable the event timing above (adds one event synchronisation per energy chunk) */
 int gnb_set_timing(gnb_ctx* ctx, int on);
 /* with timing on: accumulated device time (ms, CUDA events around each launch), algorithmic real
@@ -86,6 +90,14 @@ int gnb_sigma_add_bethe(gnb_ctx* ctx, int natoms, const int32_t* inds, const int
                         const int32_t* nb_dirs, const double* H, const double* Slist,
                         const double* Vlist, double eta, double conv, double mix, int max_iter);
 
+/* De-orthonormalisation and spin expansion of the contact self-energies (surfGBethe.py:529-539):
+ *   Sigma_tot(E) = expand( Xi [ sum_c scatter(inds_c, blk_c(E)) ] Xi ),
+ * Xi: n x n (NULL = identity; the reference uses S^(1/2) when the Bethe parameters are orthonormal), spin_mode 0: none
+ * (n = N), 1: kron(I2, .) ('u', 'ro'), 2: kron(., I2) ('g') with n = N/2.  Call after gnb_sigma_clear and before
+ * adding contacts, whose orbital indices then refer to the n-dimensional space.  The drivers build the dense
+ * Sigma(E_k) / Gamma(E_k) on the device and run the full-inverse algorithms. */
+int gnb_sigma_set_transform(gnb_ctx* ctx, int n, const double* Xi, int spin_mode, int loc);
+
 /* ---- Sigma(E) providers on their own (surfG.g / sigma, surfGBAt.sigmaK / sigma) ----------------
  * out_blk: M x nc x nc compact contact blocks (host); iters/diffs: per energy iteration count and
  * last convergence measure (may be NULL).  which: 0 = contact self-energy block,
@@ -115,7 +127,9 @@ int gnb_green_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, lon
 int gnb_transmission_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride,
                            const double* gam1, long g1_stride, const double* gam2, long g2_stride, double* T);
 /* spin-resolved transmission (transport.py:159-181): the system is 2N x 2N in block order; T4: M x 4
- * = [T_uu, T_ud, T_du, T_dd] with T_i = Re Tr[Gamma1[r,r] G[r,c] Gamma2[c,c] Ga[r,c]] */
+ * = [T_uu, T_ud, T_du, T_dd] with T_i = Re Tr[Gamma1[r,r] G[r,c] Gamma2[c,c] Ga[r,c]].
+ * sig = gam1 = gam2 = NULL: use the described self-energies (needs gnb_sigma_set_transform with a spin mode),
+ * contacts 0 and -1. */
 int gnb_transmission_spin(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride,
                           const double* gam1, long g1_stride, const double* gam2, long g2_stride, double* T4);
 int gnb_dos_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, long sig_stride,

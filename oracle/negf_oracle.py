@@ -515,7 +515,7 @@ class surfGB:
     Slater-Koster setup (ctor, :106-477) is out of scope: the parts it produces are passed in."""
 
     def __init__(self, F, S, gList, indsLists, nIndLists, Xi=None, orthonormal=False, spin="r"):
-        self.F, self.S, self.N = F, S, len(F)
+        self.F, self.S, self.N = F, S, (len(F) if spin == "r" else len(F) // 2)   # spin: F is 2N x 2N (:114-123)
         self.gList, self.indsLists, self.nIndLists = gList, indsLists, nIndLists
         self.Xi, self.orthonormal, self.spin = Xi, orthonormal, spin
 

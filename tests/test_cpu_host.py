@@ -25,6 +25,13 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gaunegf_b200.h but not exported"
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     assert b"sm_100a" in lib.gnb_version()
+    # developer switches / probes live in their own header and are not part of the drop-in ABI; nothing else is exported
+    dev = open(os.path.join(ROOT, "include", "gaunegf_b200_dev.h")).read()
+    dev_declared = set(re.findall(r"\b(gnb_dev_[a-z0-9_]+)\s*\(", dev))
+    assert dev_declared == set(_native.DEV_SIGNATURES), dev_declared ^ set(_native.DEV_SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gnb_[a-z0-9_]+)$", out, flags=re.M))
+    assert exported == declared | dev_declared, exported ^ (declared | dev_declared)
 
 
 def test_no_cpu_fallback():
@@ -152,6 +159,81 @@ assert np.max(np.abs(one - w[0] * f(E[0]))) < 1e-12
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
+
+
+GLOO_CKPT_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["GNB_ROOT"])
+import torch.distributed as dist
+dist.init_process_group("gloo")
+from gaunegf_b200 import parallel, transport as tr
+rank, world = parallel.dist_info()
+calls = []
+def fake_batch(F, S, calc, energies, spin):          # stands in for the GPU batch: T(E) = E^2 on this rank's shard
+    calls.append(len(energies))
+    return parallel.sharded_per_energy(np.asarray(energies), lambda El: El ** 2)
+tr._transmission_batch = fake_batch
+ck = os.environ["GNB_CKPT"]
+E = np.linspace(0.0, 2.0, 23)
+T = tr.calculate_transmission(None, None, None, E, checkpoint_file=ck, checkpoint_interval=5)
+assert np.allclose(T, E ** 2)
+dist.barrier()
+d = np.load(ck)                                      # complete, readable file; only rank 0 wrote it
+assert np.allclose(d["transmission"], E ** 2) and not os.path.exists(ck + ".tmp.npz")
+dist.barrier()
+# resume from a partial checkpoint: every rank must agree on what is left (rank 0 reads and broadcasts)
+if rank == 0:
+    part = E ** 2
+    part[9:] = -1
+    np.savez(ck, transmission=part, energy_list=E)
+dist.barrier()
+calls.clear()
+T2 = tr.calculate_transmission(None, None, None, E, checkpoint_file=ck, checkpoint_interval=5)
+assert np.allclose(T2, E ** 2) and sum(calls) == 23 - 9, calls
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_checkpoint_two_gloo_ranks(tmp_path):
+    """under torchrun only rank 0 writes the .npz (atomically) and resume state is broadcast"""
+    script = tmp_path / "gloo_ckpt.py"
+    script.write_text(GLOO_CKPT_SCRIPT)
+    env = dict(os.environ, GNB_ROOT=ROOT, OMP_NUM_THREADS="1", GNB_CKPT=str(tmp_path / "ck.npz"))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
+
+
+def test_bethe_objects_get_a_device_plan():
+    """surfGB-shaped objects (ours or the reference's: attributes gList / indsLists / nIndLists) are described to the
+    device, including orthonormal (Xi) and spin-expanded ones; the install sequence is transform first, then contacts"""
+    import types
+    from gaunegf_b200.sigma_plan import ObjectPlan, DESC, DENSE_CALL
+    at = types.SimpleNamespace(H=np.eye(9), Slist=[np.zeros((9, 9))] * 12, Vlist=[np.eye(9)] * 12, eta=1e-4)
+    inds = [[np.arange(9), np.arange(9, 18)], [np.arange(18, 27)]]
+    nil = [[[0, 1], [2]], [[3]]]
+    log = []
+
+    class Ctx:
+        N = 60
+        def sigma_clear(self): log.append("clear")
+        def sigma_set_transform(self, n, Xi, mode): log.append(("xform", n, Xi is not None, mode))
+        def sigma_add_bethe(self, i, nb, *a): log.append(("bethe", len(i), nb))
+    ref = types.SimpleNamespace(gList=[at, at], indsLists=inds, nIndLists=nil, Xi=np.eye(30), Sdict={"sss": 0}, spin="g")
+    plan = ObjectPlan(ref, 60)
+    assert plan.kind == DESC
+    plan.install(Ctx())
+    assert log == ["clear", ("xform", 30, True, 2), ("bethe", 18, [[0, 1], [2]]), ("bethe", 9, [[3]])]
+    log.clear()
+    ref.Sdict, ref.spin = {"sss": 0.1}, "r"
+    Ctx.N = 30
+    ObjectPlan(ref, 30).install(Ctx())
+    assert log[0] == "clear" and log[1][0] == "bethe"          # plain case: no transform
+    assert ObjectPlan(types.SimpleNamespace(sigma=None, sigmaTot=None), 30).kind == DENSE_CALL
 
 
 def test_energy_sharding_two_gloo_ranks(tmp_path):

@@ -15,7 +15,7 @@ def test_cfg1_chain_transmission_dos_current(golden):
     F, S, s1, s2 = sy.chain(64)
     calc = O.SigmaCalculator(s1, s2, energy_dependent=False)
     T = O.calculate_transmission(F, S, calc, G["E"])
-    assert np.allclose(T, G["T"], rtol=1e-9, atol=1e-12 * G["T"].max())
+    assert relerr(T, G["T"]) < 1e-10
     tot, per = O.calculate_dos(F, S, calc, G["Ed"])
     assert relerr(tot, G["dos_tot"]) < TOL and relerr(per, G["dos_site"]) < TOL
     for (qV, Tk), ref in zip(G["cur_args"], G["cur"]):
@@ -158,3 +158,55 @@ def test_oracle_vs_live_reference_when_present():
     Er, wr = np.linspace(-0.4, 0.4, 9), np.full(9, 0.1)
     for ind in (None, 0, -1):
         assert relerr(O.GrLessInt(F, S, og, Er, wr, ind), np.asarray(it.GrLessInt(F, S, g, Er, wr, ind))) < TOL
+
+
+# ---- BASELINE-size goldens (tests/golden/make_golden_full.py): a bounded part of each on the CPU -------------------
+def test_cfg4_full_size_oracle(golden):
+    """n_c = 128 fixed point: the oracle's iteration counts and g equal the reference's (3 of the 32 golden problems;
+    the GPU test covers all of them)"""
+    from full_cases import cfg4_system
+    G = golden("cfg4_full")
+    F, S, li, taus = cfg4_system()
+    og = O.surfG1D(F, S, li, taus, eta=0.02)
+    ii, jj = G["ii"], G["jj"]
+    for k, c in ((2, 0), (7, 1), (12, 1)):
+        gm = og.g(G["E"][k], c)
+        assert og.last_iters[(complex(G["E"][k]), c)][0] == G["iters_a"][k, c]
+        assert relerr(gm[ii, jj], G["g_samp_a"][k, c]) < TOL
+        assert abs(np.linalg.norm(gm) - G["g_fro_a"][k, c]) < TOL * G["g_fro_a"][k, c]
+
+
+def test_cfg5_full_size_oracle(golden):
+    """N = 2048 GrLessInt(ind = -1) with Bethe contacts: oracle == reference (4 energies, about 10 s of LAPACK)"""
+    from full_cases import bethe_atoms, check_sampled, nind_lists
+    G = golden("cfg5_full")
+    N = int(G["N"])
+    F, S = sy.hermitian_pair(N, seed=3)
+    gB = O.surfGB(F, S, bethe_atoms(G, O.surfGBAt, eta=float(G["eta"])), G["indsLists"], nind_lists(G))
+    check_sampled(O.GrLessInt(F, S, gB, G["Eg"], G["wg"], -1), G, "GL_last", TOL, relerr)
+
+
+def test_bethe_orthonormal_and_spin_oracle(golden):
+    """Xi Sigma Xi and the spin kron (surfGBethe.py:529-539): oracle == reference"""
+    from full_cases import bethe_atoms, nind_lists, spin_system
+    G = golden("bethe_xi")
+    Nb = int(G["Nb"])
+    F, S = sy.hermitian_pair(Nb, seed=3)
+    gO = O.surfGB(F, S, bethe_atoms(G, O.surfGBAt, "o_"), G["o_indsLists"], nind_lists(G, "o_"), Xi=G["o_Xi"],
+                  orthonormal=True)
+    E = G["E_o"]
+    assert relerr(gO.sigma(E[0], 0), G["o_sig0"]) < TOL and relerr(gO.sigmaTot(E[1]), G["o_sigT"]) < TOL
+    calc = O.SigmaCalculator(gO, energy_dependent=True)
+    assert relerr(O.calculate_transmission(F, S, calc, E), G["o_T"]) < TOL
+    assert relerr(O.GrLessInt(F, S, gO, E, np.array([0.2, 0.5, 0.3]), -1), G["o_GL"]) < TOL
+    assert relerr(O.GrInt(F, S, gO, E + 0.3j, np.array([0.2, 0.5j, 0.3])), G["o_GI"]) < TOL
+    ii, jj = G["ii"], G["jj"]
+    for sp in ("u", "g"):
+        F2, S2 = spin_system(F, S, sp)
+        gS = O.surfGB(F2, S2, bethe_atoms(G, O.surfGBAt, sp + "_"), G[sp + "_indsLists"], nind_lists(G, sp + "_"), spin=sp)
+        Es = G["E_" + sp]
+        assert relerr(gS.sigmaTot(Es[0])[ii, jj], G[sp + "_sigT_samp"]) < TOL
+        P = O.GrInt(F2, S2, gS, Es + 0.2j, np.array([1.0, -0.5j]))
+        assert relerr(P[ii, jj], G[sp + "_GI_samp"]) < TOL and relerr(np.diag(P), G[sp + "_GI_diag"]) < TOL
+        P = O.GrLessInt(F2, S2, gS, Es, np.array([0.6, 0.4]), 0)
+        assert relerr(P[ii, jj], G[sp + "_GL_samp"]) < TOL and relerr(np.diag(P), G[sp + "_GL_diag"]) < TOL
