@@ -41,6 +41,13 @@ extern "C" int gnb_create(gnb_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GNB_ERR_CUDA; }
     gnb_ctx* c = new gnb_ctx();
     c->device = device;
+    {   // per-call energy-chunk workspace: 60 % of the GPU's memory (B200: 108 of 180 GB), so that the 1250-energy
+        // N = 1024 step is ONE lock-step chunk (2 sub-batches of 625; +4 % against two 48 GiB chunks)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0)
+            c->ws_limit = std::max<size_t>((size_t)4 << 30, std::min<size_t>(total_b / 10 * 6, free_b / 10 * 8));
+        else cudaGetLastError();
+    }
     if (gnb_kernels_init() != cudaSuccess || gnb_rec_init() != cudaSuccess || gnb_small_init() != cudaSuccess || gnb_sigma_init() != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
         cudaEventCreate(&c->ev1) != cudaSuccess) {
         cudaGetLastError();
@@ -143,6 +150,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
+    else if (!strcmp(name, "tourn_warp")) gnb_set_tourn_warp(value);
     else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
     else return GNB_ERR_ARG;
     return GNB_OK;

@@ -397,6 +397,337 @@ k_tourn(const cplx* __restrict__ A, long strideA, int ld, int c0, int w, int r0,
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-synchronous tournament round (block width 32).  One CTA = 4 warps = up to 256 candidate rows.
+//   level 0: every warp runs Gaussian elimination with partial pivoting on ITS 64 rows (2 per lane, all 32 panel
+//            columns of a row in the registers of one lane) and nominates 32 of them;
+//   level 1: warps 0 / 1 merge two nominee lists each (64 rows, entries re-read from the matrix), nominate 32;
+//   level 2: warp 0 merges the last two lists.
+// Inside a warp a pivot step needs no CTA barrier and no cross-warp reduction: pivot search = REDUX + ballot, the
+// pivot row goes through a 32-element per-warp buffer (one lane writes, all read with LDS.128), the update is a
+// fully unrolled triangle of FMAs on registers.  Against k_tourn (128 rows per CTA, one CTA barrier per step, column
+// groups spread over the warps) a round issues less than half the warp instructions per candidate row, the CTA
+// reduces 256 rows instead of 128 (N = 1024: two launches per block instead of three), and the final round's
+// latency chain is 3 x 32 warp steps + a warp-level in-place Gauss-Jordan inverse instead of 64 CTA-barrier steps.
+// The final round (F64 on the original entries) fixes the pivot order, emits the pivot-block inverse, the net row
+// moves and the permutation update exactly like k_tourn.
+// ------------------------------------------------------------------------------------------
+#ifdef TW_DEBUG
+__device__ __forceinline__ double dbgv(float v) { return v; }
+__device__ __forceinline__ double dbgv(double v) { return v; }
+__device__ __forceinline__ double dbgv(float2 v) { return v.x; }
+__device__ __forceinline__ double dbgv(double2 v) { return v.x; }
+#endif
+// 16-byte chunks of the per-warp pivot-row buffer: PER elements of type C per LDS.128 / STS.128 (no type punning
+// through unions: explicit vector types)
+template <typename C> struct TwChunk;
+template <> struct TwChunk<float> {
+    static constexpr int PER = 4;
+    static __device__ __forceinline__ void st(float* p, const float (&e)[4]) { *reinterpret_cast<float4*>(p) = make_float4(e[0], e[1], e[2], e[3]); }
+    static __device__ __forceinline__ void ld(const float* p, float (&e)[4]) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+    }
+};
+template <> struct TwChunk<float2> {
+    static constexpr int PER = 2;
+    static __device__ __forceinline__ void st(float2* p, const float2 (&e)[2]) { *reinterpret_cast<float4*>(p) = make_float4(e[0].x, e[0].y, e[1].x, e[1].y); }
+    static __device__ __forceinline__ void ld(const float2* p, float2 (&e)[2]) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        e[0] = make_float2(v.x, v.y); e[1] = make_float2(v.z, v.w);
+    }
+};
+template <> struct TwChunk<double> {
+    static constexpr int PER = 2;
+    static __device__ __forceinline__ void st(double* p, const double (&e)[2]) { *reinterpret_cast<double2*>(p) = make_double2(e[0], e[1]); }
+    static __device__ __forceinline__ void ld(const double* p, double (&e)[2]) {
+        const double2 v = *reinterpret_cast<const double2*>(p);
+        e[0] = v.x; e[1] = v.y;
+    }
+};
+template <> struct TwChunk<double2> {
+    static constexpr int PER = 1;
+    static __device__ __forceinline__ void st(double2* p, const double2 (&e)[1]) { *p = e[0]; }
+    static __device__ __forceinline__ void ld(const double2* p, double2 (&e)[1]) { e[0] = *p; }
+};
+
+template <typename T>
+__device__ __forceinline__ void tw_load(typename T::C (&a)[2][32], const int (&rows)[2], const cplx* __restrict__ Ab, int ld,
+                                        int c0, int mixr) {
+    // loads go out in groups of 8 columns (the compiler would otherwise keep all 32 raw 16-byte values of a row live)
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        if (rows[rr] < 0) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) a[rr][k] = T::zero();
+        } else if (c0 < mixr) {                              // panel stored as real doubles (mixed layout)
+            const double2* src = reinterpret_cast<const double2*>(gnb_real_view(Ab, mixr) + (long)rows[rr] * 2 * ld + c0);
+#pragma unroll
+            for (int q0 = 0; q0 < 16; q0 += 8) {
+                double2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = src[q0 + q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    a[rr][2 * (q0 + q)] = T::ld(cmake(v[q].x, 0.0));
+                    a[rr][2 * (q0 + q) + 1] = T::ld(cmake(v[q].y, 0.0));
+                }
+                asm volatile("" ::: "memory");
+            }
+        } else {
+            const cplx* src = Ab + (long)rows[rr] * ld + c0;
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 8) {
+                cplx v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = src[k0 + k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[rr][k0 + k] = T::ld(v[k]);
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+}
+
+// WIDTH pivot steps [j0, j1) of the warp GEPP.  The rows are ROTATED left by one column per step (fused into the
+// update: a[c - 1] = a[c] - l p[c]), so the pivot column is always register column 0, every register index is
+// static and the step loop stays rolled: a fully unrolled triangle is faster per step on paper but ~9 k instructions
+// per kernel, and a tournament CTA runs its code exactly once - it was instruction-fetch bound (85 us per final
+// round against 51 us of the CTA-wide kernel).  WIDTH = live columns at j0 (32, then 16 for the second half).
+template <typename T, bool F64, int WIDTH>
+__device__ __forceinline__ void tw_steps(typename T::C (&a)[2][32], const int (&rows)[2], unsigned& alive, int j0, int j1,
+                                         typename T::C* s_prow, int* s_win, int lane, bool flag_singular, int* info) {
+    typedef typename T::C C;
+    typedef TwChunk<C> CH;
+    constexpr int PER = CH::PER;
+    const unsigned long long kzero = T::key(T::zero());
+#pragma unroll 1
+    for (int j = j0; j < j1; j++) {
+        const unsigned long long k0 = (alive & 1u) ? T::key(a[0][0]) : 0ull;
+        const unsigned long long k1 = (alive & 2u) ? T::key(a[1][0]) : 0ull;
+        const int krr = k1 > k0 ? 1 : 0;                     // first maximum wins (izamax): row 2 * lane before 2 * lane + 1
+        const unsigned long long key = krr ? k1 : k0;
+        unsigned bal;
+        bool nonzero;
+        if (!F64) {
+            const unsigned k32 = (unsigned)key;
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, k32);
+            bal = __ballot_sync(0xffffffffu, k32 == kmax);
+            nonzero = kmax > (unsigned)kzero;
+        } else {
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+            bal = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
+            nonzero = (((unsigned long long)hmax << 32) | lmax) > kzero;
+        }
+        const int src = __ffs(bal) - 1;
+        if (lane == src) {                                   // the lane of the pivot row publishes its live columns
+            s_win[j] = krr ? rows[1] : rows[0];
+            alive &= ~(1u << krr);
+#pragma unroll
+            for (int cb = 0; cb < WIDTH; cb += PER) {
+                C u[PER];
+#pragma unroll
+                for (int e = 0; e < PER; e++) u[e] = krr ? a[1][cb + e] : a[0][cb + e];
+                CH::st(&s_prow[cb], u);
+            }
+        }
+        __syncwarp();
+        if (flag_singular && !nonzero && lane == 0) *info = 1;              // exactly singular pivot (LAPACK info > 0)
+        // LAPACK zgetf2 scales the column by the reciprocal of the pivot
+        C l0, l1;
+        {
+            C u0[PER];
+            CH::ld(&s_prow[0], u0);
+            const C rinv = nonzero ? T::rcp(u0[0]) : T::zero();
+            l0 = T::mul(a[0][0], rinv);
+            l1 = T::mul(a[1][0], rinv);
+#pragma unroll
+            for (int e = 1; e < PER; e++) {
+                a[0][e - 1] = T::fnma(a[0][e], l0, u0[e]);
+                a[1][e - 1] = T::fnma(a[1][e], l1, u0[e]);
+            }
+        }
+#pragma unroll
+        for (int cb = PER; cb < WIDTH; cb += PER) {
+            C u[PER];
+            CH::ld(&s_prow[cb], u);
+#pragma unroll
+            for (int e = 0; e < PER; e++) {
+                a[0][cb + e - 1] = T::fnma(a[0][cb + e], l0, u[e]);
+                a[1][cb + e - 1] = T::fnma(a[1][cb + e], l1, u[e]);
+            }
+        }
+        a[0][WIDTH - 1] = T::zero();
+        a[1][WIDTH - 1] = T::zero();
+        __syncwarp();                                        // s_prow is rewritten in the next step
+    }
+}
+
+// GEPP of the (up to) 64 rows held by one warp; winners (global row numbers, pivot order) -> s_win[0 .. nsel).
+// s_prow / s_win are written by one lane and read by the others: never pass them as __restrict__ (the compiler then
+// keeps stale copies of the buffer in registers across __syncwarp).
+template <typename T, bool F64>
+__device__ __forceinline__ void tw_gepp(typename T::C (&a)[2][32], const int (&rows)[2], int nsel, typename T::C* s_prow,
+                                        int* s_win, int lane, bool flag_singular, int* info) {
+    unsigned alive = (rows[0] >= 0 ? 1u : 0u) | (rows[1] >= 0 ? 2u : 0u);
+    tw_steps<T, F64, 32>(a, rows, alive, 0, min(nsel, 16), s_prow, s_win, lane, flag_singular, info);
+    if (nsel > 16) tw_steps<T, F64, 16>(a, rows, alive, 16, nsel, s_prow, s_win, lane, flag_singular, info);
+}
+
+template <typename T, bool F64, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_tournw(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n_in, const int* __restrict__ cand_in,
+         int cand_in_stride, int* __restrict__ cand_out, int cand_out_stride, int final_round, cplx* __restrict__ LU,
+         int* __restrict__ moves, int* __restrict__ perm, int perm_stride, int* __restrict__ info, int mixr) {
+    typedef typename T::C C;
+    constexpr int w = GNB_NB;
+    const int b = blockIdx.y, g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ __align__(16) C s_prow[4][32];
+    __shared__ int s_list[2][4][32];
+    __shared__ int s_len[2][4];
+    __shared__ __align__(16) double s_gj[F64 ? 32 : 1];
+    const cplx* Ab = A + (long)b * strideA;
+    const int base = g * 256;
+    const int ncta = min(256, n_in - base);                  // candidate rows of this CTA
+    int rows[2];
+    C a[2][32];
+    int nlists = (ncta + 63) / 64, cur = 0;                  // lists of nominees alive after the current level
+    for (int level = 0;; level++) {                          // block-uniform loop: level 0 = 64 rows per warp, then merges
+        int nsel = 0, dst = cur;
+        bool flag = false;
+        if (level == 0) {
+            const int nw = max(0, min(64, ncta - 64 * warp));
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int i = 64 * warp + 2 * lane + rr;
+                rows[rr] = i < ncta ? (cand_in ? cand_in[(long)b * cand_in_stride + base + i] : r0 + base + i) : -1;
+            }
+            nsel = min(w, nw);
+            flag = final_round && nlists == 1;
+            if (lane == 0) s_len[cur][warp] = nsel;
+        } else {
+            const int nnext = (nlists + 1) / 2;
+            dst = cur ^ 1;
+            if (warp < nnext) {
+                const int la = 2 * warp, lb = 2 * warp + 1;
+                const int na = s_len[cur][la], nb_ = lb < nlists ? s_len[cur][lb] : 0;
+                if (nb_ == 0) {                              // an unpaired list goes up unchanged (already in pivot order)
+                    if (lane < na) s_list[dst][warp][lane] = s_list[cur][la][lane];
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++) {
+                        const int i = 2 * lane + rr;
+                        rows[rr] = i < na ? s_list[cur][la][i] : (i < na + nb_ ? s_list[cur][lb][i - na] : -1);
+                    }
+                    nsel = min(w, na + nb_);
+                    flag = final_round && nnext == 1;
+                }
+                if (lane == 0) s_len[dst][warp] = min(w, na + nb_);
+            }
+            cur = dst;
+            nlists = nnext;
+        }
+        if (nsel > 0) {                                      // warp-uniform
+            tw_load<T>(a, rows, Ab, ld, c0, mixr);
+            tw_gepp<T, F64>(a, rows, nsel, s_prow[warp], s_list[dst][warp], lane, flag, info);
+        }
+        if (nlists == 1) break;
+        __syncthreads();
+    }
+    __syncthreads();
+    const int nfin = s_len[cur][0];
+    const int* s_win = s_list[cur][0];
+    if (!final_round || !F64) {
+        if (t < nfin) cand_out[(long)b * cand_out_stride + g * w + t] = s_win[t];
+        return;
+    }
+    if (warp != 0) return;
+    // ---- final round, warp 0: explicit inverse of the pivot block (chosen rows, pivot order) by in-place Gauss-Jordan
+    // without further pivoting (the row order IS the partial-pivoting order); lane r holds row r.  Real panels only
+    // (the launcher keeps complex FP64 final rounds on k_tourn).
+    {
+        double m[32];
+        const int row = lane < nfin ? s_win[lane] : -1;
+        if (row >= 0) {
+            if (c0 < mixr) {
+                const double2* src = reinterpret_cast<const double2*>(gnb_real_view(Ab, mixr) + (long)row * 2 * ld + c0);
+#pragma unroll
+                for (int q = 0; q < 16; q++) { const double2 v = src[q]; m[2 * q] = v.x; m[2 * q + 1] = v.y; }
+            } else {
+                const cplx* src = Ab + (long)row * ld + c0;
+#pragma unroll
+                for (int k = 0; k < 32; k++) m[k] = src[k].x;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) m[k] = (k == lane) ? 1.0 : 0.0;
+        }
+        // the row is rotated left by one column per step WITH wrap-around (the finished inverse column goes to
+        // register column 31): the pivot column is always register column 0 and after 32 steps the columns are back
+        // in natural order
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) {
+            if (lane == k) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) *reinterpret_cast<double2*>(&s_gj[2 * q]) = make_double2(m[2 * q], m[2 * q + 1]);
+            }
+            __syncwarp();
+            const bool isp = lane == k;
+            const double f = m[0];
+            double rk;
+            {
+                const double2 pv = *reinterpret_cast<const double2*>(&s_gj[0]);
+                rk = pv.x != 0.0 ? 1.0 / pv.x : 0.0;
+                const double p1 = pv.y * rk;                           // scaled pivot row
+                m[0] = isp ? p1 : fma(-f, p1, m[1]);
+            }
+#pragma unroll
+            for (int q = 1; q < 16; q++) {
+                const double2 pv = *reinterpret_cast<const double2*>(&s_gj[2 * q]);
+                const double p0 = pv.x * rk, p1 = pv.y * rk;
+                m[2 * q - 1] = isp ? p0 : fma(-f, p0, m[2 * q]);
+                m[2 * q] = isp ? p1 : fma(-f, p1, m[2 * q + 1]);
+            }
+            m[31] = isp ? rk : -f * rk;
+            __syncwarp();
+        }
+        cplx* inv = LU + (long)b * GNB_NB * GNB_NB + (long)lane * GNB_NB;
+#pragma unroll
+        for (int k = 0; k < 32; k++) inv[k] = cmake(m[k], 0.0);
+    }
+    // ---- net row moves + permutation bookkeeping (same as k_tourn) ----------------------------------
+    {
+        const bool act = lane < w;
+        const int ch = act ? s_win[lane] : -1;                 // chosen global row, pivot order
+        const bool in_blk = act && ch < c0 + w;                // ch >= c0 always
+        const unsigned chosen_pos = __reduce_or_sync(0xffffffffu, in_blk ? (1u << (ch - c0)) : 0u);
+        const unsigned vacmask = __ballot_sync(0xffffffffu, act && !in_blk);
+        const unsigned dismask = 0xffffffffu & ~chosen_pos;    // block rows that were not chosen
+        int* mv = moves + (long)b * GNB_MOVES_STRIDE;
+        int d2 = -1, s2 = -1;
+        if (act) { mv[1 + 2 * lane] = c0 + lane; mv[2 + 2 * lane] = ch; }
+        if (act && !in_blk) {
+            const int rank = __popc(vacmask & ((1u << lane) - 1u));
+            const int p = __fns(dismask, 0, rank + 1);
+            d2 = ch; s2 = c0 + p;                              // displaced block row fills the vacated slot
+            mv[1 + 2 * (w + rank)] = d2;
+            mv[2 + 2 * (w + rank)] = s2;
+        }
+        if (lane == 0) mv[0] = w + __popc(vacmask);
+        if (perm) {
+            int* pb = perm + (long)b * perm_stride;
+            const int o1 = act ? pb[ch] : 0;
+            const int o2 = (s2 >= 0) ? pb[s2] : 0;
+            __syncwarp();
+            if (act) pb[c0 + lane] = o1;
+            __syncwarp();
+            if (d2 >= 0) pb[d2] = o2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Row moves of one step applied to a 64-column tile, fused with the product that turns the pivot row
 // block into  W = (L11 U11)^-1 A[k,:]  (explicit 32x32 inverse from the tournament's final round,
 // broadcast from smem; 8 independent accumulators per thread).
@@ -897,6 +1228,8 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
 static int g_tourn_fp32 = 1;      // nominating (non-final) tournament rounds in single precision
 void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
+static int g_tourn_warp = 1;      // warp-synchronous tournament kernel (k_tournw) where it applies
+void gnb_set_tourn_warp(int on) { g_tourn_warp = on; }
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
                            int* info, int real_panel, int mixr) {
@@ -904,27 +1237,47 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
     const int* cin = nullptr;
     int* cout = cand0;
     long launches = 0;
-    const int G = 128;
     for (;;) {
+        // k_tournw: 256 rows per CTA; every nominating round, and the FP64 final round of real panels
+        const bool f32 = g_tourn_fp32 != 0;
+        const bool warp_ok = g_tourn_warp && w == GNB_NB;
+        const int G = warp_ok ? 256 : 128;
         const int groups = cdiv_i(n, G);
         const int fin = groups == 1;
-        dim3 grid(groups, M);
+        // g_tourn_warp bits: 1 = nominating rounds of real panels, 2 = FP64 final round of real panels, 4 = FP32
+        // nominating rounds of complex panels.  Measured on the N = 1024 T(E) step (tools/sweep.py, profiles/r02_sweeps.txt):
+        // 1 -> +1.7 %; 2 -> -1.8 % (44 us against 51 us alone, but its 224 registers keep it from sharing an SM with the
+        // other sub-batch's rank-K CTAs); 4 -> -4 % (252 registers, 2 CTAs per SM).  Default: 1.
+        const bool use_w = warp_ok && (fin ? (real_panel && (g_tourn_warp & 2))
+                                           : (real_panel ? (g_tourn_warp & 1) != 0 : (f32 && (g_tourn_warp & 4))));
+        const int Gk = use_w ? 256 : 128;
+        const int grp = cdiv_i(n, Gk);
+        const int fink = grp == 1;
+        dim3 grid(grp, M);
 #define GNB_TOURN(T_, F64_, MINB_, FIN_)                                                                             \
     k_tourn<128, T_, F64_, MINB_><<<grid, 128, 0, st>>>(A, strideA, ld, c0, w, c0, n, cin, cand_stride, cout, cand_stride, \
                                                         FIN_, LU, moves, perm, perm_stride, info, mixr)
-        if (!fin && g_tourn_fp32) {
+#define GNB_TOURNW(T_, F64_, MINB_, FIN_)                                                                            \
+    k_tournw<T_, F64_, MINB_><<<grid, 128, 0, st>>>(A, strideA, ld, c0, c0, n, cin, cand_stride, cout, cand_stride, FIN_, LU, \
+                                                    moves, perm, perm_stride, info, mixr)
+        if (use_w) {
+            if (!fink && f32) { if (real_panel) GNB_TOURNW(TTR<float>, false, 4, 0); else GNB_TOURNW(TT<float>, false, 2, 0); }
+            else GNB_TOURNW(TTR<double>, true, 2, fink);      // real panels only (see use_w)
+        } else if (!fink && f32) {
             if (real_panel) GNB_TOURN(TTR<float>, false, 8, 0);
             else GNB_TOURN(TT<float>, false, 5, 0);
         } else {
-            if (real_panel) GNB_TOURN(TTR<double>, true, 5, fin);
-            else GNB_TOURN(TT<double>, true, 3, fin);
+            if (real_panel) GNB_TOURN(TTR<double>, true, 5, fink);
+            else GNB_TOURN(TT<double>, true, 3, fink);
         }
 #undef GNB_TOURN
+#undef GNB_TOURNW
         launches++;
-        if (fin) break;
-        n = (groups - 1) * w + min(w, n - (groups - 1) * G);
+        if (fink) break;
+        n = (grp - 1) * w + min(w, n - (grp - 1) * Gk);
         cin = cout;
         cout = (cout == cand0) ? cand1 : cand0;
+        (void)fin; (void)groups; (void)G;
     }
     return launches;
 }

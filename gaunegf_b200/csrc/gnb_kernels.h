@@ -42,6 +42,7 @@ void gnb_set_gemm_bm(int bm);
 void gnb_set_gemm_pipe(int on);
 void gnb_set_two_level(int on);
 void gnb_set_tourn_group(int g);
+void gnb_set_tourn_warp(int on);
 void gnb_launch_assemble(cudaStream_t st, int M, cplx* A, long strideA, int ld, int N, const cplx* F,
                          const cplx* S, const cplx* Sig0, const cplx* SigB, long strideSigB, const cplx* E,
                          const int* pi = nullptr, int mixr = 0);

@@ -738,29 +738,41 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve(cplx* __restrict__ A, long
 #define WM_AS 36
 #define WM_BS 34
 // mode 1: A and B real (one DMMA per tile product), 2: A real, B complex (two), 3: both complex (four)
-__device__ __forceinline__ void ws_mma_product(double (&cre)[2][2], double (&cim)[2][2], const cplx* __restrict__ sAm,
+// AT = double: the A operands (inv_a, L_ba, inv_b) are known to be real and staged as doubles (modes 1 and 2 only)
+template <typename AT>
+__device__ __forceinline__ void ws_mma_product(double (&cre)[2][2], double (&cim)[2][2], const AT* __restrict__ sAm,
                                                const cplx* __restrict__ sBk, int wm, int wn, int gid, int tig, bool neg,
                                                int mode) {
+    constexpr bool AR = sizeof(AT) == sizeof(double);
 #pragma unroll
     for (int kk = 0; kk < GNB_NB; kk += 4) {
-        cplx a[2];
+        double ax[2], ay[2];
 #pragma unroll
-        for (int mi = 0; mi < 2; mi++) a[mi] = sAm[(wm * 16 + mi * 8 + gid) * WM_AS + kk + tig];
+        for (int mi = 0; mi < 2; mi++) {
+            if (AR) {
+                ax[mi] = reinterpret_cast<const double*>(sAm)[(wm * 16 + mi * 8 + gid) * WM_AS + kk + tig];
+                ay[mi] = 0.0;
+            } else {
+                const cplx a = reinterpret_cast<const cplx*>(sAm)[(wm * 16 + mi * 8 + gid) * WM_AS + kk + tig];
+                ax[mi] = a.x; ay[mi] = a.y;
+            }
+            if (neg) { ax[mi] = -ax[mi]; ay[mi] = -ay[mi]; }
+        }
         const cplx bq = sBk[(kk + tig) * WM_BS + wn * 8 + gid];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
-            const double ax = neg ? -a[mi].x : a[mi].x, ay = neg ? -a[mi].y : a[mi].y;
-            dmma884(cre[mi][0], cre[mi][1], ax, bq.x);
-            if (mode >= 2) dmma884(cim[mi][0], cim[mi][1], ax, bq.y);
-            if (mode == 3) {
-                dmma884(cre[mi][0], cre[mi][1], -ay, bq.y);
-                dmma884(cim[mi][0], cim[mi][1], ay, bq.x);
+            dmma884(cre[mi][0], cre[mi][1], ax[mi], bq.x);
+            if (mode >= 2) dmma884(cim[mi][0], cim[mi][1], ax[mi], bq.y);
+            if (!AR && mode == 3) {
+                dmma884(cre[mi][0], cre[mi][1], -ay[mi], bq.y);
+                dmma884(cim[mi][0], cim[mi][1], ay[mi], bq.x);
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, long strideA, int ld, int c0, int nb,
+template <typename AT>
+__global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_rk_wsolve_mma(cplx* __restrict__ A, long strideA, int ld, int c0, int nb,
                                                           int jlo, int jhi, int tiles_per_cta,
                                                           const cplx* __restrict__ inv_a, const cplx* __restrict__ inv_b,
                                                           const cplx* __restrict__ Lsrc, long stridePk, int nrb,
@@ -768,20 +780,22 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
                                                           int mixr, const double* __restrict__ PpkR, long stridePkR,
                                                           double* __restrict__ WpkR, long strideWkR) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    cplx* sA = reinterpret_cast<cplx*>(smem_raw);            // [3][32][WM_AS]: inv_a, L_ba, inv_b
-    cplx* sB = sA + 3 * GNB_NB * WM_AS;                      // [64][WM_BS]: R_a / W_a rows, then R_b rows
+    constexpr bool AR = sizeof(AT) == sizeof(double);
+    AT* sA = reinterpret_cast<AT*>(smem_raw);                // [3][32][WM_AS]: inv_a, L_ba, inv_b (doubles when real)
+    cplx* sB = reinterpret_cast<cplx*>(sA + 3 * GNB_NB * WM_AS);   // [64][WM_BS]: R_a / W_a rows, then R_b rows
+    auto put_a = [&](int idx, cplx v) { if constexpr (AR) reinterpret_cast<double*>(sA)[idx] = v.x; else reinterpret_cast<cplx*>(sA)[idx] = v; };
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int gid = lane >> 2, tig = lane & 3, wm = warp >> 2, wn = warp & 3;
     cplx* Ab = A + (long)b * strideA;
     for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) {
         const int i = idx >> 5, j = idx & 31;
-        sA[i * WM_AS + j] = inv_a[(long)b * GNB_NB * GNB_NB + idx];
+        put_a(i * WM_AS + j, inv_a[(long)b * GNB_NB * GNB_NB + idx]);
         if (nb == 2) {
             const int cb = c0 + GNB_NB, k = c0 + j;
-            sA[(2 * GNB_NB + i) * WM_AS + j] = inv_b[(long)b * GNB_NB * GNB_NB + idx];
+            put_a((2 * GNB_NB + i) * WM_AS + j, inv_b[(long)b * GNB_NB * GNB_NB + idx]);
             const long loff = ((long)(k >> 4) * nrb + (cb >> 5)) * RK_PBLK + i * RK_PPS + (k & 15);
-            sA[(GNB_NB + i) * WM_AS + j] = (c0 + GNB_NB <= mixr) ? cmake(PpkR[(long)b * stridePkR + loff], 0.0)   // panel a is real-packed
-                                                                     : Lsrc[(long)b * stridePk + loff];
+            put_a((GNB_NB + i) * WM_AS + j, (c0 + GNB_NB <= mixr) ? cmake(PpkR[(long)b * stridePkR + loff], 0.0)   // panel a is real-packed
+                                                                  : Lsrc[(long)b * stridePk + loff]);
         }
     }
     const int nrows = nb * GNB_NB;
@@ -805,7 +819,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
         // ---- W_a = inv_a R_a
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
-        ws_mma_product(cre, cim, sA, sB, wm, wn, gid, tig, false, mode);
+        ws_mma_product<AT>(cre, cim, sA, sB, wm, wn, gid, tig, false, mode);
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
             const int k = c0 + wm * 16 + mi * 8 + gid;
@@ -831,7 +845,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
             }
             __syncthreads();
             // ---- R_b -= L_ba W_a
-            ws_mma_product(cre, cim, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, true, mode);
+            ws_mma_product<AT>(cre, cim, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, true, mode);
             // R_b of this warp's rows x columns is read only through B fragments of the next product
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
@@ -843,7 +857,7 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
             // ---- W_b = inv_b R_b
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) cre[mi][0] = cre[mi][1] = cim[mi][0] = cim[mi][1] = 0.0;
-            ws_mma_product(cre, cim, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WM_BS, wm, wn, gid, tig, false, mode);
+            ws_mma_product<AT>(cre, cim, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WM_BS, wm, wn, gid, tig, false, mode);
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
                 const int k = c0 + GNB_NB + wm * 16 + mi * 8 + gid;
@@ -857,6 +871,104 @@ __global__ void __launch_bounds__(256, 2) k_rk_wsolve_mma(cplx* __restrict__ A, 
                     wq[0] = v0; wq[1] = v1;
                 }
             }
+        }
+    }
+}
+
+// Fully real forward-W kernel: real pivot blocks (inv_a, L_ba, inv_b real) AND real columns (left of nreal).  Same
+// contract and warp layout as k_rk_wsolve_mma, every operand staged as doubles: 46 KB of shared memory and <= 64
+// registers, 4 CTAs per SM - the kernel is bound by the latency of its tile loads, so residency is what it needs.
+#define WR_BS 36
+__device__ __forceinline__ void ws_rr_product(double (&c)[2][2], const double* __restrict__ sAm, const double* __restrict__ sBk,
+                                              int wm, int wn, int gid, int tig, bool neg) {
+#pragma unroll
+    for (int kk = 0; kk < GNB_NB; kk += 4) {
+        const double bq = sBk[(kk + tig) * WR_BS + wn * 8 + gid];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const double ax = sAm[(wm * 16 + mi * 8 + gid) * WM_AS + kk + tig];
+            dmma884(c[mi][0], c[mi][1], neg ? -ax : ax, bq);
+        }
+    }
+}
+__global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, long strideA, int ld, int c0, int nb, int jlo,
+                                                         int jhi, int tiles_per_cta, const cplx* __restrict__ inv_a,
+                                                         const cplx* __restrict__ inv_b, const cplx* __restrict__ Lsrc,
+                                                         long stridePk, int nrb, cplx* __restrict__ Wpk, long strideWk, int ncb,
+                                                         int mixr, const double* __restrict__ PpkR, long stridePkR,
+                                                         double* __restrict__ WpkR, long strideWkR) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);        // [3][32][WM_AS]: inv_a, L_ba, inv_b
+    double* sB = sA + 3 * GNB_NB * WM_AS;                    // [64][WR_BS]: R_a / W_a rows, then R_b rows
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int gid = lane >> 2, tig = lane & 3, wm = warp >> 2, wn = warp & 3;
+    cplx* Ab = A + (long)b * strideA;
+    double* Abr = rk_real_view(Ab, mixr);
+    for (int idx = t; idx < GNB_NB * GNB_NB; idx += 256) {
+        const int i = idx >> 5, j = idx & 31;
+        sA[i * WM_AS + j] = inv_a[(long)b * GNB_NB * GNB_NB + idx].x;
+        if (nb == 2) {
+            const int cb = c0 + GNB_NB, k = c0 + j;
+            sA[(2 * GNB_NB + i) * WM_AS + j] = inv_b[(long)b * GNB_NB * GNB_NB + idx].x;
+            const long loff = ((long)(k >> 4) * nrb + (cb >> 5)) * RK_PBLK + i * RK_PPS + (k & 15);
+            sA[(GNB_NB + i) * WM_AS + j] = (c0 + GNB_NB <= mixr) ? PpkR[(long)b * stridePkR + loff] : Lsrc[(long)b * stridePk + loff].x;
+        }
+    }
+    const int nrows = nb * GNB_NB;
+    for (int tt = 0; tt < tiles_per_cta; tt++) {
+        const int cs = jlo + (blockIdx.x * tiles_per_cta + tt) * WM_TC;
+        if (cs >= jhi) break;                                 // block-uniform
+        __syncthreads();                                      // previous tile consumed; operands staged
+        const bool rstore = cs < mixr;                       // tile stored as real doubles (mixed layout)
+        for (int idx = t; idx < nrows * WM_TC; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            sB[i * WR_BS + cc] = rstore ? Abr[(long)(c0 + i) * 2 * ld + cs + cc] : Ab[(long)(c0 + i) * ld + cs + cc].x;
+        }
+        __syncthreads();
+        const int col = cs + wn * 8 + tig * 2;                // this thread's two adjacent output columns
+        cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
+        double* Wr = WpkR + (long)b * strideWkR + (long)(col >> 5) * RK_WRBLK + (col & 31);
+        auto emit = [&](int k, double v0, double v1) {        // row k of W: into A and into the packed W operand
+            if (rstore) {
+                *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0, v1);
+                *reinterpret_cast<double2*>(Wr + (long)(k >> 4) * ncb * RK_WRBLK + (k & 15) * RK_WRS) = make_double2(v0, v1);
+            } else {
+                Ab[(long)k * ld + col] = cmake(v0, 0.0); Ab[(long)k * ld + col + 1] = cmake(v1, 0.0);
+                cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
+                wq[0] = cmake(v0, 0.0); wq[1] = cmake(v1, 0.0);
+            }
+        };
+        double c[2][2];
+        // ---- W_a = inv_a R_a
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) c[mi][0] = c[mi][1] = 0.0;
+        ws_rr_product(c, sA, sB, wm, wn, gid, tig, false);
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) emit(c0 + wm * 16 + mi * 8 + gid, c[mi][0], c[mi][1]);
+        if (nb == 2) {
+            __syncthreads();                                  // every warp is done reading R_a
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm * 16 + mi * 8 + gid, cc = wn * 8 + tig * 2;
+                sB[r * WR_BS + cc] = c[mi][0];                // W_a replaces R_a
+                sB[r * WR_BS + cc + 1] = c[mi][1];
+                c[mi][0] = sB[(GNB_NB + r) * WR_BS + cc];     // accumulators <- R_b
+                c[mi][1] = sB[(GNB_NB + r) * WR_BS + cc + 1];
+            }
+            __syncthreads();
+            ws_rr_product(c, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, true);      // R_b -= L_ba W_a
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm * 16 + mi * 8 + gid, cc = wn * 8 + tig * 2;
+                sB[(GNB_NB + r) * WR_BS + cc] = c[mi][0];
+                sB[(GNB_NB + r) * WR_BS + cc + 1] = c[mi][1];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) c[mi][0] = c[mi][1] = 0.0;
+            ws_rr_product(c, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WR_BS, wm, wn, gid, tig, false);   // W_b = inv_b R_b
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) emit(c0 + GNB_NB + wm * 16 + mi * 8 + gid, c[mi][0], c[mi][1]);
         }
     }
 }
@@ -875,6 +987,9 @@ static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
 static const size_t kWmSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WM_BS) * sizeof(cplx);
+static const size_t kWmSmemR = (size_t)3 * GNB_NB * WM_AS * sizeof(double) + (size_t)2 * GNB_NB * WM_BS * sizeof(cplx);
+static const size_t kWrSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WR_BS) * sizeof(double);
+static int g_rk_wsolve_areal = 2; // real pivot blocks: A operands of the forward-W kernel staged as doubles (3 CTAs per SM)
 static int g_rk_wsolve_mma = 1;  // leaf forward-W products on the FP64 tensor pipe
 static int g_rk_fin_mma = 1;     // JORDAN pivot-column update A[:,K] = -P inv as a rank-32 strip update on the tensor pipe
 static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
@@ -890,7 +1005,9 @@ cudaError_t gnb_rec_init() {
                                   (int)rk_rp_smem<RB_, CB_, WR_>()))) return e;
     RK_RP_ATTR(2, 2, 1) RK_RP_ATTR(2, 2, 0) RK_RP_ATTR(4, 1, 1) RK_RP_ATTR(4, 1, 0)
     if ((e = cudaFuncSetAttribute(k_rk_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_rk_wsolve_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWmSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_wsolve_mma<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWmSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_wsolve_mma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWmSmemR))) return e;
+    if ((e = cudaFuncSetAttribute(k_rk_wsolve_rr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWrSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_rk_panel_fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmem))) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -905,6 +1022,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_strip")) g_rk_strip = value;
     else if (!strcmp(name, "rk_real")) g_rk_real = value;
     else if (!strcmp(name, "rk_wsolve_mma")) g_rk_wsolve_mma = value;
+    else if (!strcmp(name, "rk_wsolve_areal")) g_rk_wsolve_areal = value;
     else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
     else if (!strcmp(name, "rk_sms") && value > 0) g_rk_sms = value;      // CTAs of the persistent rank-K kernels
 }
@@ -1097,13 +1215,38 @@ struct Rec {
             }
             if (g_rk_wsolve_mma || mixr > 0) {             // the FMA kernel does not know the mixed layout
                 const int ntile = (jhi - jlo) / WM_TC;
-                const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix
-                const int per = cdiv_i(ntile, split);
-                dim3 grid(cdiv_i(ntile, per), M);
-                k_rk_wsolve_mma<<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jlo, jhi, per, inv(c0),
-                                                            nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
-                                                            ws.Wpk, ws.strideWk, ncb, g_rk_real ? ws.nreal : 0, mixr, ws.PpkR,
-                                                            ws.stridePkR, ws.WpkR, ws.strideWkR);
+                const int nr = g_rk_real ? ws.nreal : 0;
+                const bool areal = g_rk_wsolve_areal && c0 + w <= nr;      // real pivot blocks: inv_a, L_ba, inv_b are real
+                // areal = 2: the real columns [jlo, min(jhi, nreal)) go to the fully real kernel (4 CTAs per SM)
+                const int jreal = (areal && g_rk_wsolve_areal >= 2) ? std::max(jlo, std::min(jhi, nr / WM_TC * WM_TC)) : jlo;
+                if (jreal > jlo) {
+                    const int ntile = (jreal - jlo) / WM_TC;
+                    const int split = std::max(1, std::min(ntile, cdiv_i(8 * g_rk_sms, M)));
+                    const int per = cdiv_i(ntile, split);
+                    dim3 grid(cdiv_i(ntile, per), M);
+                    k_rk_wsolve_rr<<<grid, 256, kWrSmem, st>>>(A, strideA, ld, c0, nb, jlo, jreal, per, inv(c0),
+                                                               nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb, ws.Wpk,
+                                                               ws.strideWk, ncb, mixr, ws.PpkR, ws.stridePkR, ws.WpkR, ws.strideWkR);
+                    launches++;
+                }
+                if (jhi > jreal) {
+                    const int ntile = (jhi - jreal) / WM_TC;
+                    const int split = std::max(1, std::min(ntile, cdiv_i((areal ? 6 : 4) * g_rk_sms, M)));      // CTAs per matrix
+                    const int per = cdiv_i(ntile, split);
+                    dim3 grid(cdiv_i(ntile, per), M);
+                    if (areal)
+                        k_rk_wsolve_mma<double><<<grid, 256, kWmSmemR, st>>>(A, strideA, ld, c0, nb, jreal, jhi, per, inv(c0),
+                                                                             nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk,
+                                                                             nrb, ws.Wpk, ws.strideWk, ncb, nr, mixr, ws.PpkR,
+                                                                             ws.stridePkR, ws.WpkR, ws.strideWkR);
+                    else
+                        k_rk_wsolve_mma<cplx><<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jreal, jhi, per, inv(c0),
+                                                                          nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
+                                                                          ws.Wpk, ws.strideWk, ncb, nr, mixr, ws.PpkR,
+                                                                          ws.stridePkR, ws.WpkR, ws.strideWkR);
+                    launches++;
+                }
+                return;
             } else {
                 const int ntile = cdiv_i(jhi - jlo, WS_TC);
                 const int split = std::max(1, std::min(ntile, cdiv_i(4 * g_rk_sms, M)));      // CTAs per matrix

@@ -44,7 +44,7 @@ const char* gnb_last_error(const gnb_ctx* ctx);
 const char* gnb_version(void);
 /* cudaStream_t to launch on (e.g. torch.cuda.current_stream().cuda_stream); default: stream 0 */
 int gnb_set_stream(gnb_ctx* ctx, void* cuda_stream);
-/* upper bound for the per-call energy-chunk workspace in bytes (default 48 GiB) */
+/* upper bound for the per-call energy-chunk workspace in bytes (default: 60 % of the GPU's memory) */
 int gnb_set_workspace_limit(gnb_ctx* ctx, size_t bytes);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t gnb_launch_count(const gnb_ctx* ctx);
