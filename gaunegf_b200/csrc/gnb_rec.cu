@@ -300,7 +300,7 @@ template <int RB, int CB, int WR> constexpr size_t rk_rp_smem() {
 }
 
 template <int RB, int CB, int WR>
-__global__ void __launch_bounds__(288, WR ? 2 : 1) k_rk_gemm_rp(RkGemmRpArgs g, int nti, int ntj, int total) {
+__global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, int ntj, int total) {
     static_assert(RB * CB == 4, "8 consumer warps of 16 x 32");
     constexpr int NCW = 8, WN = CB, MI = 2, NI = 4, KC = 16;
     constexpr int TM = 32 * RB, TN = 32 * CB;
@@ -990,6 +990,7 @@ static const size_t kWmSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WM_BS) 
 static const size_t kWmSmemR = (size_t)3 * GNB_NB * WM_AS * sizeof(double) + (size_t)2 * GNB_NB * WM_BS * sizeof(cplx);
 static const size_t kWrSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WR_BS) * sizeof(double);
 static int g_rk_wsolve_areal = 2; // real pivot blocks: A operands of the forward-W kernel staged as doubles (3 CTAs per SM)
+static int g_rk_rp2 = 1;         // real-panel x complex-W rank-K kernel at 2 CTAs per SM
 static int g_rk_wsolve_mma = 1;  // leaf forward-W products on the FP64 tensor pipe
 static int g_rk_fin_mma = 1;     // JORDAN pivot-column update A[:,K] = -P inv as a rank-32 strip update on the tensor pipe
 static const size_t kWsSmem = (size_t)(2 * GNB_NB * WS_TC + 3 * GNB_NB * GNB_NB) * sizeof(cplx);
@@ -1023,6 +1024,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_real")) g_rk_real = value;
     else if (!strcmp(name, "rk_wsolve_mma")) g_rk_wsolve_mma = value;
     else if (!strcmp(name, "rk_wsolve_areal")) g_rk_wsolve_areal = value;
+    else if (!strcmp(name, "rk_rp2")) g_rk_rp2 = value;
     else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
     else if (!strcmp(name, "rk_sms") && value > 0) g_rk_sms = value;      // CTAs of the persistent rank-K kernels
 }
@@ -1104,7 +1106,7 @@ struct Rec {
             const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
             const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
             const long total = (long)M * nti * ntj;
-            const int grid = (int)std::min<long>(total, (long)g_rk_sms * (wr ? 2 : 1));
+            const int grid = (int)std::min<long>(total, (long)g_rk_sms * ((wr || g_rk_rp2) ? 2 : 1));
             const double flops = (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M * (wr ? 2.0 : 4.0);
             TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
             if (ws.timer) ws.timer->begin(st);
