@@ -46,12 +46,14 @@ SIGNATURES = {
     "gnb_transmission": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "gnb_dos": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "gnb_gr_int": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "gnb_gr_int_seg": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
     "gnb_gless_int": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int]),
     "gnb_green_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_int]),
     "gnb_transmission_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
     "gnb_transmission_spin": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_long, _vp]),
     "gnb_dos_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_long, _vp, _vp]),
     "gnb_gr_int_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp, C.c_int]),
+    "gnb_gr_int_seg_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_int]),
     "gnb_gless_int_dense": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_long, _vp, C.c_long, _vp, C.c_int]),
     "gnb_inverse_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int]),
 }
@@ -283,6 +285,24 @@ class Context:
             return None
         out = np.empty((self.N, self.N), dtype=np.complex128)
         self.check(self.lib.gnb_gr_int(self.h, E.size, ptr(E), ptr(w), ptr(out), HOST))
+        return out
+
+    def gr_int_seg(self, E, w, seg_end, sig=None, out_device_ptr=None):
+        """len(seg_end) weighted sums over consecutive energy ranges in one batch -> (nseg, N, N); sig: dense Sigma_tot
+        (one matrix or one per energy) instead of the described contacts."""
+        E, w = c128(np.atleast_1d(E)), c128(np.atleast_1d(w))
+        assert E.size == w.size, "Elist and weights must have the same length"
+        ends = np.ascontiguousarray(seg_end, dtype=np.int32)
+        if sig is None:
+            call = lambda o, loc: self.lib.gnb_gr_int_seg(self.h, E.size, ptr(E), ptr(w), ends.size, ptr(ends), o, loc)
+        else:
+            s, ss = self._dense(sig, E.size)
+            call = lambda o, loc: self.lib.gnb_gr_int_seg_dense(self.h, E.size, ptr(E), ptr(w), ends.size, ptr(ends), ptr(s), ss, o, loc)
+        if out_device_ptr is not None:
+            self.check(call(_vp(out_device_ptr), DEVICE))
+            return None
+        out = np.empty((ends.size, self.N, self.N), dtype=np.complex128)
+        self.check(call(ptr(out), HOST))
         return out
 
     def gless_int(self, E, w, contact=-1, out_device_ptr=None):

@@ -28,6 +28,12 @@ static int g_chain_joint = 1;     // chain contacts with equal block size / iter
 static int g_small = 1;           // N <= gnb_small_max_n(): one CTA per energy, matrix on chip (gnb_small.cu)
 int gnb_small_enabled() { return g_small; }
 static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
+static int g_rec_stagger_us = 0;  // sub-batch s starts s * this many microseconds late (phase offset between the streams)
+__global__ void k_stagger(long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { __nanosleep(1000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while ((long)(t - t0) < ns);
+}
 
 extern "C" const char* gnb_version(void) { return "gaunegf_b200 0.1 (sm_100a)"; }
 
@@ -141,6 +147,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "gemm_bm")) gnb_set_gemm_bm(value);
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
+    else if (!strcmp(name, "rec_stagger_us")) g_rec_stagger_us = value;
     else if (!strcmp(name, "small_fused")) g_small = value;
     else if (!strcmp(name, "chain_joint")) g_chain_joint = value;
     else if (!strcmp(name, "chain_compact")) gnb_chain_set_compact(value);
@@ -501,7 +508,11 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
         } else {
             for (int s = 0; s < S; s++)
                 if (!c->sub[s]) {
-                    GNB_CK(cudaStreamCreateWithFlags(&c->sub[s], cudaStreamNonBlocking));
+                    // highest stream priority: with rk_lowprio the rank-K launches opt down to the lowest, so the panel
+                    // kernels of one sub-batch are dispatched ahead of the other sub-batch's rank-K CTAs
+                    int prio_lo = 0, prio_hi = 0;
+                    GNB_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                    GNB_CK(cudaStreamCreateWithPriority(&c->sub[s], cudaStreamNonBlocking, prio_hi));
                     GNB_CK(cudaEventCreateWithFlags(&c->sub_ev[s], cudaEventDisableTiming));
                 }
             if (!c->fork_ev) GNB_CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
@@ -517,6 +528,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
                 ws.PpkR = w.PpkR ? w.PpkR + (long)m0 * w.stridePkR : nullptr;
                 ws.WpkR = w.WpkR ? w.WpkR + (long)m0 * w.strideWkR : nullptr;
                 GNB_CK(cudaStreamWaitEvent(c->sub[s], c->fork_ev, 0));
+                if (g_rec_stagger_us > 0 && s > 0) k_stagger<<<1, 1, 0, c->sub[s]>>>((long)s * g_rec_stagger_us * 1000L);
                 c->launches += gnb_eliminate_rec(c->sub[s], m1 - m0, L.Np, L.naugp, A + (long)m0 * strideA, strideA, L.ld,
                                                  jordan, ws);
                 GNB_CK(cudaEventRecord(c->sub_ev[s], c->sub[s]));
@@ -676,9 +688,9 @@ static int stage_dense(gnb_ctx* c, DevBuf& buf, const DenseSrc& s, int k0, int m
     return rc;
 }
 
-static int get_out(gnb_ctx* c, double* out, int loc, cplx** d_out) {
+static int get_out(gnb_ctx* c, double* out, int loc, cplx** d_out, int nmat = 1) {
     if (loc == GNB_DEVICE) { *d_out = reinterpret_cast<cplx*>(out); return GNB_OK; }
-    GNB_CK(c->out.ensure((size_t)c->N * c->N * sizeof(cplx)));
+    GNB_CK(c->out.ensure((size_t)nmat * c->N * c->N * sizeof(cplx)));
     *d_out = c->out.as<cplx>();
     return GNB_OK;
 }
@@ -744,9 +756,14 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     if (small) per = (size_t)(2 + (sig.p && sig.stride) + 2 * (g1.p && g1.stride) + 2 + (xform ? 4 : 0)) * nn * 16 + (size_t)N * 16 + 64;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     cplx* d_out = nullptr;
+    // segmented GrInt (gnb_gr_int_seg): nseg weighted sums over consecutive energy ranges, [nseg][N][N]
+    const int nseg = (mode == MODE_GRINT && c->seg_end) ? c->seg_n : 1;
+    const int* seg_end = (mode == MODE_GRINT) ? c->seg_end : nullptr;
     if (mode == MODE_GRINT || mode == MODE_GLESS_DENSE) {
-        if ((rc = get_out(c, out0, loc, &d_out))) return rc;
-        if (M == 0) GNB_CK(cudaMemsetAsync(d_out, 0, nn * sizeof(cplx), c->stream));
+        if ((rc = get_out(c, out0, loc, &d_out, nseg))) return rc;
+        if (M == 0) GNB_CK(cudaMemsetAsync(d_out, 0, (size_t)nseg * nn * sizeof(cplx), c->stream));
+        for (int sgi = 0, lo = 0; seg_end && sgi < nseg; lo = seg_end[sgi++])       // empty segments: zero
+            if (seg_end[sgi] <= lo) GNB_CK(cudaMemsetAsync(d_out + (size_t)sgi * nn, 0, nn * sizeof(cplx), c->stream));
     }
     for (int k0 = 0; k0 < M; k0 += Mc) {
         const int m = std::min(Mc, M - k0);
@@ -818,8 +835,18 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
                 GNB_CK(cudaMemcpyAsync(out1 + (size_t)k0 * N, c->dDosP.p, (size_t)m * N * sizeof(double),
                                        cudaMemcpyDeviceToHost, c->stream));
         } else if (mode == MODE_GRINT) {
-            gnb_launch_weighted_sum(c->stream, m, N, A, strideA, lda, inv, pst, c->dW.as<cplx>(), d_out, k0 > 0);
-            c->launches++;
+            if (!seg_end) {
+                gnb_launch_weighted_sum(c->stream, m, N, A, strideA, lda, inv, pst, c->dW.as<cplx>(), d_out, k0 > 0);
+                c->launches++;
+            } else {
+                for (int sgi = 0, lo = 0; sgi < nseg; lo = seg_end[sgi++]) {          // part of segment sgi in this chunk
+                    const int a = std::max(lo, k0) - k0, b = std::min(seg_end[sgi], k0 + m) - k0;
+                    if (b <= a) continue;
+                    gnb_launch_weighted_sum(c->stream, b - a, N, A + (long)a * strideA, strideA, lda, inv ? inv + (long)a * pst : nullptr,
+                                            pst, c->dW.as<cplx>() + a, d_out + (size_t)sgi * nn, lo < k0);
+                    c->launches++;
+                }
+            }
         } else if (mode == MODE_T_DENSE) {
             const cplx *g1c = nullptr, *g1b = nullptr, *g2c = nullptr, *g2b = nullptr;
             if (xform) {
@@ -910,7 +937,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         if (k0 + Mc < M) GNB_CK(cudaStreamSynchronize(c->stream));   // staging buffers are reused per chunk
     }
     if ((mode == MODE_GRINT || mode == MODE_GLESS_DENSE) && loc == GNB_HOST)
-        if ((rc = result_to_host(c, out0, d_out, nn * sizeof(cplx)))) return rc;
+        if ((rc = result_to_host(c, out0, d_out, (size_t)nseg * nn * sizeof(cplx)))) return rc;
     return end_call(c);
 }
 
@@ -923,6 +950,29 @@ extern "C" int gnb_dos(gnb_ctx* c, int M, const double* E, double* tot, double* 
 extern "C" int gnb_gr_int(gnb_ctx* c, int M, const double* E, const double* w, double* out, int loc) {
     if (M > 0 && !w) return gnb_fail(c, GNB_ERR_ARG, "weights required");
     return run_jordan(c, MODE_GRINT, M, E, w, true, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, out, nullptr, loc);
+}
+// nseg weighted sums in ONE batch: out[s] = sum_{seg_end[s-1] <= k < seg_end[s]} w[k] G(E[k]).  The nested levels of the
+// adaptive quadratures (density.py:234-270) are known a priori, so several levels go to the GPU as one launch chain.
+static int gr_int_seg(gnb_ctx* c, int M, const double* E, const double* w, int nseg, const int32_t* seg_end, bool use_desc,
+                      DenseSrc sig, double* out, int loc) {
+    if (!c) return GNB_ERR_ARG;
+    if (nseg < 1 || !seg_end || (M > 0 && !w)) return gnb_fail(c, GNB_ERR_ARG, "segments and weights required");
+    for (int i = 0; i < nseg; i++)
+        if (seg_end[i] < (i ? seg_end[i - 1] : 0) || seg_end[i] > M) return gnb_fail(c, GNB_ERR_ARG, "segment ends must be non-decreasing and <= M");
+    if (seg_end[nseg - 1] != M) return gnb_fail(c, GNB_ERR_ARG, "last segment must end at M");
+    std::vector<int> ends(seg_end, seg_end + nseg);
+    c->seg_n = nseg; c->seg_end = ends.data();
+    const int rc = run_jordan(c, MODE_GRINT, M, E, w, use_desc, sig, {nullptr, 0}, {nullptr, 0}, out, nullptr, loc);
+    c->seg_n = 0; c->seg_end = nullptr;
+    return rc;
+}
+extern "C" int gnb_gr_int_seg(gnb_ctx* c, int M, const double* E, const double* w, int nseg, const int32_t* seg_end,
+                              double* out, int loc) {
+    return gr_int_seg(c, M, E, w, nseg, seg_end, true, {nullptr, 0}, out, loc);
+}
+extern "C" int gnb_gr_int_seg_dense(gnb_ctx* c, int M, const double* E, const double* w, int nseg, const int32_t* seg_end,
+                                    const double* sig, long ss, double* out, int loc) {
+    return gr_int_seg(c, M, E, w, nseg, seg_end, false, {sig, ss}, out, loc);
 }
 extern "C" int gnb_green_dense(gnb_ctx* c, int M, const double* E, const double* sig, long ss, double* G, int loc) {
     return run_jordan(c, MODE_GREEN, M, E, nullptr, false, {sig, ss}, {nullptr, 0}, {nullptr, 0}, G, nullptr, loc);

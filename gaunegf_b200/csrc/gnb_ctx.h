@@ -101,6 +101,8 @@ struct gnb_ctx {
     // memcpy after the synchronisation in end_call, instead of the driver's chunked pageable staging
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     void* pend_dst = nullptr; size_t pend_bytes = 0;
+    // segmented GrInt (gnb_gr_int_seg): host array of cumulative segment ends, valid during the call only
+    int seg_n = 0; const int* seg_end = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double elim_ms = 0.0;
     double elim_flops = 0.0;        // executed FP64 flops of the elimination launches of the last compute call

@@ -575,6 +575,94 @@ __device__ __forceinline__ void tw_gepp(typename T::C (&a)[2][32], const int (&r
     if (nsel > 16) tw_steps<T, F64, 16>(a, rows, alive, 16, nsel, s_prow, s_win, lane, flag_singular, info);
 }
 
+// Final round of a real panel, ONE warp: explicit inverse of the pivot block (chosen rows s_win[0 .. nfin), pivot order) by
+// in-place Gauss-Jordan without further pivoting, then the net row moves and the permutation update (as in k_tourn).
+__device__ __forceinline__ void tw_finish_real(const cplx* __restrict__ Ab, int ld, int c0, int mixr, const int* s_win, int nfin,
+                                               double* s_gj, cplx* __restrict__ LUb, int* __restrict__ mvb, int* pb, int lane) {
+    constexpr int w = GNB_NB;
+    // ---- final round, warp 0: explicit inverse of the pivot block (chosen rows, pivot order) by in-place Gauss-Jordan
+    // without further pivoting (the row order IS the partial-pivoting order); lane r holds row r.  Real panels only
+    // (the launcher keeps complex FP64 final rounds on k_tourn).
+    {
+        double m[32];
+        const int row = lane < nfin ? s_win[lane] : -1;
+        if (row >= 0) {
+            if (c0 < mixr) {
+                const double2* src = reinterpret_cast<const double2*>(gnb_real_view(Ab, mixr) + (long)row * 2 * ld + c0);
+#pragma unroll
+                for (int q = 0; q < 16; q++) { const double2 v = src[q]; m[2 * q] = v.x; m[2 * q + 1] = v.y; }
+            } else {
+                const cplx* src = Ab + (long)row * ld + c0;
+#pragma unroll
+                for (int k = 0; k < 32; k++) m[k] = src[k].x;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) m[k] = (k == lane) ? 1.0 : 0.0;
+        }
+        // the row is rotated left by one column per step WITH wrap-around (the finished inverse column goes to
+        // register column 31): the pivot column is always register column 0 and after 32 steps the columns are back
+        // in natural order
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) {
+            if (lane == k) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) *reinterpret_cast<double2*>(&s_gj[2 * q]) = make_double2(m[2 * q], m[2 * q + 1]);
+            }
+            __syncwarp();
+            const bool isp = lane == k;
+            const double f = m[0];
+            double rk;
+            {
+                const double2 pv = *reinterpret_cast<const double2*>(&s_gj[0]);
+                rk = pv.x != 0.0 ? 1.0 / pv.x : 0.0;
+                const double p1 = pv.y * rk;                           // scaled pivot row
+                m[0] = isp ? p1 : fma(-f, p1, m[1]);
+            }
+#pragma unroll
+            for (int q = 1; q < 16; q++) {
+                const double2 pv = *reinterpret_cast<const double2*>(&s_gj[2 * q]);
+                const double p0 = pv.x * rk, p1 = pv.y * rk;
+                m[2 * q - 1] = isp ? p0 : fma(-f, p0, m[2 * q]);
+                m[2 * q] = isp ? p1 : fma(-f, p1, m[2 * q + 1]);
+            }
+            m[31] = isp ? rk : -f * rk;
+            __syncwarp();
+        }
+        cplx* inv = LUb + (long)lane * GNB_NB;
+#pragma unroll
+        for (int k = 0; k < 32; k++) inv[k] = cmake(m[k], 0.0);
+    }
+    // ---- net row moves + permutation bookkeeping (same as k_tourn) ----------------------------------
+    {
+        const bool act = lane < w;
+        const int ch = act ? s_win[lane] : -1;                 // chosen global row, pivot order
+        const bool in_blk = act && ch < c0 + w;                // ch >= c0 always
+        const unsigned chosen_pos = __reduce_or_sync(0xffffffffu, in_blk ? (1u << (ch - c0)) : 0u);
+        const unsigned vacmask = __ballot_sync(0xffffffffu, act && !in_blk);
+        const unsigned dismask = 0xffffffffu & ~chosen_pos;    // block rows that were not chosen
+        int* mv = mvb;
+        int d2 = -1, s2 = -1;
+        if (act) { mv[1 + 2 * lane] = c0 + lane; mv[2 + 2 * lane] = ch; }
+        if (act && !in_blk) {
+            const int rank = __popc(vacmask & ((1u << lane) - 1u));
+            const int p = __fns(dismask, 0, rank + 1);
+            d2 = ch; s2 = c0 + p;                              // displaced block row fills the vacated slot
+            mv[1 + 2 * (w + rank)] = d2;
+            mv[2 + 2 * (w + rank)] = s2;
+        }
+        if (lane == 0) mv[0] = w + __popc(vacmask);
+        if (pb) {
+            const int o1 = act ? pb[ch] : 0;
+            const int o2 = (s2 >= 0) ? pb[s2] : 0;
+            __syncwarp();
+            if (act) pb[c0 + lane] = o1;
+            __syncwarp();
+            if (d2 >= 0) pb[d2] = o2;
+        }
+    }
+}
+
 template <typename T, bool F64, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_tournw(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n_in, const int* __restrict__ cand_in,
@@ -643,87 +731,99 @@ k_tournw(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
         return;
     }
     if (warp != 0) return;
-    // ---- final round, warp 0: explicit inverse of the pivot block (chosen rows, pivot order) by in-place Gauss-Jordan
-    // without further pivoting (the row order IS the partial-pivoting order); lane r holds row r.  Real panels only
-    // (the launcher keeps complex FP64 final rounds on k_tourn).
-    {
-        double m[32];
-        const int row = lane < nfin ? s_win[lane] : -1;
-        if (row >= 0) {
-            if (c0 < mixr) {
-                const double2* src = reinterpret_cast<const double2*>(gnb_real_view(Ab, mixr) + (long)row * 2 * ld + c0);
+    tw_finish_real(Ab, ld, c0, mixr, s_win, nfin, s_gj, LU + (long)b * GNB_NB * GNB_NB, moves + (long)b * GNB_MOVES_STRIDE,
+                   perm ? perm + (long)b * perm_stride : nullptr, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-INDEPENDENT tournament round for real panels (block width 32).  One WARP = one group of up to 256 candidate
+// rows: it runs the level-0 eliminations of its (up to four) 64-row lists one after the other, then the merges, with
+// no CTA barrier anywhere.  k_tournw gives a 256-row group to a 4-warp CTA, but after level 0 two, then three of the
+// four warps only wait at the barrier while they hold their registers (ncu, N = 1024 step: barrier = 37 % of the
+// stall samples, 39 % issue utilisation, 23 % of the warp slots busy with 128 registers per thread); here every
+// resident warp always has a pivot step to run, so an SM works on 16-20 groups at a time instead of on 4.
+// The final round (F64) is one warp per matrix: eliminations, merges, the in-place Gauss-Jordan inverse of the pivot
+// block and the bookkeeping stay in that warp (17 k warp instructions per matrix against 52 k of the CTA-wide k_tourn,
+// whose shared-memory Gauss-Jordan runs complex arithmetic on real data).
+// ------------------------------------------------------------------------------------------
+template <typename T, bool F64, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n_in, int grp, int total_groups,
+         const int* __restrict__ cand_in, int cand_in_stride, int* __restrict__ cand_out, int cand_out_stride,
+         int final_round, cplx* __restrict__ LU, int* __restrict__ moves, int* __restrict__ perm, int perm_stride,
+         int* __restrict__ info, int mixr) {
+    typedef typename T::C C;
+    static_assert(sizeof(C) <= 8, "real panels only");
+    constexpr int w = GNB_NB;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ __align__(16) C s_prow_all[NW][32];
+    __shared__ int s_list_all[NW][2][4][32];
+    __shared__ __align__(16) double s_gj_all[F64 ? NW : 1][32];
+    const int gid = blockIdx.x * NW + warp;
+    if (gid >= total_groups) return;                         // warp-uniform; no CTA barrier below
+    const int b = gid / grp, g = gid - b * grp;
+    C* s_prow = s_prow_all[warp];
+    int (*s_list)[4][32] = s_list_all[warp];
+    const cplx* Ab = A + (long)b * strideA;
+    const int base = g * 256;
+    const int ncand = min(256, n_in - base);                 // candidate rows of this warp
+    int rows[2];
+    C a[2][32];
+    int nl = (ncand + 63) / 64, cur = 0, level = 0, q = 0;
+    unsigned lens = 0;                                       // 8 bits per list: nominees in list q of the current level
+    unsigned lens_next = 0;
+    for (;;) {                                               // warp-uniform loop over (level, q): ONE inlined elimination
+        int nsel = 0, dst = level == 0 ? 0 : (cur ^ 1);
+        bool flag = false;
+        const int nn = (nl + 1) / 2;
+        if (level == 0) {
+            const int nwr = min(64, ncand - 64 * q);
 #pragma unroll
-                for (int q = 0; q < 16; q++) { const double2 v = src[q]; m[2 * q] = v.x; m[2 * q + 1] = v.y; }
-            } else {
-                const cplx* src = Ab + (long)row * ld + c0;
-#pragma unroll
-                for (int k = 0; k < 32; k++) m[k] = src[k].x;
+            for (int rr = 0; rr < 2; rr++) {
+                const int i = 64 * q + 2 * lane + rr;
+                rows[rr] = i < ncand ? (cand_in ? cand_in[(long)b * cand_in_stride + base + i] : r0 + base + i) : -1;
             }
+            nsel = min(w, nwr);
+            flag = final_round && nl == 1;
+            lens_next |= (unsigned)nsel << (8 * q);
         } else {
+            const int la = 2 * q, lb = 2 * q + 1;
+            const int na = (lens >> (8 * la)) & 255, nb_ = lb < nl ? (lens >> (8 * lb)) & 255 : 0;
+            if (nb_ == 0) {                                  // an unpaired list goes up unchanged (already in pivot order)
+                if (lane < na) s_list[dst][q][lane] = s_list[cur][la][lane];
+            } else {
 #pragma unroll
-            for (int k = 0; k < 32; k++) m[k] = (k == lane) ? 1.0 : 0.0;
+                for (int rr = 0; rr < 2; rr++) {
+                    const int i = 2 * lane + rr;
+                    rows[rr] = i < na ? s_list[cur][la][i] : (i < na + nb_ ? s_list[cur][lb][i - na] : -1);
+                }
+                nsel = min(w, na + nb_);
+                flag = final_round && nn == 1;
+            }
+            lens_next |= (unsigned)min(w, na + nb_) << (8 * q);
         }
-        // the row is rotated left by one column per step WITH wrap-around (the finished inverse column goes to
-        // register column 31): the pivot column is always register column 0 and after 32 steps the columns are back
-        // in natural order
-#pragma unroll 1
-        for (int k = 0; k < 32; k++) {
-            if (lane == k) {
-#pragma unroll
-                for (int q = 0; q < 16; q++) *reinterpret_cast<double2*>(&s_gj[2 * q]) = make_double2(m[2 * q], m[2 * q + 1]);
-            }
-            __syncwarp();
-            const bool isp = lane == k;
-            const double f = m[0];
-            double rk;
-            {
-                const double2 pv = *reinterpret_cast<const double2*>(&s_gj[0]);
-                rk = pv.x != 0.0 ? 1.0 / pv.x : 0.0;
-                const double p1 = pv.y * rk;                           // scaled pivot row
-                m[0] = isp ? p1 : fma(-f, p1, m[1]);
-            }
-#pragma unroll
-            for (int q = 1; q < 16; q++) {
-                const double2 pv = *reinterpret_cast<const double2*>(&s_gj[2 * q]);
-                const double p0 = pv.x * rk, p1 = pv.y * rk;
-                m[2 * q - 1] = isp ? p0 : fma(-f, p0, m[2 * q]);
-                m[2 * q] = isp ? p1 : fma(-f, p1, m[2 * q + 1]);
-            }
-            m[31] = isp ? rk : -f * rk;
-            __syncwarp();
+        if (nsel > 0) {
+            tw_load<T>(a, rows, Ab, ld, c0, mixr);
+            tw_gepp<T, F64>(a, rows, nsel, s_prow, s_list[dst][q], lane, flag, info);
         }
-        cplx* inv = LU + (long)b * GNB_NB * GNB_NB + (long)lane * GNB_NB;
-#pragma unroll
-        for (int k = 0; k < 32; k++) inv[k] = cmake(m[k], 0.0);
+        __syncwarp();
+        q++;
+        if (q == (level == 0 ? nl : nn)) {                   // level finished
+            if (level > 0) { cur ^= 1; nl = nn; }
+            lens = lens_next; lens_next = 0;
+            level++; q = 0;
+            if (nl == 1) break;
+        }
     }
-    // ---- net row moves + permutation bookkeeping (same as k_tourn) ----------------------------------
-    {
-        const bool act = lane < w;
-        const int ch = act ? s_win[lane] : -1;                 // chosen global row, pivot order
-        const bool in_blk = act && ch < c0 + w;                // ch >= c0 always
-        const unsigned chosen_pos = __reduce_or_sync(0xffffffffu, in_blk ? (1u << (ch - c0)) : 0u);
-        const unsigned vacmask = __ballot_sync(0xffffffffu, act && !in_blk);
-        const unsigned dismask = 0xffffffffu & ~chosen_pos;    // block rows that were not chosen
-        int* mv = moves + (long)b * GNB_MOVES_STRIDE;
-        int d2 = -1, s2 = -1;
-        if (act) { mv[1 + 2 * lane] = c0 + lane; mv[2 + 2 * lane] = ch; }
-        if (act && !in_blk) {
-            const int rank = __popc(vacmask & ((1u << lane) - 1u));
-            const int p = __fns(dismask, 0, rank + 1);
-            d2 = ch; s2 = c0 + p;                              // displaced block row fills the vacated slot
-            mv[1 + 2 * (w + rank)] = d2;
-            mv[2 + 2 * (w + rank)] = s2;
-        }
-        if (lane == 0) mv[0] = w + __popc(vacmask);
-        if (perm) {
-            int* pb = perm + (long)b * perm_stride;
-            const int o1 = act ? pb[ch] : 0;
-            const int o2 = (s2 >= 0) ? pb[s2] : 0;
-            __syncwarp();
-            if (act) pb[c0 + lane] = o1;
-            __syncwarp();
-            if (d2 >= 0) pb[d2] = o2;
-        }
+    const int nfin = lens & 255;
+    const int* s_win = s_list[cur][0];
+    if (!final_round || !F64) {
+        if (lane < nfin) cand_out[(long)b * cand_out_stride + g * w + lane] = s_win[lane];
+        return;
+    }
+    if constexpr (F64) {
+        tw_finish_real(Ab, ld, c0, mixr, s_win, nfin, s_gj_all[warp], LU + (long)b * GNB_NB * GNB_NB,
+                       moves + (long)b * GNB_MOVES_STRIDE, perm ? perm + (long)b * perm_stride : nullptr, lane);
     }
 }
 
@@ -1228,7 +1328,7 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
 static int g_tourn_fp32 = 1;      // nominating (non-final) tournament rounds in single precision
 void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
-static int g_tourn_warp = 1;      // warp-synchronous tournament kernel (k_tournw) where it applies
+static int g_tourn_warp = 9;      // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
 void gnb_set_tourn_warp(int on) { g_tourn_warp = on; }
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
@@ -1247,9 +1347,34 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         // g_tourn_warp bits: 1 = nominating rounds of real panels, 2 = FP64 final round of real panels, 4 = FP32
         // nominating rounds of complex panels.  Measured on the N = 1024 T(E) step (tools/sweep.py, profiles/r02_sweeps.txt):
         // 1 -> +1.7 %; 2 -> -1.8 % (44 us against 51 us alone, but its 224 registers keep it from sharing an SM with the
-        // other sub-batch's rank-K CTAs); 4 -> -4 % (252 registers, 2 CTAs per SM).  Default: 1.
+        // other sub-batch's rank-K CTAs); 4 -> -4 % (252 registers, 2 CTAs per SM); 8 = warp-independent k_tournq for every
+        // round of a real panel (takes precedence over 1 and 2).  Default: 9.
         const bool use_w = warp_ok && (fin ? (real_panel && (g_tourn_warp & 2))
                                            : (real_panel ? (g_tourn_warp & 1) != 0 : (f32 && (g_tourn_warp & 4))));
+        if (warp_ok && real_panel && (g_tourn_warp & 8)) {    // warp-independent kernel: one warp per 256-row group / matrix
+            const int grp = cdiv_i(n, 256);
+            const int total = M * grp;
+            if (grp > 1) {
+                if (f32 && (g_tourn_warp & 16))
+                    k_tournq<TTR<float>, false, 4, 3><<<cdiv_i(total, 4), 128, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                        cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
+                else if (f32)
+                    k_tournq<TTR<float>, false, 4, 4><<<cdiv_i(total, 4), 128, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                        cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
+                else
+                    k_tournq<TTR<double>, true, 2, 4><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                       cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
+            } else {
+                k_tournq<TTR<double>, true, 2, 4><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                   cout, cand_stride, 1, LU, moves, perm, perm_stride, info, mixr);
+            }
+            launches++;
+            if (grp == 1) break;
+            n = (grp - 1) * w + min(w, n - (grp - 1) * 256);
+            cin = cout;
+            cout = (cout == cand0) ? cand1 : cand0;
+            continue;
+        }
         const int Gk = use_w ? 256 : 128;
         const int grp = cdiv_i(n, Gk);
         const int fink = grp == 1;

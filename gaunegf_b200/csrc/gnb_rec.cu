@@ -86,7 +86,7 @@ template <int RB, int CB> constexpr size_t rk_smem() {
 
 // CTA tile = (32 RB) x (32 CB), RB * CB = 4: 64 x 64 for the general case, 128 x 32 for 32-column strips.
 template <int M3, int RB, int CB>
-__global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int ntj, int total) {
+__global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int ntj, int total, int g0, int tcap) {
     static_assert(RB * CB == 4, "8 consumer warps of 16 x 32");
     constexpr int NCW = 8, WN = CB, MI = 2, NI = 4, KC = 16;
     constexpr int TM = 32 * RB, TN = 32 * CB;
@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
     unsigned long long* empty = full + RK_ST;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per_mat = nti * ntj;
-    const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // CTA c works on tiles first, first + g0, ... (at most tcap of them): g0 = CTAs resident at a time, so a wave of CTAs
+    // walks a contiguous window of tiles; tcap bounds the CTA's lifetime (short-lived CTAs let the high-priority panel
+    // kernels of the other sub-batch in), tcap >= total / g0 is the persistent kernel
+    const int first = ((int)blockIdx.x / g0) * g0 * tcap + (int)blockIdx.x % g0;
+    const int my_tiles = first < total ? min(tcap, (total - first + g0 - 1) / g0) : 0;
     if (tid == 0) {
         for (int s = 0; s < RK_ST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
         if (lane != 0) return;
         int q = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const int tile = blockIdx.x + it * gridDim.x;
+            const int tile = first + it * g0;
             const int b = tile / per_mat, rem = tile - b * per_mat;
             const int ti = rem / ntj, tj = rem - ti * ntj;
             const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
         }
     int q = 0;
     for (int it = 0; it < my_tiles; it++) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = first + it * g0;
         const int b = tile / per_mat, rem = tile - b * per_mat;
         const int ti = rem / ntj, tj = rem - ti * ntj;
         const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
@@ -300,7 +304,7 @@ template <int RB, int CB, int WR> constexpr size_t rk_rp_smem() {
 }
 
 template <int RB, int CB, int WR>
-__global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, int ntj, int total) {
+__global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, int ntj, int total, int g0, int tcap) {
     static_assert(RB * CB == 4, "8 consumer warps of 16 x 32");
     constexpr int NCW = 8, WN = CB, MI = 2, NI = 4, KC = 16;
     constexpr int TM = 32 * RB, TN = 32 * CB;
@@ -310,7 +314,11 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
     unsigned long long* empty = full + RK_ST;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per_mat = nti * ntj;
-    const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // CTA c works on tiles first, first + g0, ... (at most tcap of them): g0 = CTAs resident at a time, so a wave of CTAs
+    // walks a contiguous window of tiles; tcap bounds the CTA's lifetime (short-lived CTAs let the high-priority panel
+    // kernels of the other sub-batch in), tcap >= total / g0 is the persistent kernel
+    const int first = ((int)blockIdx.x / g0) * g0 * tcap + (int)blockIdx.x % g0;
+    const int my_tiles = first < total ? min(tcap, (total - first + g0 - 1) / g0) : 0;
     if (tid == 0) {
         for (int s = 0; s < RK_ST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
         if (lane != 0) return;
         int q = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const int tile = blockIdx.x + it * gridDim.x;
+            const int tile = first + it * g0;
             const int b = tile / per_mat, rem = tile - b * per_mat;
             const int ti = rem / ntj, tj = rem - ti * ntj;
             const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
         }
     int q = 0;
     for (int it = 0; it < my_tiles; it++) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = first + it * g0;
         const int b = tile / per_mat, rem = tile - b * per_mat;
         const int ti = rem / ntj, tj = rem - ti * ntj;
         const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
@@ -778,7 +786,9 @@ __global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_r
                                                           const cplx* __restrict__ Lsrc, long stridePk, int nrb,
                                                           cplx* __restrict__ Wpk, long strideWk, int ncb, int nreal,
                                                           int mixr, const double* __restrict__ PpkR, long stridePkR,
-                                                          double* __restrict__ WpkR, long strideWkR) {
+                                                          double* __restrict__ WpkR, long strideWkR, int a_lo) {
+    // a_lo: W rows below a_lo are not written back to A (FORWARD mode: only the packed copy is ever read again; the
+    // back-substitution of the contact-column path touches rows >= back_row_lo only)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool AR = sizeof(AT) == sizeof(double);
     AT* sA = reinterpret_cast<AT*>(smem_raw);                // [3][32][WM_AS]: inv_a, L_ba, inv_b (doubles when real)
@@ -824,8 +834,10 @@ __global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_r
         for (int mi = 0; mi < 2; mi++) {
             const int k = c0 + wm * 16 + mi * 8 + gid;
             const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
-            if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
-            else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
+            if (k >= a_lo) {
+                if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
+                else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
+            }
             if (rstore) {
                 *reinterpret_cast<double2*>(Wr + (long)(k >> 4) * ncb * RK_WRBLK + (k & 15) * RK_WRS) = make_double2(v0.x, v1.x);
             } else {
@@ -862,8 +874,10 @@ __global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_r
             for (int mi = 0; mi < 2; mi++) {
                 const int k = c0 + GNB_NB + wm * 16 + mi * 8 + gid;
                 const cplx v0 = cmake(cre[mi][0], cim[mi][0]), v1 = cmake(cre[mi][1], cim[mi][1]);
-                if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
-            else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
+                if (k >= a_lo) {
+                    if (rstore) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0.x, v1.x);
+                    else { Ab[(long)k * ld + col] = v0; Ab[(long)k * ld + col + 1] = v1; }
+                }
                 if (rstore) {
                     *reinterpret_cast<double2*>(Wr + (long)(k >> 4) * ncb * RK_WRBLK + (k & 15) * RK_WRS) = make_double2(v0.x, v1.x);
                 } else {
@@ -896,7 +910,7 @@ __global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, l
                                                          const cplx* __restrict__ inv_b, const cplx* __restrict__ Lsrc,
                                                          long stridePk, int nrb, cplx* __restrict__ Wpk, long strideWk, int ncb,
                                                          int mixr, const double* __restrict__ PpkR, long stridePkR,
-                                                         double* __restrict__ WpkR, long strideWkR) {
+                                                         double* __restrict__ WpkR, long strideWkR, int a_lo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);        // [3][32][WM_AS]: inv_a, L_ba, inv_b
     double* sB = sA + 3 * GNB_NB * WM_AS;                    // [64][WR_BS]: R_a / W_a rows, then R_b rows
@@ -930,10 +944,10 @@ __global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, l
         double* Wr = WpkR + (long)b * strideWkR + (long)(col >> 5) * RK_WRBLK + (col & 31);
         auto emit = [&](int k, double v0, double v1) {        // row k of W: into A and into the packed W operand
             if (rstore) {
-                *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0, v1);
+                if (k >= a_lo) *reinterpret_cast<double2*>(Abr + (long)k * 2 * ld + col) = make_double2(v0, v1);
                 *reinterpret_cast<double2*>(Wr + (long)(k >> 4) * ncb * RK_WRBLK + (k & 15) * RK_WRS) = make_double2(v0, v1);
             } else {
-                Ab[(long)k * ld + col] = cmake(v0, 0.0); Ab[(long)k * ld + col + 1] = cmake(v1, 0.0);
+                if (k >= a_lo) { Ab[(long)k * ld + col] = cmake(v0, 0.0); Ab[(long)k * ld + col + 1] = cmake(v1, 0.0); }
                 cplx* wq = Wb + (long)(k >> 4) * ncb * RK_WBLK + (k & 15) * RK_WPS;
                 wq[0] = cmake(v0, 0.0); wq[1] = cmake(v1, 0.0);
             }
@@ -985,6 +999,9 @@ static int g_rk_kskip = 1;
 static int g_rk_real = 1;        // skip the imaginary DMMAs where the operands are known to be real
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
+static int g_rk_wskip = 1;       // forward-W: skip the dead write of W into A (FORWARD mode, rows above back_row_lo)
+static int g_rk_tcap_k = 0;      // > 0: a rank-K CTA works on at most max(1, tcap_k / K) tiles (short-lived CTAs), 0: persistent
+static int g_rk_lowprio = 0;     // rank-K launches carry the lowest launch priority (the sub-batch streams are high priority)
 static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
 static const size_t kWmSmem = (size_t)(3 * GNB_NB * WM_AS + 2 * GNB_NB * WM_BS) * sizeof(cplx);
 static const size_t kWmSmemR = (size_t)3 * GNB_NB * WM_AS * sizeof(double) + (size_t)2 * GNB_NB * WM_BS * sizeof(cplx);
@@ -1026,6 +1043,9 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_wsolve_areal")) g_rk_wsolve_areal = value;
     else if (!strcmp(name, "rk_rp2")) g_rk_rp2 = value;
     else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
+    else if (!strcmp(name, "rk_tcap_k")) g_rk_tcap_k = value;
+    else if (!strcmp(name, "rk_wskip")) g_rk_wskip = value;
+    else if (!strcmp(name, "rk_lowprio")) g_rk_lowprio = value;
     else if (!strcmp(name, "rk_sms") && value > 0) g_rk_sms = value;      // CTAs of the persistent rank-K kernels
 }
 
@@ -1073,6 +1093,22 @@ int gnb_rec_trace_dump(const char* path) {
     return 0;
 }
 
+// Launch of a rank-K kernel: g0 = CTAs resident at a time, tile cap per CTA from the K extent, optional low priority.
+template <typename KT, typename AT>
+static void rk_launch(KT kern, const AT& args, int nti, int ntj, long total, int resident, int K, size_t smem, cudaStream_t st) {
+    const int g0 = (int)std::min<long>(total, (long)resident);
+    const int persistent = cdiv_i(total, g0);
+    const int tcap = g_rk_tcap_k > 0 ? std::min(persistent, std::max(1, g_rk_tcap_k / std::max(K, 1))) : persistent;
+    const int grid = (int)((total + (long)g0 * tcap - 1) / ((long)g0 * tcap)) * g0;      // whole groups; surplus CTAs find no tile
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(288); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = 0;                                  // numerically largest = lowest priority
+    cfg.attrs = at; cfg.numAttrs = g_rk_lowprio ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, args, nti, ntj, (int)total, g0, tcap);
+}
+
 namespace {
 struct Rec {
     cudaStream_t st; int M, N, naug; cplx* A; long strideA; int ld; int jordan;
@@ -1106,16 +1142,16 @@ struct Rec {
             const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
             const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
             const long total = (long)M * nti * ntj;
-            const int grid = (int)std::min<long>(total, (long)g_rk_sms * ((wr || g_rk_rp2) ? 2 : 1));
+            const int resident = g_rk_sms * ((wr || g_rk_rp2) ? 2 : 1), K = khi - klo;
             const double flops = (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M * (wr ? 2.0 : 4.0);
             TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
             if (ws.timer) ws.timer->begin(st);
             if (strip) {
-                if (wr) k_rk_gemm_rp<4, 1, 1><<<grid, 288, rk_rp_smem<4, 1, 1>(), st>>>(r, nti, ntj, (int)total);
-                else k_rk_gemm_rp<4, 1, 0><<<grid, 288, rk_rp_smem<4, 1, 0>(), st>>>(r, nti, ntj, (int)total);
+                if (wr) rk_launch(k_rk_gemm_rp<4, 1, 1>, r, nti, ntj, total, resident, K, rk_rp_smem<4, 1, 1>(), st);
+                else rk_launch(k_rk_gemm_rp<4, 1, 0>, r, nti, ntj, total, resident, K, rk_rp_smem<4, 1, 0>(), st);
             } else {
-                if (wr) k_rk_gemm_rp<2, 2, 1><<<grid, 288, rk_rp_smem<2, 2, 1>(), st>>>(r, nti, ntj, (int)total);
-                else k_rk_gemm_rp<2, 2, 0><<<grid, 288, rk_rp_smem<2, 2, 0>(), st>>>(r, nti, ntj, (int)total);
+                if (wr) rk_launch(k_rk_gemm_rp<2, 2, 1>, r, nti, ntj, total, resident, K, rk_rp_smem<2, 2, 1>(), st);
+                else rk_launch(k_rk_gemm_rp<2, 2, 0>, r, nti, ntj, total, resident, K, rk_rp_smem<2, 2, 0>(), st);
             }
             if (ws.timer) ws.timer->end(st, flops);
             if (ws.flops_acc) *ws.flops_acc += flops;
@@ -1135,7 +1171,6 @@ struct Rec {
         const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
         const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
         const long total = (long)M * nti * ntj;
-        const int grid = (int)std::min<long>(total, (long)g_rk_sms);
         // executed arithmetic in 4-multiplication-equivalent real flops: 8 per complex MAC, 4 where P is real and W
         // complex, 2 where both are real (tiles entirely left of nreal)
         int ncol1 = 0;
@@ -1149,11 +1184,11 @@ struct Rec {
         if (ws.timer) ws.timer->begin(st);
         const bool m3 = g_rk_m3 && khi - klo >= g_rk_m3_mink;
         if (strip) {
-            if (m3) k_rk_gemm<1, 4, 1><<<grid, 288, rk_smem<4, 1>(), st>>>(g, nti, ntj, (int)total);
-            else k_rk_gemm<0, 4, 1><<<grid, 288, rk_smem<4, 1>(), st>>>(g, nti, ntj, (int)total);
+            if (m3) rk_launch(k_rk_gemm<1, 4, 1>, g, nti, ntj, total, g_rk_sms, khi - klo, rk_smem<4, 1>(), st);
+            else rk_launch(k_rk_gemm<0, 4, 1>, g, nti, ntj, total, g_rk_sms, khi - klo, rk_smem<4, 1>(), st);
         } else {
-            if (m3) k_rk_gemm<1, 2, 2><<<grid, 288, rk_smem<2, 2>(), st>>>(g, nti, ntj, (int)total);
-            else k_rk_gemm<0, 2, 2><<<grid, 288, rk_smem<2, 2>(), st>>>(g, nti, ntj, (int)total);
+            if (m3) rk_launch(k_rk_gemm<1, 2, 2>, g, nti, ntj, total, g_rk_sms, khi - klo, rk_smem<2, 2>(), st);
+            else rk_launch(k_rk_gemm<0, 2, 2>, g, nti, ntj, total, g_rk_sms, khi - klo, rk_smem<2, 2>(), st);
         }
         if (ws.timer) ws.timer->end(st, flops);
         if (ws.flops_acc) *ws.flops_acc += flops;
@@ -1216,6 +1251,8 @@ struct Rec {
                 *ws.flops_acc += (nb == 2 ? 3.0 : 1.0) * 32.0 * 32.0 * per * M;
             }
             if (g_rk_wsolve_mma || mixr > 0) {             // the FMA kernel does not know the mixed layout
+                // FORWARD: W rows above the back-substitution's first row live on in the packed copy only
+                const int a_lo = (!jordan && g_rk_wskip) ? std::max(0, ws.back_row_lo) / GNB_NB * GNB_NB : 0;
                 const int ntile = (jhi - jlo) / WM_TC;
                 const int nr = g_rk_real ? ws.nreal : 0;
                 const bool areal = g_rk_wsolve_areal && c0 + w <= nr;      // real pivot blocks: inv_a, L_ba, inv_b are real
@@ -1228,7 +1265,7 @@ struct Rec {
                     dim3 grid(cdiv_i(ntile, per), M);
                     k_rk_wsolve_rr<<<grid, 256, kWrSmem, st>>>(A, strideA, ld, c0, nb, jlo, jreal, per, inv(c0),
                                                                nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb, ws.Wpk,
-                                                               ws.strideWk, ncb, mixr, ws.PpkR, ws.stridePkR, ws.WpkR, ws.strideWkR);
+                                                               ws.strideWk, ncb, mixr, ws.PpkR, ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo);
                     launches++;
                 }
                 if (jhi > jreal) {
@@ -1240,12 +1277,12 @@ struct Rec {
                         k_rk_wsolve_mma<double><<<grid, 256, kWmSmemR, st>>>(A, strideA, ld, c0, nb, jreal, jhi, per, inv(c0),
                                                                              nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk,
                                                                              nrb, ws.Wpk, ws.strideWk, ncb, nr, mixr, ws.PpkR,
-                                                                             ws.stridePkR, ws.WpkR, ws.strideWkR);
+                                                                             ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo);
                     else
                         k_rk_wsolve_mma<cplx><<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jreal, jhi, per, inv(c0),
                                                                           nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
                                                                           ws.Wpk, ws.strideWk, ncb, nr, mixr, ws.PpkR,
-                                                                          ws.stridePkR, ws.WpkR, ws.strideWkR);
+                                                                          ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo);
                     launches++;
                 }
                 return;

@@ -7,7 +7,7 @@ from scipy.special import roots_legendre
 
 from .config import (TEMPERATURE, ADAPTIVE_INTEGRATION_TOL, FERMI_CALCULATION_TOL, FERMI_SEARCH_CYCLES, N_KT,
                      ENERGY_MIN, MAX_CYCLES, MAX_GRID_POINTS)
-from .integrate import GrInt, GrLessInt
+from .integrate import GrInt, GrLessInt, GrIntLevels
 from ._native import default_context
 from .sigma_plan import ObjectPlan, DESC, DENSE_CONST
 
@@ -37,24 +37,60 @@ def getANTPoints(N):
     return np.concatenate((x, -1 * x)), np.concatenate((w, w))
 
 
+# Nested levels evaluated per GPU batch when the integrand offers `computePoint.levels` (speculation: the nodes of
+# level 3N are known before level N's convergence test).  Groups of nested grid sizes: a group costs one launch
+# chain; levels computed past the converged one are discarded.
+_SPECULATIVE_GROUPS = ((2, 6, 18), (54, 162), (486,), (1458,), (4374,))
+
+
 def integratePointsAdaptiveANT(computePoint, tol=ADAPTIVE_INTEGRATION_TOL, maxN=MAX_GRID_POINTS, debug=False):
     """Nested refinement N = 2, 6, 18, ... (density.py:211-273): each level rescales the previous
     integral by the weight ratio of the re-used nodes and adds ONLY the new nodes, which go to the
-    GPU as one batch (2, 4, 12, 36, 108, 324 energies)."""
+    GPU as one batch (2, 4, 12, 36, 108, 324 energies).
+
+    If `computePoint` has an attribute `levels` (a function of [(x, w), ...] returning the list of integrals), the new
+    nodes of SEVERAL consecutive levels are evaluated in one GPU batch (2 + 4 + 12, then 36 + 108, ...): the host
+    arithmetic (P * ratio + new, the convergence test and the prints) is the reference's, level by level, on sums
+    that are the same as those of separate calls."""
+    many = None if debug else getattr(computePoint, "levels", None)
+    ahead = {}                       # N -> integral over the NEW nodes of level N, computed speculatively
+
+    def new_nodes_sum(N, x_new, w_new, later):
+        if many is None:
+            return computePoint(x_new, w_new)
+        if N not in ahead:
+            group = next((g for g in _SPECULATIVE_GROUPS if N in g), (N,))
+            todo = [(N, x_new, w_new)] + [t for t in later(group) if t[0] > N]
+            for (n, _, _), val in zip(todo, many([(xx, ww) for _, xx, ww in todo])):
+                ahead[n] = val
+        return ahead.pop(N)
+
+    def later_levels(group):
+        """(N, new x, new w) of the levels of `group` above the current one, within maxN"""
+        out = []
+        for n in group:
+            if n > maxN or n < 6:
+                continue
+            xa, wa = getANTPoints(n)
+            xp, _ = getANTPoints(n // 3)
+            mask = ~np.isin(np.round(xa, 14), np.round(xp, 14))
+            out.append((n, xa[mask], wa[mask]))
+        return out
+
     prev_x = prev_sumW = P = new_P = None
     N = 2
     maxDP = 1e10
     while N <= maxN:
         x, w = getANTPoints(N)
         if prev_x is None:
-            P = computePoint(x[0:2], w[0:2])
+            P = new_nodes_sum(N, x[0:2], w[0:2], later_levels)
         else:
             old_mask = np.isin(np.round(x, 14), np.round(prev_x, 14))
             assert int(old_mask.sum()) == prev_x.size, "Old nodes mismatch"
             ratio = float(np.sum(w[old_mask]) / prev_sumW)
             new_mask = ~old_mask
             new_P = P * ratio
-            new_P += computePoint(x[new_mask], w[new_mask])
+            new_P += new_nodes_sum(N, x[new_mask], w[new_mask], later_levels)
             maxDP = np.max(np.abs(new_P - P))
             if debug:
                 P_debug = computePoint(x, w)
@@ -204,21 +240,29 @@ def densityComplexN(F, S, g, Emin, mu, N=100, T=TEMPERATURE, showText=True, meth
 def densityComplex(F, S, g, Emin, mu, tol=ADAPTIVE_INTEGRATION_TOL, T=TEMPERATURE, debug=False):
     center, r, broadening = _semicircle(Emin, mu, T)
 
-    def computePoint(x, w):
+    def contour(x, w):
         theta = np.pi / 2 * (x + 1)
         z = center + r * np.exp(1j * theta)
         dz = 1j * r * np.exp(1j * theta)
-        return GrInt(F, S, g, z, (np.pi / 2) * w * dz * fermi(z, mu, T))
+        return z, (np.pi / 2) * w * dz * fermi(z, mu, T)
 
+    def computePoint(x, w):
+        return GrInt(F, S, g, *contour(x, w))
+
+    computePoint.levels = lambda pairs: GrIntLevels(F, S, g, [contour(x, w) for x, w in pairs])
     print('Complex Contour Integration:')
     lineInt = integratePointsAdaptiveANT(computePoint, tol=tol, debug=debug)
     if T > 0:
         print('Integrating Fermi Broadening:')
 
-        def computePointBroadening(x, w):
+        def tail(x, w):
             E = broadening * (x) + mu
-            return GrInt(F, S, g, E, broadening * w * fermi(E, mu, T))
+            return E, broadening * w * fermi(E, mu, T)
 
+        def computePointBroadening(x, w):
+            return GrInt(F, S, g, *tail(x, w))
+
+        computePointBroadening.levels = lambda pairs: GrIntLevels(F, S, g, [tail(x, w) for x, w in pairs])
         lineInt += integratePointsAdaptiveANT(computePointBroadening, tol=tol, debug=debug)
     return (1 + 0j) * np.imag(lineInt) / np.pi
 

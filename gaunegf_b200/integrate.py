@@ -75,6 +75,34 @@ def GrInt(F, S, g, Elist, weights):
     return parallel.sharded_matrix_sum(N, Elist, weights, run, device=_device_of(ctx) if world > 1 else None)
 
 
+def GrIntLevels(F, S, g, levels):
+    """[GrInt(F, S, g, E_l, w_l) for (E_l, w_l) in levels] evaluated as ONE batch on the GPU (gnb_gr_int_seg): the
+    nested levels of the adaptive quadratures (density.py:234-270) are known before the convergence test of the current
+    one, so several of them share one launch chain.  Each level's sum runs over that level's energies only and in
+    their order, exactly as its own GrInt call would."""
+    levels = [_check(F, S, E, w) for E, w in levels]
+    N = np.shape(F)[0]
+    ctx = default_context()
+    ctx.set_system(F, S)
+    plan = ObjectPlan(g, N)
+    plan.install(ctx)
+    if plan.kind not in (DESC, DENSE_CONST):            # host-evaluated Sigma objects: level by level
+        return [GrInt(F, S, g, E, w) for E, w in levels]
+    Eall = np.concatenate([E for E, _ in levels])
+    wall = np.concatenate([w for _, w in levels])
+    ends = np.cumsum([E.size for E, _ in levels])
+    parallel_logger.info("Calculating G^R with GInt on B200: %dx%d, %d energies in %d levels", N, N, Eall.size, len(levels))
+
+    def run(E, w, local_ends, out):
+        ptr_ = out.data_ptr() if out is not None else None
+        sig = None if plan.kind == DESC else plan.sigma_total()
+        return ctx.gr_int_seg(E, w, local_ends, sig=sig, out_device_ptr=ptr_)
+
+    _, world = parallel.dist_info()
+    res = parallel.sharded_matrix_sums(N, Eall, wall, ends, run, device=_device_of(ctx) if world > 1 else None)
+    return [res[i] for i in range(len(levels))]
+
+
 def GrLessInt(F, S, g, Elist, weights, ind=None):
     """sum_k weights[k] * G^R Gamma G^A with Gamma = i(sigma - sigma^H); sigma = g.sigmaTot(E) if
     ind is None else g.sigma(E, ind)   (integrate.py:177-208)"""

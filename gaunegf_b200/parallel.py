@@ -94,6 +94,45 @@ def sharded_matrix_sum(N, Elist, weights, partial_fn, device=None):
     return t.numpy().view(np.complex128).reshape(N, N)
 
 
+def sharded_matrix_sums(N, Elist, weights, seg_end, partial_fn, device=None):
+    """Several weighted sums in one batch: segment s = energies [seg_end[s-1], seg_end[s]).  Every segment is split
+    cyclically over the ranks (each rank's local list stays ordered segment by segment) and ONE all-reduce carries
+    the (nseg, N, N) partial sums.  partial_fn(E_local, w_local, local_seg_end, out) -> (nseg, N, N) or writes `out`."""
+    rank, world = dist_info()
+    Elist = np.asarray(Elist)
+    weights = np.asarray(weights)
+    seg_end = np.asarray(seg_end, dtype=np.int64)
+    nseg = seg_end.size
+    if world == 1:
+        return partial_fn(Elist, weights, seg_end, None)
+    idx, ends, lo = [], [], 0
+    for hi in seg_end:
+        idx.append(lo + shard_indices(int(hi - lo), rank, world))
+        ends.append((ends[-1] if ends else 0) + idx[-1].size)
+        lo = int(hi)
+    idx = np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
+    ends = np.asarray(ends, dtype=np.int64)
+    import torch
+    import torch.distributed as dist
+    if device is not None:
+        key = ("seg", nseg, N, device.index)
+        if key not in _buffers:
+            for k in [k for k in _buffers if k[0] == "seg"]:
+                del _buffers[k]
+            _buffers[key] = (torch.empty((nseg, N, N), dtype=torch.complex128, device=device),
+                             torch.empty((nseg, N, N), dtype=torch.complex128).pin_memory())
+        out, host = _buffers[key]
+        partial_fn(Elist[idx], weights[idx], ends, out)
+        dist.all_reduce(torch.view_as_real(out), op=dist.ReduceOp.SUM)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(device)
+        return host.numpy().copy()
+    part = np.asarray(partial_fn(Elist[idx], weights[idx], ends, None), dtype=np.complex128)
+    t = torch.from_numpy(np.ascontiguousarray(part).view(np.float64).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy().view(np.complex128).reshape(nseg, N, N)
+
+
 def sharded_per_energy(Elist, per_energy_fn, width=None):
     """per-energy results (T(E): (M,), DOS rows: (M, width)) with the energies split over the ranks;
     every rank returns the full array (all-gather of the cyclic slices)."""

@@ -116,6 +116,12 @@ int gnb_transmission(gnb_ctx* ctx, int M, const double* E, int ca, int cb, doubl
 int gnb_dos(gnb_ctx* ctx, int M, const double* E, double* dos_total, double* dos_per_site);
 /* out = sum_k w_k G(E_k)   (integrate.GrInt, integrate.py:146-173).  out: N x N complex. */
 int gnb_gr_int(gnb_ctx* ctx, int M, const double* E, const double* w, double* out, int loc);
+/* nseg such sums over consecutive energy ranges in ONE batch: out[s] = sum of w_k G(E_k) for seg_end[s-1] <= k <
+ * seg_end[s] (seg_end non-decreasing, seg_end[nseg-1] = M).  out: nseg x N x N complex.  Serves the nested adaptive
+ * quadratures (density.integratePointsAdaptiveANT, density.py:211-273: the nodes of the next levels are known before
+ * the convergence test of the current one, so several levels share one launch chain). */
+int gnb_gr_int_seg(gnb_ctx* ctx, int M, const double* E, const double* w, int nseg, const int32_t* seg_end,
+                   double* out, int loc);
 /* out = sum_k w_k G Gamma G^H  (integrate.GrLessInt, integrate.py:177-208);
  * contact >= 0: Gamma of that contact; contact = -1: Gamma of Sigma_tot (ind=None). */
 int gnb_gless_int(gnb_ctx* ctx, int M, const double* E, const double* w, int contact, double* out, int loc);
@@ -136,6 +142,8 @@ int gnb_dos_dense(gnb_ctx* ctx, int M, const double* E, const double* sig, long 
                   double* dos_total, double* dos_per_site);
 int gnb_gr_int_dense(gnb_ctx* ctx, int M, const double* E, const double* w, const double* sig,
                      long sig_stride, double* out, int loc);
+int gnb_gr_int_seg_dense(gnb_ctx* ctx, int M, const double* E, const double* w, int nseg, const int32_t* seg_end,
+                         const double* sig, long sig_stride, double* out, int loc);
 int gnb_gless_int_dense(gnb_ctx* ctx, int M, const double* E, const double* w, const double* sig,
                         long sig_stride, const double* gam, long gam_stride, double* out, int loc);
 

@@ -257,8 +257,49 @@ def test_n2_fermi_search_host_logic(golden, monkeypatch):
     from n2_cases import run_cases, compare
     monkeypatch.setattr(D, "GrInt", O.GrInt)
     monkeypatch.setattr(D, "GrLessInt", O.GrLessInt)
+    # the speculative multi-level batches of the adaptive quadrature: each level is its own oracle integral
+    monkeypatch.setattr(D, "GrIntLevels", lambda F, S, g, levels: [O.GrInt(F, S, g, E, w) for E, w in levels])
     monkeypatch.setattr(D, "_compute_dos_at_energy", O.compute_dos_at_energy)
     compare(run_cases(D, surfGTest, None), golden("n2_fermi"), 1e-9)
+
+
+def test_adaptive_ant_speculation_is_transparent():
+    """integratePointsAdaptiveANT with a `levels` batch evaluator (several nested levels per GPU batch) returns the same
+    value, visits the same levels and prints the same text as the level-by-level reference loop (density.py:211-273)."""
+    import contextlib, io
+    import gaunegf_b200.density as D
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+
+    def f(x, w):                                   # a smooth matrix-valued integrand: converges at N = 54 or 162
+        return sum(wk * np.linalg.inv(np.eye(4) * (2.5 + xk) + 0.1 * A) for xk, wk in zip(x, w))
+
+    calls = []
+
+    def g(x, w):
+        calls.append(("point", len(x)))
+        return f(x, w)
+
+    def levels(pairs):
+        calls.append(("levels", [len(x) for x, _ in pairs]))
+        return [f(x, w) for x, w in pairs]
+
+    out0, out1 = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out0):
+        ref = D.integratePointsAdaptiveANT(g, tol=1e-9)
+    seq = list(calls)
+    calls.clear()
+    g.levels = levels
+    with contextlib.redirect_stdout(out1):
+        spec = D.integratePointsAdaptiveANT(g, tol=1e-9)
+    assert np.array_equal(ref, spec) and out0.getvalue() == out1.getvalue()
+    assert all(kind == "levels" for kind, _ in calls) and len(calls) < len(seq)
+    assert calls[0] == ("levels", [2, 4, 12])
+    # maxN cuts the speculation, too
+    calls.clear()
+    with contextlib.redirect_stdout(io.StringIO()):
+        D.integratePointsAdaptiveANT(g, tol=0.0, maxN=54)
+    assert [c[1] for c in calls] == [[2, 4, 12], [36]]
 
 
 def test_n4_analytic_density(golden):

@@ -94,6 +94,38 @@ def test_integrals(ctx, N, nc):
     assert relerr(ctx.gr_int_dense(z, w, np.broadcast_to(st, (len(z), N, N)).copy()), O.GrInt(F, S, g, z, w)) < TOL
 
 
+@pytest.mark.parametrize("N,nc", [(48, 6), (200, 24)])
+def test_segmented_gr_int_equals_separate_calls(ctx, N, nc):
+    """gnb_gr_int_seg (several nested quadrature levels in one batch): every segment equals its own gnb_gr_int call
+    bit for bit, with ragged and empty segments, across chunk boundaries, and for a dense Sigma"""
+    F, S, inds, sig = const_system(ctx, N, nc, seed=5)
+    z, w = sy.contour_points(18, -12.0, 0.0)
+    ends = [2, 6, 6, 18]
+    seg = ctx.gr_int_seg(z, w, ends)
+    assert seg.shape == (4, N, N)
+    lo = 0
+    for s_, hi in enumerate(ends):
+        ref = ctx.gr_int(z[lo:hi], w[lo:hi])
+        assert np.array_equal(seg[s_], ref)
+        lo = hi
+    st = sig[0] + sig[1]
+    segd = ctx.gr_int_seg(z, w, ends, sig=st)
+    assert relerr(segd[3], seg[3]) < TOL and relerr(segd[0], seg[0]) < TOL
+    ctx.set_workspace_limit(64 << 20)                      # force several chunks: segments straddle them
+    try:
+        z2, w2 = sy.contour_points(162, -12.0, 0.0)
+        ends2 = [36, 144, 162]
+        seg2 = ctx.gr_int_seg(z2, w2, ends2)
+        lo = 0
+        for s_, hi in enumerate(ends2):
+            assert relerr(seg2[s_], O.GrInt(F, S, type("G", (), {"sigmaTot": lambda self, E: st})(), z2[lo:hi], w2[lo:hi])) < TOL
+            lo = hi
+    finally:
+        ctx.set_workspace_limit(48 << 30)
+    with pytest.raises(Exception):
+        ctx.gr_int_seg(z, w, [4, 2, 18])
+
+
 def test_chunking_matches_single_pass(ctx):
     F, S, inds, sig = const_system(ctx, 96, 8, seed=9)
     z, w = sy.contour_points(54, -12.0, 0.0)
