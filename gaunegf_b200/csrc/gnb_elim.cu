@@ -450,12 +450,12 @@ template <> struct TwChunk<double2> {
     static __device__ __forceinline__ void ld(const double2* p, double2 (&e)[1]) { e[0] = *p; }
 };
 
-template <typename T>
-__device__ __forceinline__ void tw_load(typename T::C (&a)[2][32], const int (&rows)[2], const cplx* __restrict__ Ab, int ld,
+template <typename T, int NR = 2>
+__device__ __forceinline__ void tw_load(typename T::C (&a)[NR][32], const int (&rows)[NR], const cplx* __restrict__ Ab, int ld,
                                         int c0, int mixr) {
     // loads go out in groups of 8 columns (the compiler would otherwise keep all 32 raw 16-byte values of a row live)
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
+    for (int rr = 0; rr < NR; rr++) {
         if (rows[rr] < 0) {
 #pragma unroll
             for (int k = 0; k < 32; k++) a[rr][k] = T::zero();
@@ -493,8 +493,8 @@ __device__ __forceinline__ void tw_load(typename T::C (&a)[2][32], const int (&r
 // static and the step loop stays rolled: a fully unrolled triangle is faster per step on paper but ~9 k instructions
 // per kernel, and a tournament CTA runs its code exactly once - it was instruction-fetch bound (85 us per final
 // round against 51 us of the CTA-wide kernel).  WIDTH = live columns at j0 (32, then 16 for the second half).
-template <typename T, bool F64, int WIDTH>
-__device__ __forceinline__ void tw_steps(typename T::C (&a)[2][32], const int (&rows)[2], unsigned& alive, int j0, int j1,
+template <typename T, bool F64, int WIDTH, int NR = 2>
+__device__ __forceinline__ void tw_steps(typename T::C (&a)[NR][32], const int (&rows)[NR], unsigned& alive, int j0, int j1,
                                          typename T::C* s_prow, int* s_win, int lane, bool flag_singular, int* info) {
     typedef typename T::C C;
     typedef TwChunk<C> CH;
@@ -502,10 +502,14 @@ __device__ __forceinline__ void tw_steps(typename T::C (&a)[2][32], const int (&
     const unsigned long long kzero = T::key(T::zero());
 #pragma unroll 1
     for (int j = j0; j < j1; j++) {
-        const unsigned long long k0 = (alive & 1u) ? T::key(a[0][0]) : 0ull;
-        const unsigned long long k1 = (alive & 2u) ? T::key(a[1][0]) : 0ull;
-        const int krr = k1 > k0 ? 1 : 0;                     // first maximum wins (izamax): row 2 * lane before 2 * lane + 1
-        const unsigned long long key = krr ? k1 : k0;
+        // first maximum wins (izamax): the rows of a lane are consecutive candidates, lower row first
+        unsigned long long key = (alive & 1u) ? T::key(a[0][0]) : 0ull;
+        int krr = 0;
+#pragma unroll
+        for (int rr = 1; rr < NR; rr++) {
+            const unsigned long long kq = ((alive >> rr) & 1u) ? T::key(a[rr][0]) : 0ull;
+            if (kq > key) { key = kq; krr = rr; }
+        }
         unsigned bal;
         bool nonzero;
         if (!F64) {
@@ -522,30 +526,35 @@ __device__ __forceinline__ void tw_steps(typename T::C (&a)[2][32], const int (&
         }
         const int src = __ffs(bal) - 1;
         if (lane == src) {                                   // the lane of the pivot row publishes its live columns
-            s_win[j] = krr ? rows[1] : rows[0];
             alive &= ~(1u << krr);
 #pragma unroll
-            for (int cb = 0; cb < WIDTH; cb += PER) {
-                C u[PER];
+            for (int rr = 0; rr < NR; rr++) {
+                if (krr == rr) {
+                    s_win[j] = rows[rr];
 #pragma unroll
-                for (int e = 0; e < PER; e++) u[e] = krr ? a[1][cb + e] : a[0][cb + e];
-                CH::st(&s_prow[cb], u);
+                    for (int cb = 0; cb < WIDTH; cb += PER) {
+                        C u[PER];
+#pragma unroll
+                        for (int e = 0; e < PER; e++) u[e] = a[rr][cb + e];
+                        CH::st(&s_prow[cb], u);
+                    }
+                }
             }
         }
         __syncwarp();
         if (flag_singular && !nonzero && lane == 0) *info = 1;              // exactly singular pivot (LAPACK info > 0)
         // LAPACK zgetf2 scales the column by the reciprocal of the pivot
-        C l0, l1;
+        C l[NR];
         {
             C u0[PER];
             CH::ld(&s_prow[0], u0);
             const C rinv = nonzero ? T::rcp(u0[0]) : T::zero();
-            l0 = T::mul(a[0][0], rinv);
-            l1 = T::mul(a[1][0], rinv);
+#pragma unroll
+            for (int rr = 0; rr < NR; rr++) l[rr] = T::mul(a[rr][0], rinv);
 #pragma unroll
             for (int e = 1; e < PER; e++) {
-                a[0][e - 1] = T::fnma(a[0][e], l0, u0[e]);
-                a[1][e - 1] = T::fnma(a[1][e], l1, u0[e]);
+#pragma unroll
+                for (int rr = 0; rr < NR; rr++) a[rr][e - 1] = T::fnma(a[rr][e], l[rr], u0[e]);
             }
         }
 #pragma unroll
@@ -554,12 +563,12 @@ __device__ __forceinline__ void tw_steps(typename T::C (&a)[2][32], const int (&
             CH::ld(&s_prow[cb], u);
 #pragma unroll
             for (int e = 0; e < PER; e++) {
-                a[0][cb + e - 1] = T::fnma(a[0][cb + e], l0, u[e]);
-                a[1][cb + e - 1] = T::fnma(a[1][cb + e], l1, u[e]);
+#pragma unroll
+                for (int rr = 0; rr < NR; rr++) a[rr][cb + e - 1] = T::fnma(a[rr][cb + e], l[rr], u[e]);
             }
         }
-        a[0][WIDTH - 1] = T::zero();
-        a[1][WIDTH - 1] = T::zero();
+#pragma unroll
+        for (int rr = 0; rr < NR; rr++) a[rr][WIDTH - 1] = T::zero();
         __syncwarp();                                        // s_prow is rewritten in the next step
     }
 }
@@ -567,12 +576,14 @@ __device__ __forceinline__ void tw_steps(typename T::C (&a)[2][32], const int (&
 // GEPP of the (up to) 64 rows held by one warp; winners (global row numbers, pivot order) -> s_win[0 .. nsel).
 // s_prow / s_win are written by one lane and read by the others: never pass them as __restrict__ (the compiler then
 // keeps stale copies of the buffer in registers across __syncwarp).
-template <typename T, bool F64>
-__device__ __forceinline__ void tw_gepp(typename T::C (&a)[2][32], const int (&rows)[2], int nsel, typename T::C* s_prow,
+template <typename T, bool F64, int NR = 2>
+__device__ __forceinline__ void tw_gepp(typename T::C (&a)[NR][32], const int (&rows)[NR], int nsel, typename T::C* s_prow,
                                         int* s_win, int lane, bool flag_singular, int* info) {
-    unsigned alive = (rows[0] >= 0 ? 1u : 0u) | (rows[1] >= 0 ? 2u : 0u);
-    tw_steps<T, F64, 32>(a, rows, alive, 0, min(nsel, 16), s_prow, s_win, lane, flag_singular, info);
-    if (nsel > 16) tw_steps<T, F64, 16>(a, rows, alive, 16, nsel, s_prow, s_win, lane, flag_singular, info);
+    unsigned alive = 0;
+#pragma unroll
+    for (int rr = 0; rr < NR; rr++) alive |= (rows[rr] >= 0 ? 1u : 0u) << rr;
+    tw_steps<T, F64, 32, NR>(a, rows, alive, 0, min(nsel, 16), s_prow, s_win, lane, flag_singular, info);
+    if (nsel > 16) tw_steps<T, F64, 16, NR>(a, rows, alive, 16, nsel, s_prow, s_win, lane, flag_singular, info);
 }
 
 // Final round of a real panel, ONE warp: explicit inverse of the pivot block (chosen rows s_win[0 .. nfin), pivot order) by
@@ -746,15 +757,18 @@ k_tournw(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
 // block and the bookkeeping stay in that warp (17 k warp instructions per matrix against 52 k of the CTA-wide k_tourn,
 // whose shared-memory Gauss-Jordan runs complex arithmetic on real data).
 // ------------------------------------------------------------------------------------------
-template <typename T, bool F64, int NW, int MINB>
+template <typename T, bool F64, int NW, int MINB, int NR0>
 __global__ void __launch_bounds__(32 * NW, MINB)
 k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n_in, int grp, int total_groups,
          const int* __restrict__ cand_in, int cand_in_stride, int* __restrict__ cand_out, int cand_out_stride,
          int final_round, cplx* __restrict__ LU, int* __restrict__ moves, int* __restrict__ perm, int perm_stride,
          int* __restrict__ info, int mixr) {
+    // NR0 = candidate rows per lane at level 0 (lists of 32 NR0 rows): 4 halves the number of sequential eliminations
+    // of a 256-row group (2 + 1 instead of 4 + 2 + 1) at 1.5 x the work per pivot step; the merges always hold 2 rows per lane
     typedef typename T::C C;
     static_assert(sizeof(C) <= 8, "real panels only");
-    constexpr int w = GNB_NB;
+    static_assert(NR0 == 2 || NR0 == 4, "rows per lane at level 0");
+    constexpr int w = GNB_NB, L0 = 32 * NR0;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     __shared__ __align__(16) C s_prow_all[NW][32];
     __shared__ int s_list_all[NW][2][4][32];
@@ -767,12 +781,30 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
     const cplx* Ab = A + (long)b * strideA;
     const int base = g * 256;
     const int ncand = min(256, n_in - base);                 // candidate rows of this warp
-    int rows[2];
-    C a[2][32];
-    int nl = (ncand + 63) / 64, cur = 0, level = 0, q = 0;
+    int nl = (ncand + L0 - 1) / L0, cur = 0, level = 0, q = 0;
     unsigned lens = 0;                                       // 8 bits per list: nominees in list q of the current level
     unsigned lens_next = 0;
-    for (;;) {                                               // warp-uniform loop over (level, q): ONE inlined elimination
+    if constexpr (NR0 == 4) {                                // level 0 with four rows per lane
+        for (q = 0; q < nl; q++) {
+            int rows4[4];
+            C a4[4][32];
+            const int nwr = min(L0, ncand - L0 * q);
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                const int i = L0 * q + 4 * lane + rr;
+                rows4[rr] = i < ncand ? (cand_in ? cand_in[(long)b * cand_in_stride + base + i] : r0 + base + i) : -1;
+            }
+            const int nsel = min(w, nwr);
+            lens |= (unsigned)nsel << (8 * q);
+            tw_load<T, 4>(a4, rows4, Ab, ld, c0, mixr);
+            tw_gepp<T, F64, 4>(a4, rows4, nsel, s_prow, s_list[0][q], lane, final_round && nl == 1, info);
+            __syncwarp();
+        }
+        level = 1; q = 0;
+    }
+    int rows[2];
+    C a[2][32];
+    while (nl > 1 || level == 0) {                           // warp-uniform loop over (level, q): ONE inlined elimination
         int nsel = 0, dst = level == 0 ? 0 : (cur ^ 1);
         bool flag = false;
         const int nn = (nl + 1) / 2;
@@ -812,7 +844,6 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
             if (level > 0) { cur ^= 1; nl = nn; }
             lens = lens_next; lens_next = 0;
             level++; q = 0;
-            if (nl == 1) break;
         }
     }
     const int nfin = lens & 255;
@@ -1328,7 +1359,7 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
 static int g_tourn_fp32 = 1;      // nominating (non-final) tournament rounds in single precision
 void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
-static int g_tourn_warp = 9;      // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
+static int g_tourn_warp = 25;     // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
 void gnb_set_tourn_warp(int on) { g_tourn_warp = on; }
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
@@ -1348,7 +1379,8 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         // nominating rounds of complex panels.  Measured on the N = 1024 T(E) step (tools/sweep.py, profiles/r02_sweeps.txt):
         // 1 -> +1.7 %; 2 -> -1.8 % (44 us against 51 us alone, but its 224 registers keep it from sharing an SM with the
         // other sub-batch's rank-K CTAs); 4 -> -4 % (252 registers, 2 CTAs per SM); 8 = warp-independent k_tournq for every
-        // round of a real panel (takes precedence over 1 and 2).  Default: 9.
+        // round of a real panel (takes precedence over 1 and 2): +3 %; 16 = four candidate rows per lane at level 0 of the
+        // FP32 nominating rounds of k_tournq (3 sequential eliminations per 256-row group instead of 7): +1.8 %.  Default: 25.
         const bool use_w = warp_ok && (fin ? (real_panel && (g_tourn_warp & 2))
                                            : (real_panel ? (g_tourn_warp & 1) != 0 : (f32 && (g_tourn_warp & 4))));
         if (warp_ok && real_panel && (g_tourn_warp & 8)) {    // warp-independent kernel: one warp per 256-row group / matrix
@@ -1356,16 +1388,16 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
             const int total = M * grp;
             if (grp > 1) {
                 if (f32 && (g_tourn_warp & 16))
-                    k_tournq<TTR<float>, false, 4, 3><<<cdiv_i(total, 4), 128, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                    k_tournq<TTR<float>, false, 4, 3, 4><<<cdiv_i(total, 4), 128, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
                                                                                         cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
                 else if (f32)
-                    k_tournq<TTR<float>, false, 4, 4><<<cdiv_i(total, 4), 128, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                    k_tournq<TTR<float>, false, 4, 4, 2><<<cdiv_i(total, 4), 128, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
                                                                                         cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
                 else
-                    k_tournq<TTR<double>, true, 2, 4><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                    k_tournq<TTR<double>, true, 2, 4, 2><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
                                                                                        cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
             } else {
-                k_tournq<TTR<double>, true, 2, 4><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                k_tournq<TTR<double>, true, 2, 4, 2><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
                                                                                    cout, cand_stride, 1, LU, moves, perm, perm_stride, info, mixr);
             }
             launches++;

@@ -292,12 +292,22 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
 // Same warp-specialised structure as k_rk_gemm; one real DMMA per tile product (WR = 1) or two (WR = 0).
 // Row strides 20 / 36 doubles keep the LDS.64 fragment loads conflict-free.
 // ------------------------------------------------------------------------------------------------
+// Column-tile order of a launch whose right half of column tiles is cheap (real-valued augmented columns, see jre): cheap
+// and expensive tiles alternate in the tile index, and the host makes the CTA stride odd, so every persistent CTA works
+// on both kinds in turn (with the natural order and a stride that is a multiple of ntj a CTA sees ONE column tile only:
+// half of the CTAs would finish in half the time).
+__device__ __forceinline__ int rk_col_tile(int tjp, int ntj, bool interleave) {
+    return interleave ? ((tjp & 1) ? (ntj >> 1) + (tjp >> 1) : (tjp >> 1)) : tjp;
+}
 struct RkGemmRpArgs {
     cplx* C; long sC; int ldc;
     const double* P; long sP; int nrb;
     const void* W; long sW; int ncb;        // doubles (WR = 1) or cplx (WR = 0); sW in elements of that type
     int ilo, ihi, jlo, jhi, klo, khi;
     int mixr;
+    int jint;       // interleave cheap / expensive column tiles (rk_col_tile)
+    int jre;        // WR = 0: columns >= jre hold REAL values in complex storage (the augmented unit columns stay real
+                    // while the pivot blocks are real: real multipliers, real pivot-block inverses) - no imaginary DMMAs
 };
 template <int RB, int CB, int WR> constexpr size_t rk_rp_smem() {
     return (size_t)RK_ST * (RB * RK_PRBLK * 8 + CB * (WR ? RK_WRBLK * 8 : RK_WBLK * 16)) + 2 * RK_ST * 8;
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
         for (int it = 0; it < my_tiles; it++) {
             const int tile = first + it * g0;
             const int b = tile / per_mat, rem = tile - b * per_mat;
-            const int ti = rem / ntj, tj = rem - ti * ntj;
+            const int ti = rem / ntj, tj = rk_col_tile(rem - ti * ntj, ntj, !WR && g.jint);
             const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
             const double* Pb = g.P + (long)b * g.sP + ((long)kc0 * g.nrb + i0 / 32) * RK_PRBLK;
             const char* Wb = WR ? reinterpret_cast<const char*>(reinterpret_cast<const double*>(g.W) + (long)b * g.sW +
@@ -365,9 +375,10 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
     for (int it = 0; it < my_tiles; it++) {
         const int tile = first + it * g0;
         const int b = tile / per_mat, rem = tile - b * per_mat;
-        const int ti = rem / ntj, tj = rem - ti * ntj;
+        const int ti = rem / ntj, tj = rk_col_tile(rem - ti * ntj, ntj, !WR && g.jint);
         const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
         const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);
+        const bool wre = !WR && (j0 + wn * 32 >= g.jre);      // warp-uniform: this warp's 32 columns are real-valued
         for (int ch = 0; ch < nch_all; ch++, q++) {
             const int s = q % RK_ST;
             mbar_wait(&full[s], (q / RK_ST) & 1);
@@ -382,6 +393,23 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
                         for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PRS + kk];
 #pragma unroll
                         for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[kk * RK_WRS + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < NI; ni++) dmma884(cre[mi][ni][0], cre[mi][ni][1], af[mi], bf[ni]);
+                    }
+                } else if (wre) {
+                    // real-valued W in complex storage: only the real parts are read, one DMMA per tile product.  A separate
+                    // loop, not a predicate: a predicated-off DMMA still pays its 16 issue cycles
+                    const double* Ws = reinterpret_cast<const double*>(reinterpret_cast<const cplx*>(smem_raw + s * SBYTES + PBYTES) +
+                                                                       wn * RK_WBLK + tig * RK_WPS + gid);
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        double af[MI], bf[NI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) af[mi] = Ps[(mi * 8) * RK_PRS + kk];
+#pragma unroll
+                        for (int ni = 0; ni < NI; ni++) bf[ni] = Ws[2 * (kk * RK_WPS + ni * 8)];
 #pragma unroll
                         for (int mi = 0; mi < MI; mi++)
 #pragma unroll
@@ -786,7 +814,8 @@ __global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_r
                                                           const cplx* __restrict__ Lsrc, long stridePk, int nrb,
                                                           cplx* __restrict__ Wpk, long strideWk, int ncb, int nreal,
                                                           int mixr, const double* __restrict__ PpkR, long stridePkR,
-                                                          double* __restrict__ WpkR, long strideWkR, int a_lo) {
+                                                          double* __restrict__ WpkR, long strideWkR, int a_lo, int jre) {
+    // jre: columns >= jre hold real values in complex storage (see RkGemmRpArgs::jre)
     // a_lo: W rows below a_lo are not written back to A (FORWARD mode: only the packed copy is ever read again; the
     // back-substitution of the contact-column path touches rows >= back_row_lo only)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -822,7 +851,7 @@ __global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_r
         __syncthreads();
         double cre[2][2], cim[2][2];
         // pivot blocks left of nreal are real; so are the columns left of nreal (see RkGemmArgs::nreal)
-        const int mode = (c0 + nrows <= nreal) ? (cs + WM_TC <= nreal ? 1 : 2) : 3;
+        const int mode = (c0 + nrows <= nreal) ? ((cs + WM_TC <= nreal || cs >= jre) ? 1 : 2) : 3;
         const int col = cs + wn * 8 + tig * 2;                // this thread's two adjacent output columns
         cplx* Wb = Wpk + (long)b * strideWk + (long)(col >> 5) * RK_WBLK + (col & 31);
         double* Wr = WpkR + (long)b * strideWkR + (long)(col >> 5) * RK_WRBLK + (col & 31);   // real-packed copy (rstore tiles)
@@ -1000,6 +1029,7 @@ static int g_rk_real = 1;        // skip the imaginary DMMAs where the operands 
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static int g_rk_wskip = 1;       // forward-W: skip the dead write of W into A (FORWARD mode, rows above back_row_lo)
+static int g_rk_augreal = 1;     // FORWARD: real arithmetic on the augmented columns while the pivot blocks are real
 static int g_rk_tcap_k = 0;      // > 0: a rank-K CTA works on at most max(1, tcap_k / K) tiles (short-lived CTAs), 0: persistent
 static int g_rk_lowprio = 0;     // rank-K launches carry the lowest launch priority (the sub-batch streams are high priority)
 static const size_t kPfSmem = (size_t)(GNB_NB * GNB_NB + PF_ROWS * PF_PS) * sizeof(cplx);
@@ -1045,6 +1075,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
     else if (!strcmp(name, "rk_tcap_k")) g_rk_tcap_k = value;
     else if (!strcmp(name, "rk_wskip")) g_rk_wskip = value;
+    else if (!strcmp(name, "rk_augreal")) g_rk_augreal = value;
     else if (!strcmp(name, "rk_lowprio")) g_rk_lowprio = value;
     else if (!strcmp(name, "rk_sms") && value > 0) g_rk_sms = value;      // CTAs of the persistent rank-K kernels
 }
@@ -1138,12 +1169,20 @@ struct Rec {
             r.P = ws.PpkR; r.sP = ws.stridePkR; r.nrb = nrb;
             r.W = wr ? (const void*)ws.WpkR : (const void*)ws.Wpk; r.sW = wr ? ws.strideWkR : ws.strideWk; r.ncb = ncb;
             r.ilo = ilo; r.ihi = ihi; r.jlo = jlo; r.jhi = jhi; r.klo = klo; r.khi = khi; r.mixr = mixr;
+            // FORWARD: the augmented unit columns (from column N on) are real-valued as long as the pivot blocks are
+            r.jre = (!jordan && g_rk_augreal && khi <= ws.nreal) ? N : (1 << 30);
             const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);
             const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
             const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
             const long total = (long)M * nti * ntj;
-            const int resident = g_rk_sms * ((wr || g_rk_rp2) ? 2 : 1), K = khi - klo;
-            const double flops = (double)(ihi - ilo) * (double)(jhi - jlo) * (double)(khi - klo) * M * (wr ? 2.0 : 4.0);
+            int resident = g_rk_sms * ((wr || g_rk_rp2) ? 2 : 1);
+            const int K = khi - klo;
+            // exactly half of the column tiles are the cheap real-valued ones: interleave them, odd CTA stride
+            r.jint = (!wr && !strip && r.jre > jlo && r.jre < jhi && (ntj % 2 == 0) && (r.jre - jlo) == (ntj / 2) * tn) ? 1 : 0;
+            if (r.jint && resident % 2 == 0) resident--;
+            const double cre_cols = wr ? 0.0 : (double)std::max(0, jhi - std::max(jlo, r.jre));     // real-valued complex-stored columns
+            const double flops = (double)(ihi - ilo) * (double)(khi - klo) * M *
+                                 (wr ? 2.0 * (jhi - jlo) : 4.0 * ((jhi - jlo) - cre_cols) + 2.0 * cre_cols);
             TraceScope ts(khi - klo >= 256 ? "gemm256+" : khi - klo >= 128 ? "gemm128" : khi - klo >= 64 ? "gemm64" : "gemm32", st, M);
             if (ws.timer) ws.timer->begin(st);
             if (strip) {
@@ -1253,6 +1292,7 @@ struct Rec {
             if (g_rk_wsolve_mma || mixr > 0) {             // the FMA kernel does not know the mixed layout
                 // FORWARD: W rows above the back-substitution's first row live on in the packed copy only
                 const int a_lo = (!jordan && g_rk_wskip) ? std::max(0, ws.back_row_lo) / GNB_NB * GNB_NB : 0;
+                const int jre = (!jordan && g_rk_augreal && c0 + w <= (g_rk_real ? ws.nreal : 0)) ? N : (1 << 30);
                 const int ntile = (jhi - jlo) / WM_TC;
                 const int nr = g_rk_real ? ws.nreal : 0;
                 const bool areal = g_rk_wsolve_areal && c0 + w <= nr;      // real pivot blocks: inv_a, L_ba, inv_b are real
@@ -1277,12 +1317,12 @@ struct Rec {
                         k_rk_wsolve_mma<double><<<grid, 256, kWmSmemR, st>>>(A, strideA, ld, c0, nb, jreal, jhi, per, inv(c0),
                                                                              nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk,
                                                                              nrb, ws.Wpk, ws.strideWk, ncb, nr, mixr, ws.PpkR,
-                                                                             ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo);
+                                                                             ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo, jre);
                     else
                         k_rk_wsolve_mma<cplx><<<grid, 256, kWmSmem, st>>>(A, strideA, ld, c0, nb, jreal, jhi, per, inv(c0),
                                                                           nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb,
                                                                           ws.Wpk, ws.strideWk, ncb, nr, mixr, ws.PpkR,
-                                                                          ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo);
+                                                                          ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo, jre);
                     launches++;
                 }
                 return;
