@@ -153,6 +153,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "chain_compact")) gnb_chain_set_compact(value);
     else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
     else if (!strcmp(name, "small_cluster")) gnb_small_set_cluster(value);
+    else if (!strcmp(name, "small_cluster_maxm")) gnb_small_set_cluster_max_m(value);
     else if (!strcmp(name, "small_wide")) gnb_small_set_wide(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
@@ -703,8 +704,11 @@ static int put_chunk_scalars(gnb_ctx* c, const double* E, const double* w, int k
 }
 
 // Small-orbital-count path (gnb_small.cu): is it usable for this call, and the common part of its arguments
-static bool small_ok(const gnb_ctx* c, bool use_desc) {
-    return g_small && c->N <= gnb_small_max_n() && (!use_desc || c->contacts.size() <= GNB_SMALL_MAX_CONTACTS);
+// M > 0: the call may also use the thread-block-cluster kernels (GREEN mode only, 96 < N <= 192) when its batch is small
+static bool small_ok(const gnb_ctx* c, bool use_desc, int M = 0) {
+    if (!g_small || (use_desc && c->contacts.size() > GNB_SMALL_MAX_CONTACTS)) return false;
+    if (c->N <= gnb_small_max_n()) return true;
+    return M > 0 && M <= gnb_small_cluster_max_m(c->N) && c->N <= gnb_small_inverse_max_n();
 }
 static GnbSmallArgs small_args(gnb_ctx* c, int m, const cplx* dE, bool use_desc, const cplx* sig_const,
                                const cplx* sig_batch) {
@@ -752,7 +756,8 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
     if (g2.p && g2.stride) per += nn * 16;
     const bool xform = use_desc && transformed(c);       // dense Sigma (and Gammas) built on the device per chunk
     if (xform) per += nn * 16 * (mode == MODE_T_DENSE || mode == MODE_T_SPIN ? 4 : mode == MODE_GLESS_DENSE ? 3 : 2);
-    const bool small = small_ok(c, use_desc && !xform);
+    const bool small = small_ok(c, use_desc && !xform, M);
+    const bool small_cl = small && c->N > gnb_small_max_n();     // cluster kernels: GREEN mode, reductions as separate kernels
     if (small) per = (size_t)(2 + (sig.p && sig.stride) + 2 * (g1.p && g1.stride) + 2 + (xform ? 4 : 0)) * nn * 16 + (size_t)N * 16 + 64;
     const int Mc = chunk_size(c, std::max(M, 1), per);
     cplx* d_out = nullptr;
@@ -791,7 +796,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         if (small) {
             // one CTA per energy: assembly, pivoted Gauss-Jordan and (for DOS) the reduction stay in shared memory
             GnbSmallArgs sa = small_args(c, m, dE, desc_asm, sc, sb);
-            if (mode == MODE_DOS) {
+            if (mode == MODE_DOS && !small_cl) {
                 GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
                 if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
                 sa.mode = GNB_SMALL_DOS;
@@ -825,7 +830,7 @@ static int run_jordan(gnb_ctx* c, int mode, int M, const double* E, const double
         } else if (mode == MODE_DOS) {
             GNB_CK(c->dDosT.ensure((size_t)m * sizeof(double)));
             if (out1) GNB_CK(c->dDosP.ensure((size_t)m * N * sizeof(double)));
-            if (!small) {
+            if (!small || small_cl) {
                 gnb_launch_dos(c->stream, m, N, A, strideA, lda, inv, pst, c->dDosT.as<double>(),
                                out1 ? c->dDosP.as<double>() : nullptr);
                 c->launches++;
@@ -1239,7 +1244,10 @@ extern "C" int gnb_inverse_batch(gnb_ctx* c, int n, int M, const double* Ain, do
         cplx* G;
         if (loc == GNB_DEVICE) G = reinterpret_cast<cplx*>(Aout) + (size_t)k0 * nn;
         else { GNB_CK(c->G.ensure((size_t)m * nn * sizeof(cplx))); G = c->G.as<cplx>(); }
-        if (g_small && n <= gnb_small_inverse_max_n()) {  // one CTA (or 2-CTA cluster) per matrix, on chip (gnb_small.cu)
+        // above the one-CTA limit the cluster kernels are a latency play: large batches stay on the block engine (96 < n <= 128 keeps
+        // the measured round-1 dispatch: always on chip)
+        if (g_small && (n <= std::max(gnb_small_max_n(), std::min(128, gnb_small_inverse_max_n())) ||
+                        (n <= gnb_small_inverse_max_n() && m <= gnb_small_cluster_max_m(n)))) {  // one CTA (or 2-CTA cluster) per matrix, on chip (gnb_small.cu)
             const cplx* Araw = reinterpret_cast<const cplx*>(Ain) + (size_t)k0 * nn;
             if (loc == GNB_HOST) {
                 if ((rc = put(c, c->A, Ain + (size_t)k0 * nn * 2, (size_t)m * nn * sizeof(cplx), loc))) return rc;

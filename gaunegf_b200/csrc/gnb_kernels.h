@@ -98,7 +98,7 @@ long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long st
 // gnb_small.cu : one CTA per energy, matrix resident in shared memory (N <= GNB_SMALL_MAX_N)
 #define GNB_SMALL_MAX_N 119            // N*(N|1)*16 B + bookkeeping <= 227 KB
 #define GNB_SMALL_REG_MAX_N 96         // register-resident variant: 32*RA rows x NW*CB columns over 32*NW threads
-#define GNB_SMALL_CLUSTER_MAX_N 128     // 2-CTA-cluster register-resident inverse (GREEN mode only)
+#define GNB_SMALL_CLUSTER_MAX_N 192     // thread-block-cluster register-resident inverse: 2 CTAs to 128, 4 CTAs to 192 (GREEN mode)
 #define GNB_SMALL_MAX_CONTACTS 6
 enum { GNB_SMALL_GREEN = 0, GNB_SMALL_DOS = 1, GNB_SMALL_T = 2 };
 struct GnbSmallContact {
@@ -120,9 +120,11 @@ struct GnbSmallArgs {
 cudaError_t gnb_small_init();
 void gnb_small_set_reg(int on);        // developer switch "small_reg": register-resident (1) or shared-memory (0) kernel
 int gnb_small_max_n();                 // 96 (register-resident kernel, default) or 119 (small_reg=0)
-int gnb_small_inverse_max_n();         // largest n whose plain inverse runs on chip (128 with the cluster kernel)
+int gnb_small_inverse_max_n();         // largest n whose plain inverse runs on chip (192 with the cluster kernels)
+int gnb_small_cluster_max_m(int n);    // largest batch for which the cluster kernels are preferred to the block engine
 void gnb_small_set_wide(int on);       // developer switch "small_wide"
 void gnb_small_set_cluster(int on);    // developer switch "small_cluster"
+void gnb_small_set_cluster_max_m(int m);   // developer switch "small_cluster_maxm"
 int gnb_small_enabled();               // developer switch "small_fused" (gnb_api.cu)
 void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a);
 

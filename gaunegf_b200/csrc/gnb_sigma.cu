@@ -103,8 +103,10 @@ void gnb_chain_set_compact(int on) { g_chain_compact = on; }
 
 static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
     int rc;
-    if (gnb_small_enabled() && nc <= gnb_small_max_n()) {    // one CTA per matrix, on chip (gnb_small.cu); the 2-CTA-cluster
-        // kernel (97..128) is not used here: at the 512-problem batches of BASELINE cfg 4 the block engine is 7 % faster
+    // one CTA per matrix, on chip (gnb_small.cu).  The thread-block-cluster kernels (97..192) serve the TAIL of the fixed
+    // point only: with few live problems the iteration is bound by the block engine's launch chain (~25 dependent launches
+    // per inverse), which one cluster launch replaces; at the 512-problem batches of BASELINE cfg 4 the block engine is faster
+    if (gnb_small_enabled() && (nc <= gnb_small_max_n() || (nc <= gnb_small_inverse_max_n() && M <= gnb_small_cluster_max_m(nc)))) {
         GnbSmallArgs sa{};
         sa.N = nc; sa.M = M; sa.mode = GNB_SMALL_GREEN; sa.Araw = Min; sa.info = c->info.as<int>();
         sa.G = Gout; sa.strideG = (long)nc * nc; sa.ldg = nc;

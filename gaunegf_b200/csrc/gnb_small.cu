@@ -686,11 +686,23 @@ cudaError_t gnb_small_init() {
     if ((e = cudaFuncSetAttribute(k_reg_gj<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_reg_gj<3, 6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
-    return cudaFuncSetAttribute(k_reg_gj_cl<4, 4, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if ((e = cudaFuncSetAttribute(k_reg_gj_cl<4, 4, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024))) return e;
+    return cudaFuncSetAttribute(k_reg_gj_cl<6, 6, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
 }
 
 static int g_cluster = 1;               // developer switch "small_cluster"
+static int g_cluster_max_m = 0;         // developer switch "small_cluster_maxm": > 0 overrides the measured batch limits
 void gnb_small_set_cluster(int on) { g_cluster = on; }
+void gnb_small_set_cluster_max_m(int m) { g_cluster_max_m = m; }
+// The cluster kernels win on latency: one launch instead of the block engine's launch chain.  For large batches the block
+// engine's tensor-pipe updates catch up, so energy-grid calls use the cluster kernels up to a measured batch size
+// (profiles/r02_small_probe.json, GrInt / DOS through the C ABI: N = 112 / 128: 2 x faster up to 36 matrices, even at 324;
+// N = 160 / 192: 2 x faster up to 12, 1.3 x at 36, slower at 108).
+int gnb_small_cluster_max_m(int n) {
+    if (!(g_reg_resident && g_cluster)) return 0;
+    if (g_cluster_max_m > 0) return g_cluster_max_m;
+    return n <= 128 ? 324 : 72;
+}
 // largest n for which a plain inverse (GREEN mode from given matrices) runs on chip
 int gnb_small_inverse_max_n() { return (g_reg_resident && g_cluster) ? GNB_SMALL_CLUSTER_MAX_N : gnb_small_max_n(); }
 
@@ -698,7 +710,8 @@ void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a) {
     if (a.M <= 0) return;
     const int N = a.N;
     if (g_reg_resident && g_cluster && N > GNB_SMALL_REG_MAX_N && N <= GNB_SMALL_CLUSTER_MAX_N && a.mode == GNB_SMALL_GREEN) {
-        launch_reg_cl<4, 4, 16, 2>(st, a);
+        if (N <= 128) launch_reg_cl<4, 4, 16, 2>(st, a);       // 2 CTAs x 16 warps, 4 x 4 complex per thread
+        else launch_reg_cl<6, 6, 8, 4>(st, a);                 // 4 CTAs x 8 warps, 6 x 6 complex per thread (N <= 192)
         return;
     }
     if (g_reg_resident && N <= GNB_SMALL_REG_MAX_N) {

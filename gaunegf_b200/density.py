@@ -9,6 +9,7 @@ from .config import (TEMPERATURE, ADAPTIVE_INTEGRATION_TOL, FERMI_CALCULATION_TO
                      ENERGY_MIN, MAX_CYCLES, MAX_GRID_POINTS)
 from .integrate import GrInt, GrLessInt, GrIntLevels
 from ._native import default_context
+from .utils import inv
 from .sigma_plan import ObjectPlan, DESC, DENSE_CONST
 
 # CONSTANTS (density.py:59-61)
@@ -281,7 +282,7 @@ def calcEmin(F, S, g, tol=FERMI_CALCULATION_TOL, maxN=MAX_CYCLES):
     """Lower integration bound from the DOS tail (density.py:821-834).  The generalised eigenvalue
     estimate is setup-time host linear algebra; the DOS samples run on the GPU."""
     # eigh of inv(S) @ F, exactly as the reference does (it reads the lower triangle only)
-    D = np.linalg.eigvalsh(np.linalg.solve(np.asarray(S), np.eye(len(S))) @ np.asarray(F))
+    D = np.linalg.eigvalsh(inv(np.asarray(S)) @ np.asarray(F))          # S^-1 on the GPU (utils.inv), eigvalsh on the host
     Emin = min(D.real.flatten()) - 5
     counter = 0
     dP = _compute_dos_at_energy(Emin, F, S, g.sigmaTot(Emin))
@@ -362,7 +363,7 @@ def _electrons(P, S, nOrbs=0):
 
 def _mid_gap(F, S, ne, per_cell=1, hermitian=False):
     """sorted real eigenvalues of inv(S) F and the middle of the gap above orbital per_cell*ne"""
-    M = np.linalg.solve(np.asarray(S), np.eye(len(S))) @ np.asarray(F)
+    M = inv(np.asarray(S)) @ np.asarray(F)                              # S^-1 on the GPU (utils.inv)
     orbs = np.sort(np.real(np.linalg.eigvalsh(M) if hermitian else np.linalg.eigvals(M)))
     k = per_cell * int(ne)
     return orbs, (orbs[k - 1] + orbs[k]) / 2

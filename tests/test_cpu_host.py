@@ -260,6 +260,7 @@ def test_n2_fermi_search_host_logic(golden, monkeypatch):
     # the speculative multi-level batches of the adaptive quadrature: each level is its own oracle integral
     monkeypatch.setattr(D, "GrIntLevels", lambda F, S, g, levels: [O.GrInt(F, S, g, E, w) for E, w in levels])
     monkeypatch.setattr(D, "_compute_dos_at_energy", O.compute_dos_at_energy)
+    monkeypatch.setattr(D, "inv", np.linalg.inv)           # utils.inv (GPU) of the eigenvalue estimates
     compare(run_cases(D, surfGTest, None), golden("n2_fermi"), 1e-9)
 
 

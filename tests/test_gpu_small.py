@@ -19,10 +19,10 @@ def _small(ctx, on, reg=1):
 
 
 @pytest.mark.parametrize("reg", [1, 0])
-@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 96, 97, 118, 119, 120, 127, 128, 129])
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 96, 97, 118, 119, 120, 127, 128, 129, 160, 191, 192, 193])
 def test_small_inverse_batch(ctx, n, reg):
-    """utils.inv (utils.py:52-54): reg=1: n <= 96 in the registers of one CTA, n <= 128 in those of a 2-CTA cluster, above
-    on the block engine; reg=0: n <= 119 in shared memory"""
+    """utils.inv (utils.py:52-54): reg=1: n <= 96 in the registers of one CTA, n <= 128 in those of a 2-CTA cluster,
+    n <= 192 in those of a 4-CTA cluster (small batches), above on the block engine; reg=0: n <= 119 in shared memory"""
     rng = np.random.default_rng(n)
     A = rng.standard_normal((9, n, n)) + 1j * rng.standard_normal((9, n, n))
     A[3] = np.triu(A[3]) + np.eye(n) * 1e-3          # forces row exchanges to matter little / much
@@ -52,6 +52,36 @@ def test_cluster_inverse_matches_block_engine(ctx):
             ctx.lib.gnb_dev_set_option(b"small_cluster", 1)
         assert relerr(res[1], res[0]) < 1e-10
         assert relerr(res[1][7] @ A[7], np.eye(n)) < 1e-10
+
+
+@pytest.mark.parametrize("N,nc", [(100, 12), (128, 16), (129, 9), (160, 20), (192, 24)])
+def test_cluster_energy_grid_modes(ctx, N, nc):
+    """96 < N <= 192 on the energy-grid calls (BASELINE north star: small orbital counts stay on chip): Green's function,
+    DOS and the contour integral of a SMALL batch run on the 2- / 4-CTA cluster kernels (assembly + inverse in one
+    launch); same results as the block engine (small_cluster=0) and the oracle; large batches stay on the block engine"""
+    F, S, inds, sig = const_system(ctx, N, nc, seed=N, complex_F=(N == 129))
+    st = sig[0] + sig[1]
+    E = np.concatenate([np.linspace(-1.2, 1.1, 9), [0.3 + 0.7j, -2 + 0.01j]])
+    z, w = sy.contour_points(36, -8.0, 0.0)
+    out = {}
+    try:
+        for cl in (1, 0):
+            ctx.lib.gnb_dev_set_option(b"small_cluster", cl)
+            n0 = ctx.launches
+            res = [ctx.green(E[-4:]), *ctx.dos(E), ctx.gr_int(z, w), ctx.gr_int_dense(z, w, st), ctx.dos_dense(E, st)[0],
+                   ctx.gr_int_seg(z, w, [4, 12, 36])]
+            out[cl] = (res, ctx.launches - n0)
+    finally:
+        ctx.lib.gnb_dev_set_option(b"small_cluster", 1)
+    for a, b in zip(out[1][0], out[0][0]):
+        assert relerr(a, b) < TOL
+    assert out[1][1] < out[0][1] / 4                        # one launch per call instead of the block engine's chain
+    Gref = np.array([O.gr_matrix(st, e, F, S) for e in E[-4:]])
+    assert relerr(out[1][0][0], Gref) < TOL
+    assert relerr(out[1][0][3], O.GrInt(F, S, _ConstG(st), z, w)) < TOL
+    # a batch above the cluster limit takes the block engine and agrees
+    z2, w2 = sy.contour_points(162, -8.0, 0.0)
+    assert relerr(ctx.gr_int(z2, w2), O.GrInt(F, S, _ConstG(st), z2, w2)) < TOL
 
 
 def test_small_singular_raises(ctx):
