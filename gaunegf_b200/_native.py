@@ -33,6 +33,7 @@ SIGNATURES = {
     "gnb_set_timing": (C.c_int, [_vp, C.c_int]),
     "gnb_gemm_stats": (C.c_int, [_vp, _dp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "gnb_set_system": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "gnb_set_system_cached": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "gnb_sigma_clear": (C.c_int, [_vp]),
     "gnb_sigma_set_dense0": (C.c_int, [_vp, _vp, C.c_int]),
     "gnb_sigma_add_const_block": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -115,7 +116,7 @@ class Context:
         self.h = h
         self.device = device
         self.N = 0
-        self._sys_cache = None                 # host copy of the resident F, S (set_system)
+        self.last_system_upload = 3
         self.system_uploads_skipped = 0
         # workspace limit in GiB (default 48 GiB inside the library): GNB_WS_GIB=100
         if os.environ.get("GNB_WS_GIB"):
@@ -183,25 +184,22 @@ class Context:
 
     # -- system / sigma -------------------------------------------------------------------
     def set_system(self, F, S):
-        """F, S of the following calls.  They stay resident in HBM: a call with the same values as the last one
-        (checked against a host copy, a few ms of memcmp at N = 2048) uploads nothing — the reference re-sends F and S
-        on every integrator call (integrate.py:92-95), the adaptive drivers make up to six such calls per integral."""
+        """F, S of the following calls.  They stay resident in HBM: the library compares the arrays with pinned shadow
+        copies (one multi-threaded pass) and uploads only the matrix that changed (gnb_set_system_cached) — the reference
+        re-sends F and S on every integrator call (integrate.py:92-95), the adaptive drivers make up to six such calls
+        per integral, and an SCF step changes F but not S."""
         Fa, Sa = np.asarray(F), np.asarray(S)
         assert Fa.shape == Sa.shape, "F and S must have the same shape"
         assert Fa.ndim == 2 and Fa.shape[0] == Fa.shape[1], "F and S must be square matrices"
-        cached = self._sys_cache
-        if (cached is not None and cached[0].shape == Fa.shape and cached[0].dtype == Fa.dtype
-                and cached[1].dtype == Sa.dtype and np.array_equal(cached[0], Fa) and np.array_equal(cached[1], Sa)):
-            self.system_uploads_skipped += 1
-            return
-        self._sys_cache = None
         Fc, Sc = c128(Fa), c128(Sa)
         self.N = Fc.shape[0]
-        self.check(self.lib.gnb_set_system(self.h, self.N, ptr(Fc), ptr(Sc), HOST))
-        self._sys_cache = (Fa.copy(), Sa.copy())
+        up = C.c_int(0)
+        self.check(self.lib.gnb_set_system_cached(self.h, self.N, ptr(Fc), ptr(Sc), C.byref(up)))
+        self.last_system_upload = up.value                 # bit 0: F was sent, bit 1: S was sent
+        if up.value == 0:
+            self.system_uploads_skipped += 1
 
     def set_system_device(self, N, F_ptr, S_ptr):
-        self._sys_cache = None
         self.N = int(N)
         self.check(self.lib.gnb_set_system(self.h, self.N, _vp(F_ptr), _vp(S_ptr), DEVICE))
 

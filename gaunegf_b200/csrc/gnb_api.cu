@@ -2,6 +2,7 @@
 // Host orchestration only — every floating-point operation of the path runs in the kernels of
 // gnb_elim.cu / gnb_reduce.cu / gnb_sigma.cu / gnb_small.cu.  There is no CPU fallback.
 #include <algorithm>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -118,6 +119,9 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->hF) cudaFreeHost(c->hF);
+    if (c->hS) cudaFreeHost(c->hS);
+    if (c->shadow_ev) cudaEventDestroy(c->shadow_ev);
     delete c;
     return GNB_OK;
 }
@@ -176,15 +180,20 @@ static int put(gnb_ctx* c, DevBuf& buf, const void* src, size_t bytes, int loc) 
     return GNB_OK;
 }
 
-extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* S, int loc) {
-    if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
-    cudaSetDevice(c->device);
+static void system_resized(gnb_ctx* c, int N) {
     if (N != c->N) {                      // a new size invalidates the self-energy description
         retire_contacts(c);
         c->has_sig0 = false;
         c->sig_n = 0; c->sig_spin = 0; c->has_xi = false;
     }
     c->N = N;
+}
+
+extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* S, int loc) {
+    if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
+    cudaSetDevice(c->device);
+    system_resized(c, N);
+    c->shadow_N = 0;                      // the resident copies no longer mirror the host shadows
     const size_t bytes = (size_t)N * N * sizeof(cplx);
     int rc;
     c->real_FS = false;
@@ -196,6 +205,74 @@ extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* 
     if ((rc = put(c, c->dF, F, bytes, loc))) return rc;
     if ((rc = put(c, c->dS, S, bytes, loc))) return rc;
     GNB_CK(cudaStreamSynchronize(c->stream));
+    return GNB_OK;
+}
+
+// One pass over a host matrix against its pinned shadow copy, split over a few host threads: a slice that differs is
+// copied into the shadow and its imaginary parts are tested on the way (the flags of unchanged slices are kept in
+// real_slice from the pass that copied them).  Returns (changed, real).
+static void shadow_pass(const double* src, double* shadow, size_t ndoubles, bool have_shadow, std::vector<char>& real_slice,
+                        bool* changed, bool* real) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int T = (int)std::min<size_t>(std::min(8u, hw), std::max<size_t>(1, ndoubles / (1 << 16)));
+    if ((int)real_slice.size() != T) { real_slice.assign(T, 0); have_shadow = false; }     // another slicing: start over
+    std::vector<char> ch(T, 0);
+    auto work = [&](int t) {
+        const size_t lo = (ndoubles / 2 * t / T) * 2, hi = (ndoubles / 2 * (t + 1) / T) * 2;     // whole complex elements
+        bool c_ = !have_shadow;
+        if (!c_) c_ = memcmp(src + lo, shadow + lo, (hi - lo) * sizeof(double)) != 0;
+        if (c_) {
+            bool r_ = true;
+            double* dst = shadow + lo;
+            const double* s_ = src + lo;
+            for (size_t i = 0; i < hi - lo; i += 2) { dst[i] = s_[i]; dst[i + 1] = s_[i + 1]; r_ &= (s_[i + 1] == 0.0); }
+            real_slice[t] = r_;
+        }
+        ch[t] = c_;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    *changed = false; *real = true;
+    for (int t = 0; t < T; t++) { *changed |= ch[t] != 0; *real &= real_slice[t] != 0; }
+}
+
+// set_system for host arrays that usually repeat: F and S are compared with pinned shadow copies kept by the context and only
+// what changed goes over PCIe (the reference re-sends F and S on every integrator call, integrate.py:92-95; an SCF step
+// changes F but not S).  uploaded: bit 0 = F was sent, bit 1 = S was sent.
+extern "C" int gnb_set_system_cached(gnb_ctx* c, int N, const double* F, const double* S, int* uploaded) {
+    if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
+    cudaSetDevice(c->device);
+    system_resized(c, N);
+    const size_t bytes = (size_t)N * N * sizeof(cplx);
+    if (c->shadow_ev) GNB_CK(cudaEventSynchronize(c->shadow_ev));          // the previous upload has left the shadows
+    else GNB_CK(cudaEventCreateWithFlags(&c->shadow_ev, cudaEventDisableTiming));
+    if (bytes > c->shadow_cap) {
+        if (c->hF) cudaFreeHost(c->hF);
+        if (c->hS) cudaFreeHost(c->hS);
+        c->hF = c->hS = nullptr; c->shadow_cap = 0; c->shadow_N = 0;
+        if (cudaHostAlloc(&c->hF, bytes, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&c->hS, bytes, cudaHostAllocDefault) != cudaSuccess) {      // no pinned memory: plain path
+            cudaGetLastError();
+            if (c->hF) cudaFreeHost(c->hF);
+            c->hF = c->hS = nullptr;
+            if (uploaded) *uploaded = 3;
+            return gnb_set_system(c, N, F, S, GNB_HOST);
+        }
+        c->shadow_cap = bytes;
+    }
+    const bool have = c->shadow_N == N;
+    bool chF, chS, reF, reS;
+    shadow_pass(F, static_cast<double*>(c->hF), 2 * (size_t)N * N, have, c->realF_slice, &chF, &reF);
+    shadow_pass(S, static_cast<double*>(c->hS), 2 * (size_t)N * N, have, c->realS_slice, &chS, &reS);
+    c->shadow_N = N;
+    c->real_FS = reF && reS;
+    int rc;
+    if (chF && (rc = put(c, c->dF, c->hF, bytes, GNB_HOST))) return rc;
+    if (chS && (rc = put(c, c->dS, c->hS, bytes, GNB_HOST))) return rc;
+    if (chF || chS) GNB_CK(cudaEventRecord(c->shadow_ev, c->stream));
+    if (uploaded) *uploaded = (chF ? 1 : 0) | (chS ? 2 : 0);
     return GNB_OK;
 }
 

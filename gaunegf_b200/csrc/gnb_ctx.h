@@ -101,6 +101,9 @@ struct gnb_ctx {
     // memcpy after the synchronisation in end_call, instead of the driver's chunked pageable staging
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     void* pend_dst = nullptr; size_t pend_bytes = 0;
+    // pinned host shadows of the resident F and S (gnb_set_system_cached): shadow_N = size they mirror, 0 = none
+    void* hF = nullptr; void* hS = nullptr; size_t shadow_cap = 0; int shadow_N = 0; cudaEvent_t shadow_ev = nullptr;
+    std::vector<char> realF_slice, realS_slice;      // per host-thread slice: imaginary parts all zero
     // segmented GrInt (gnb_gr_int_seg): host array of cumulative segment ends, valid during the call only
     int seg_n = 0; const int* seg_end = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

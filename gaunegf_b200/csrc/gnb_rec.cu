@@ -62,6 +62,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, int bytes, 
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 
+// bulk copy with an L2 evict-last policy: the packed operands are what the tiles of a matrix share
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_keep(void* dst, const void* src, int bytes, unsigned long long* b, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)), "l"(pol) : "memory");
+}
+// C is read once and written once per launch and nothing re-reads it before it has left the L2 (the working set of a
+// chunk is ~100 x the L2): streaming (evict-first) accesses keep it from displacing the packed operands, which every
+// row / column tile of a matrix re-reads (ncu: DRAM reads of the mid-K launches were 1.6 x their algorithmic bytes)
+__device__ __forceinline__ double2 rk_ldc(const double2* p, int cs) { return cs ? __ldcs(p) : *p; }
+__device__ __forceinline__ void rk_stc(double2* p, double2 v, int cs) { if (cs) __stcs(p, v); else *p = v; }
+
 // ------------------------------------------------------------------------------------------------
 // Rank-K update on packed operands:  C[ilo:ihi, jlo:jhi] -= P[ilo:ihi, klo:khi] * W[klo:khi, jlo:jhi]
 // All bounds are multiples of 32.  CTA tile 64 x 64 anchored at (ilo, jlo); a trailing half tile is masked.
@@ -77,6 +93,7 @@ struct RkGemmArgs {
     int preal;      // the panel operand P is real (imaginary parts exactly zero)
     int nreal;      // columns [0, nreal) of C / W are real (real F, S, E with the contact orbitals ordered last)
     int mixr;       // columns [0, mixr) of C are STORED as real doubles (launches never straddle mixr)
+    int cs;         // streaming (evict-first) accesses to C
 };
 
 #define RK_ST 4
@@ -112,6 +129,7 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
     if (warp == NCW) {
         // ---------------- producer: one lane, two bulk copies per K chunk ----------------
         if (lane != 0) return;
+        const unsigned long long keep = l2_evict_last_policy();
         int q = 0;
         for (int it = 0; it < my_tiles; it++) {
             const int tile = first + it * g0;
@@ -127,8 +145,13 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
                 if (q >= RK_ST) mbar_wait(&empty[s], ((q / RK_ST) - 1) & 1);
                 cplx* Ps = sm + s * RK_STAGE;
                 mbar_expect_tx(&full[s], RK_STAGE * 16);
-                bulk_g2s(Ps, Pb + (long)ch * g.nrb * RK_PBLK, RK_PST * 16, &full[s]);
-                bulk_g2s(Ps + RK_PST, Wb + (long)ch * g.ncb * RK_WBLK, RK_WST * 16, &full[s]);
+                if (g.cs & 2) {
+                    bulk_g2s_keep(Ps, Pb + (long)ch * g.nrb * RK_PBLK, RK_PST * 16, &full[s], keep);
+                    bulk_g2s_keep(Ps + RK_PST, Wb + (long)ch * g.ncb * RK_WBLK, RK_WST * 16, &full[s], keep);
+                } else {
+                    bulk_g2s(Ps, Pb + (long)ch * g.nrb * RK_PBLK, RK_PST * 16, &full[s]);
+                    bulk_g2s(Ps + RK_PST, Wb + (long)ch * g.ncb * RK_WBLK, RK_WST * 16, &full[s]);
+                }
             }
         }
         return;
@@ -247,12 +270,12 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
                 for (int mi = 0; mi < MI; mi++) {
                     double2 v[NI];
 #pragma unroll
-                    for (int ni = 0; ni < NI; ni++) v[ni] = *reinterpret_cast<const double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8);
+                    for (int ni = 0; ni < NI; ni++) v[ni] = rk_ldc(reinterpret_cast<const double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8), g.cs);
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) {
                         v[ni].x -= cre[mi][ni][0]; v[ni].y -= cre[mi][ni][1];
                         cre[mi][ni][0] = cre[mi][ni][1] = 0.0;
-                        *reinterpret_cast<double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8) = v[ni];
+                        rk_stc(reinterpret_cast<double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8), v[ni], g.cs);
                     }
                 }
             } else {
@@ -262,8 +285,8 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
                 cplx v[NI][2];
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) {
-                    v[ni][0] = Cb[(long)(mi * 8) * g.ldc + ni * 8];
-                    v[ni][1] = Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1];
+                    v[ni][0] = rk_ldc(&Cb[(long)(mi * 8) * g.ldc + ni * 8], g.cs);
+                    v[ni][1] = rk_ldc(&Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1], g.cs);
                 }
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) {
@@ -276,8 +299,8 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
                         cre[mi][ni][e] = 0.0; cim[mi][ni][e] = 0.0;
                         if (M3) c3[mi][ni][e] = 0.0;
                     }
-                    Cb[(long)(mi * 8) * g.ldc + ni * 8] = v[ni][0];
-                    Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1] = v[ni][1];
+                    rk_stc(&Cb[(long)(mi * 8) * g.ldc + ni * 8], v[ni][0], g.cs);
+                    rk_stc(&Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1], v[ni][1], g.cs);
                 }
             }
             }
@@ -305,6 +328,7 @@ struct RkGemmRpArgs {
     const void* W; long sW; int ncb;        // doubles (WR = 1) or cplx (WR = 0); sW in elements of that type
     int ilo, ihi, jlo, jhi, klo, khi;
     int mixr;
+    int cs;         // streaming (evict-first) accesses to C
     int jint;       // interleave cheap / expensive column tiles (rk_col_tile)
     int jre;        // WR = 0: columns >= jre hold REAL values in complex storage (the augmented unit columns stay real
                     // while the pivot blocks are real: real multipliers, real pivot-block inverses) - no imaginary DMMAs
@@ -338,6 +362,7 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
 
     if (warp == NCW) {
         if (lane != 0) return;
+        const unsigned long long keep = l2_evict_last_policy();
         int q = 0;
         for (int it = 0; it < my_tiles; it++) {
             const int tile = first + it * g0;
@@ -355,8 +380,13 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
                 if (q >= RK_ST) mbar_wait(&empty[s], ((q / RK_ST) - 1) & 1);
                 unsigned char* st = smem_raw + s * SBYTES;
                 mbar_expect_tx(&full[s], SBYTES);
-                bulk_g2s(st, Pb + (long)ch * g.nrb * RK_PRBLK, PBYTES, &full[s]);
-                bulk_g2s(st + PBYTES, Wb + ch * wstep, WBYTES, &full[s]);
+                if (g.cs & 2) {
+                    bulk_g2s_keep(st, Pb + (long)ch * g.nrb * RK_PRBLK, PBYTES, &full[s], keep);
+                    bulk_g2s_keep(st + PBYTES, Wb + ch * wstep, WBYTES, &full[s], keep);
+                } else {
+                    bulk_g2s(st, Pb + (long)ch * g.nrb * RK_PRBLK, PBYTES, &full[s]);
+                    bulk_g2s(st + PBYTES, Wb + ch * wstep, WBYTES, &full[s]);
+                }
             }
         }
         return;
@@ -447,12 +477,12 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
                 for (int mi = 0; mi < MI; mi++) {
                     double2 v[NI];
 #pragma unroll
-                    for (int ni = 0; ni < NI; ni++) v[ni] = *reinterpret_cast<const double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8);
+                    for (int ni = 0; ni < NI; ni++) v[ni] = rk_ldc(reinterpret_cast<const double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8), g.cs);
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) {
                         v[ni].x -= cre[mi][ni][0]; v[ni].y -= cre[mi][ni][1];
                         cre[mi][ni][0] = cre[mi][ni][1] = 0.0;
-                        *reinterpret_cast<double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8) = v[ni];
+                        rk_stc(reinterpret_cast<double2*>(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8), v[ni], g.cs);
                     }
                 }
             } else {
@@ -462,8 +492,8 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
                     cplx v[NI][2];
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) {
-                        v[ni][0] = Cb[(long)(mi * 8) * g.ldc + ni * 8];
-                        v[ni][1] = Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1];
+                        v[ni][0] = rk_ldc(&Cb[(long)(mi * 8) * g.ldc + ni * 8], g.cs);
+                        v[ni][1] = rk_ldc(&Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1], g.cs);
                     }
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) {
@@ -472,8 +502,8 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
                             v[ni][e].x -= cre[mi][ni][e]; v[ni][e].y -= cim[WR ? 0 : mi][WR ? 0 : ni][e];
                             cre[mi][ni][e] = 0.0; cim[WR ? 0 : mi][WR ? 0 : ni][e] = 0.0;
                         }
-                        Cb[(long)(mi * 8) * g.ldc + ni * 8] = v[ni][0];
-                        Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1] = v[ni][1];
+                        rk_stc(&Cb[(long)(mi * 8) * g.ldc + ni * 8], v[ni][0], g.cs);
+                        rk_stc(&Cb[(long)(mi * 8) * g.ldc + ni * 8 + 1], v[ni][1], g.cs);
                     }
                 }
             }
@@ -1029,6 +1059,8 @@ static int g_rk_real = 1;        // skip the imaginary DMMAs where the operands 
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static int g_rk_wskip = 1;       // forward-W: skip the dead write of W into A (FORWARD mode, rows above back_row_lo)
+static int g_rk_cs = 0;          // bit 0: streaming (evict-first) read-modify-write of C in the rank-K kernels, bit 1: L2 evict-last operand
+                                 // copies.  Measured: no effect on the step (59.23 / 59.28 / 59.22 / 59.31 ms for 0 / 1 / 2 / 3), so off
 static int g_rk_augreal = 1;     // FORWARD: real arithmetic on the augmented columns while the pivot blocks are real
 static int g_rk_tcap_k = 0;      // > 0: a rank-K CTA works on at most max(1, tcap_k / K) tiles (short-lived CTAs), 0: persistent
 static int g_rk_lowprio = 0;     // rank-K launches carry the lowest launch priority (the sub-batch streams are high priority)
@@ -1076,6 +1108,7 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_tcap_k")) g_rk_tcap_k = value;
     else if (!strcmp(name, "rk_wskip")) g_rk_wskip = value;
     else if (!strcmp(name, "rk_augreal")) g_rk_augreal = value;
+    else if (!strcmp(name, "rk_cs")) g_rk_cs = value;
     else if (!strcmp(name, "rk_lowprio")) g_rk_lowprio = value;
     else if (!strcmp(name, "rk_sms") && value > 0) g_rk_sms = value;      // CTAs of the persistent rank-K kernels
 }
@@ -1169,6 +1202,7 @@ struct Rec {
             r.P = ws.PpkR; r.sP = ws.stridePkR; r.nrb = nrb;
             r.W = wr ? (const void*)ws.WpkR : (const void*)ws.Wpk; r.sW = wr ? ws.strideWkR : ws.strideWk; r.ncb = ncb;
             r.ilo = ilo; r.ihi = ihi; r.jlo = jlo; r.jhi = jhi; r.klo = klo; r.khi = khi; r.mixr = mixr;
+            r.cs = g_rk_cs;
             // FORWARD: the augmented unit columns (from column N on) are real-valued as long as the pivot blocks are
             r.jre = (!jordan && g_rk_augreal && khi <= ws.nreal) ? N : (1 << 30);
             const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);
@@ -1206,6 +1240,7 @@ struct Rec {
         g.nreal = g_rk_real ? ws.nreal : 0;
         g.preal = (g.nreal > 0 && khi <= g.nreal) ? 1 : 0;
         g.mixr = mixr;
+        g.cs = g_rk_cs;
         const bool strip = g_rk_strip && (jhi - jlo == 32) && (ihi - ilo >= 128);     // 128 x 32 tiles for 32-column strips
         const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
         const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);

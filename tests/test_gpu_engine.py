@@ -126,6 +126,41 @@ def test_segmented_gr_int_equals_separate_calls(ctx, N, nc):
         ctx.gr_int_seg(z, w, [4, 2, 18])
 
 
+def test_set_system_cached_uploads_only_what_changed(ctx):
+    """gnb_set_system_cached: F and S are compared with the context's pinned shadows; an in-place change of either is
+    seen, only the changed matrix is re-sent, and the results follow the new values"""
+    N, nc = 70, 6
+    F, S, inds, sig = const_system(ctx, N, nc, seed=11)
+    st = sig[0] + sig[1]
+    E = np.array([0.13, -0.4 + 0.2j])
+    ctx.set_system(F, S)
+    assert ctx.last_system_upload == 0                     # const_system has just installed the same arrays
+    F2 = np.array(F, dtype=complex)
+    F2[5, 7] += 0.01; F2[7, 5] += 0.01
+    ctx.set_system(F2, S)
+    assert ctx.last_system_upload == 1
+    G = ctx.green(E)
+    assert relerr(G, np.array([O.gr_matrix(st, e, F2, S) for e in E])) < TOL
+    F2[0, 0] += 1e-13                                      # in-place change of one entry of the caller's array
+    ctx.set_system(F2, S)
+    assert ctx.last_system_upload == 1
+    S2 = np.array(S, dtype=complex)
+    S2[3, 3] *= 1.001
+    ctx.set_system(F2, S2)
+    assert ctx.last_system_upload == 2
+    assert relerr(ctx.green(E), np.array([O.gr_matrix(st, e, F2, S2) for e in E])) < TOL
+    Fc = F2 + 0.003j * (np.triu(np.ones((N, N)), 1) - np.tril(np.ones((N, N)), -1))      # complex Hermitian F
+    ctx.set_system(Fc, S2)
+    Er = np.linspace(-0.3, 0.3, 5)
+    g1 = 1j * (sig[0] - sig[0].conj().T); g2 = 1j * (sig[1] - sig[1].conj().T)
+    assert relerr(ctx.transmission(Er, 0, -1), np.array([O.transmission_restricted(e, Fc, S2, st, g1, g2) for e in Er])) < TOL
+    ctx.set_system(F2, S2)                                 # back to real input: the real-structure shortcut applies again
+    assert relerr(ctx.transmission(Er, 0, -1), np.array([O.transmission_restricted(e, F2, S2, st, g1, g2) for e in Er])) < TOL
+    Fs, Ss = sy.hermitian_pair(40, seed=2)
+    ctx.set_system(Fs, Ss)
+    assert ctx.last_system_upload == 3 and ctx.N == 40
+
+
 def test_chunking_matches_single_pass(ctx):
     F, S, inds, sig = const_system(ctx, 96, 8, seed=9)
     z, w = sy.contour_points(54, -12.0, 0.0)

@@ -15,7 +15,6 @@ for N, nc in ((128, 8), (160, 8), (192, 16), (256, 16), (320, 16), (384, 16), (5
     for tw, f32 in ((0, 1), (3, 1), (1, 1), (2, 1), (1, 0)):
         ctx.lib.gnb_dev_set_option(b"tourn_warp", tw)
         ctx.lib.gnb_dev_set_option(b"tourn_fp32", f32)
-        ctx._sys_cache = None
         ctx.set_system(F, S); ctx.sigma_clear()
         ctx.sigma_add_const_block(np.arange(nc), np.diag(s1[:nc]))
         ctx.sigma_add_const_block(np.arange(N - nc, N), np.diag(s2[N - nc:]))
