@@ -33,7 +33,7 @@ SIGNATURES = {
     "gnb_set_timing": (C.c_int, [_vp, C.c_int]),
     "gnb_gemm_stats": (C.c_int, [_vp, _dp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "gnb_set_system": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
-    "gnb_set_system_cached": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "gnb_set_system_cached": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp]),
     "gnb_sigma_clear": (C.c_int, [_vp]),
     "gnb_sigma_set_dense0": (C.c_int, [_vp, _vp, C.c_int]),
     "gnb_sigma_add_const_block": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -191,10 +191,14 @@ class Context:
         Fa, Sa = np.asarray(F), np.asarray(S)
         assert Fa.shape == Sa.shape, "F and S must have the same shape"
         assert Fa.ndim == 2 and Fa.shape[0] == Fa.shape[1], "F and S must be square matrices"
-        Fc, Sc = c128(Fa), c128(Sa)
+        def as_input(a):        # real float64 arrays go to the library as they are (no complex copy per call)
+            if a.dtype == np.float64 and a.flags.c_contiguous:
+                return a, 1
+            return c128(a), 0
+        (Fc, fr), (Sc, sr) = as_input(Fa), as_input(Sa)
         self.N = Fc.shape[0]
         up = C.c_int(0)
-        self.check(self.lib.gnb_set_system_cached(self.h, self.N, ptr(Fc), ptr(Sc), C.byref(up)))
+        self.check(self.lib.gnb_set_system_cached(self.h, self.N, ptr(Fc), ptr(Sc), fr | (sr << 1), C.byref(up)))
         self.last_system_upload = up.value                 # bit 0: F was sent, bit 1: S was sent
         if up.value == 0:
             self.system_uploads_skipped += 1

@@ -211,8 +211,9 @@ extern "C" int gnb_set_system(gnb_ctx* c, int N, const double* F, const double* 
 // One pass over a host matrix against its pinned shadow copy, split over a few host threads: a slice that differs is
 // copied into the shadow and its imaginary parts are tested on the way (the flags of unchanged slices are kept in
 // real_slice from the pass that copied them).  Returns (changed, real).
-static void shadow_pass(const double* src, double* shadow, size_t ndoubles, bool have_shadow, std::vector<char>& real_slice,
-                        bool* changed, bool* real) {
+// src_real: the caller's array holds N^2 real doubles (the shadow and the device copy are always complex128).
+static void shadow_pass(const double* src, bool src_real, double* shadow, size_t ndoubles, bool have_shadow,
+                        std::vector<char>& real_slice, bool* changed, bool* real) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const int T = (int)std::min<size_t>(std::min(8u, hw), std::max<size_t>(1, ndoubles / (1 << 16)));
     if ((int)real_slice.size() != T) { real_slice.assign(T, 0); have_shadow = false; }     // another slicing: start over
@@ -220,13 +221,27 @@ static void shadow_pass(const double* src, double* shadow, size_t ndoubles, bool
     auto work = [&](int t) {
         const size_t lo = (ndoubles / 2 * t / T) * 2, hi = (ndoubles / 2 * (t + 1) / T) * 2;     // whole complex elements
         bool c_ = !have_shadow;
-        if (!c_) c_ = memcmp(src + lo, shadow + lo, (hi - lo) * sizeof(double)) != 0;
-        if (c_) {
-            bool r_ = true;
-            double* dst = shadow + lo;
+        double* dst = shadow + lo;
+        if (src_real) {
+            const double* s_ = src + lo / 2;
+            const size_t n = (hi - lo) / 2;
+            if (!c_) {
+                bool diff = false;
+                for (size_t i = 0; i < n; i++) diff |= (dst[2 * i] != s_[i]) | (dst[2 * i + 1] != 0.0);
+                c_ = diff;
+            }
+            if (c_) {
+                for (size_t i = 0; i < n; i++) { dst[2 * i] = s_[i]; dst[2 * i + 1] = 0.0; }
+                real_slice[t] = 1;
+            }
+        } else {
             const double* s_ = src + lo;
-            for (size_t i = 0; i < hi - lo; i += 2) { dst[i] = s_[i]; dst[i + 1] = s_[i + 1]; r_ &= (s_[i + 1] == 0.0); }
-            real_slice[t] = r_;
+            if (!c_) c_ = memcmp(s_, dst, (hi - lo) * sizeof(double)) != 0;
+            if (c_) {
+                bool r_ = true;
+                for (size_t i = 0; i < hi - lo; i += 2) { dst[i] = s_[i]; dst[i + 1] = s_[i + 1]; r_ &= (s_[i + 1] == 0.0); }
+                real_slice[t] = r_;
+            }
         }
         ch[t] = c_;
     };
@@ -240,8 +255,9 @@ static void shadow_pass(const double* src, double* shadow, size_t ndoubles, bool
 
 // set_system for host arrays that usually repeat: F and S are compared with pinned shadow copies kept by the context and only
 // what changed goes over PCIe (the reference re-sends F and S on every integrator call, integrate.py:92-95; an SCF step
-// changes F but not S).  uploaded: bit 0 = F was sent, bit 1 = S was sent.
-extern "C" int gnb_set_system_cached(gnb_ctx* c, int N, const double* F, const double* S, int* uploaded) {
+// changes F but not S).  real_input: bit 0 = F holds N^2 real doubles, bit 1 = S does (else complex128).
+// uploaded: bit 0 = F was sent, bit 1 = S was sent.
+extern "C" int gnb_set_system_cached(gnb_ctx* c, int N, const double* F, const double* S, int real_input, int* uploaded) {
     if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
     cudaSetDevice(c->device);
     system_resized(c, N);
@@ -258,14 +274,15 @@ extern "C" int gnb_set_system_cached(gnb_ctx* c, int N, const double* F, const d
             if (c->hF) cudaFreeHost(c->hF);
             c->hF = c->hS = nullptr;
             if (uploaded) *uploaded = 3;
+            if (real_input) return gnb_fail(c, GNB_ERR_NOMEM, "set_system_cached: no pinned memory for the shadow copies");
             return gnb_set_system(c, N, F, S, GNB_HOST);
         }
         c->shadow_cap = bytes;
     }
     const bool have = c->shadow_N == N;
     bool chF, chS, reF, reS;
-    shadow_pass(F, static_cast<double*>(c->hF), 2 * (size_t)N * N, have, c->realF_slice, &chF, &reF);
-    shadow_pass(S, static_cast<double*>(c->hS), 2 * (size_t)N * N, have, c->realS_slice, &chS, &reS);
+    shadow_pass(F, (real_input & 1) != 0, static_cast<double*>(c->hF), 2 * (size_t)N * N, have, c->realF_slice, &chF, &reF);
+    shadow_pass(S, (real_input & 2) != 0, static_cast<double*>(c->hS), 2 * (size_t)N * N, have, c->realS_slice, &chS, &reS);
     c->shadow_N = N;
     c->real_FS = reF && reS;
     int rc;

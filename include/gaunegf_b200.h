@@ -67,8 +67,9 @@ int gnb_set_system(gnb_ctx* ctx, int N, const double* F, const double* S, int lo
 /* The same for HOST arrays that usually repeat between calls (the reference passes F and S to every integrator call,
  * integrate.py:92-95; an SCF step changes F but not S): both are compared with pinned shadow copies kept by the context
  * (one multi-threaded pass that also detects real-valued input) and only the matrix that changed goes over PCIe.  F and S
- * are fully consumed when the call returns.  uploaded (may be NULL): bit 0 = F was sent, bit 1 = S was sent. */
-int gnb_set_system_cached(gnb_ctx* ctx, int N, const double* F, const double* S, int* uploaded);
+ * are fully consumed when the call returns.  real_input: bit 0 = F holds N*N real doubles, bit 1 = S does (restricted-spin
+ * Gaussian output; otherwise complex128).  uploaded (may be NULL): bit 0 = F was sent, bit 1 = S was sent. */
+int gnb_set_system_cached(gnb_ctx* ctx, int N, const double* F, const double* S, int real_input, int* uploaded);
 
 /* ---- self-energy description ------------------------------------------------------------------
  * Sigma_tot(E) = Sigma0 + sum_c scatter(inds_c, blk_c(E)).  Contacts are numbered 0..nc-1; the
