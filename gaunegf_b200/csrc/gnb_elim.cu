@@ -589,7 +589,8 @@ __device__ __forceinline__ void tw_gepp(typename T::C (&a)[NR][32], const int (&
 // Final round of a real panel, ONE warp: explicit inverse of the pivot block (chosen rows s_win[0 .. nfin), pivot order) by
 // in-place Gauss-Jordan without further pivoting, then the net row moves and the permutation update (as in k_tourn).
 __device__ __forceinline__ void tw_finish_real(const cplx* __restrict__ Ab, int ld, int c0, int mixr, const int* s_win, int nfin,
-                                               double* s_gj, cplx* __restrict__ LUb, int* __restrict__ mvb, int* pb, int lane) {
+                                               double* s_gj, cplx* __restrict__ LUb, int* __restrict__ mvb, int* pb, int lane,
+                                               int* info = nullptr) {
     constexpr int w = GNB_NB;
     // ---- final round, warp 0: explicit inverse of the pivot block (chosen rows, pivot order) by in-place Gauss-Jordan
     // without further pivoting (the row order IS the partial-pivoting order); lane r holds row r.  Real panels only
@@ -627,6 +628,7 @@ __device__ __forceinline__ void tw_finish_real(const cplx* __restrict__ Ab, int 
             {
                 const double2 pv = *reinterpret_cast<const double2*>(&s_gj[0]);
                 rk = pv.x != 0.0 ? 1.0 / pv.x : 0.0;
+                if (info && pv.x == 0.0 && lane == 0) *info = 1;       // exactly singular pivot (when the order came from FP32 rounds)
                 const double p1 = pv.y * rk;                           // scaled pivot row
                 m[0] = isp ? p1 : fma(-f, p1, m[1]);
             }
@@ -772,7 +774,7 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     __shared__ __align__(16) C s_prow_all[NW][32];
     __shared__ int s_list_all[NW][2][4][32];
-    __shared__ __align__(16) double s_gj_all[F64 ? NW : 1][32];
+    __shared__ __align__(16) double s_gj_all[NW][32];
     const int gid = blockIdx.x * NW + warp;
     if (gid >= total_groups) return;                         // warp-uniform; no CTA barrier below
     const int b = gid / grp, g = gid - b * grp;
@@ -797,7 +799,7 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
             const int nsel = min(w, nwr);
             lens |= (unsigned)nsel << (8 * q);
             tw_load<T, 4>(a4, rows4, Ab, ld, c0, mixr);
-            tw_gepp<T, F64, 4>(a4, rows4, nsel, s_prow, s_list[0][q], lane, final_round && nl == 1, info);
+            tw_gepp<T, F64, 4>(a4, rows4, nsel, s_prow, s_list[0][q], lane, F64 && final_round && nl == 1, info);
             __syncwarp();
         }
         level = 1; q = 0;
@@ -816,7 +818,7 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
                 rows[rr] = i < ncand ? (cand_in ? cand_in[(long)b * cand_in_stride + base + i] : r0 + base + i) : -1;
             }
             nsel = min(w, nwr);
-            flag = final_round && nl == 1;
+            flag = F64 && final_round && nl == 1;
             lens_next |= (unsigned)nsel << (8 * q);
         } else {
             const int la = 2 * q, lb = 2 * q + 1;
@@ -830,7 +832,7 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
                     rows[rr] = i < na ? s_list[cur][la][i] : (i < na + nb_ ? s_list[cur][lb][i - na] : -1);
                 }
                 nsel = min(w, na + nb_);
-                flag = final_round && nn == 1;
+                flag = F64 && final_round && nn == 1;
             }
             lens_next |= (unsigned)min(w, na + nb_) << (8 * q);
         }
@@ -848,14 +850,15 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
     }
     const int nfin = lens & 255;
     const int* s_win = s_list[cur][0];
-    if (!final_round || !F64) {
+    if (!final_round) {
         if (lane < nfin) cand_out[(long)b * cand_out_stride + g * w + lane] = s_win[lane];
         return;
     }
-    if constexpr (F64) {
-        tw_finish_real(Ab, ld, c0, mixr, s_win, nfin, s_gj_all[warp], LU + (long)b * GNB_NB * GNB_NB,
-                       moves + (long)b * GNB_MOVES_STRIDE, perm ? perm + (long)b * perm_stride : nullptr, lane);
-    }
+    // final round: the pivot block is inverted in FP64 on the original entries.  With T = float the pivot ORDER comes from
+    // single-precision eliminations (a near-tie may resolve differently than in FP64: a threshold-pivoting order with
+    // threshold 1 - 1e-7, as stable as partial pivoting); exact singularity is then detected by the FP64 Gauss-Jordan
+    tw_finish_real(Ab, ld, c0, mixr, s_win, nfin, s_gj_all[warp], LU + (long)b * GNB_NB * GNB_NB,
+                   moves + (long)b * GNB_MOVES_STRIDE, perm ? perm + (long)b * perm_stride : nullptr, lane, F64 ? nullptr : info);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1359,7 +1362,7 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
 static int g_tourn_fp32 = 1;      // nominating (non-final) tournament rounds in single precision
 void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
-static int g_tourn_warp = 25;     // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
+static int g_tourn_warp = 57;     // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
 void gnb_set_tourn_warp(int on) { g_tourn_warp = on; }
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
@@ -1380,7 +1383,9 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         // 1 -> +1.7 %; 2 -> -1.8 % (44 us against 51 us alone, but its 224 registers keep it from sharing an SM with the
         // other sub-batch's rank-K CTAs); 4 -> -4 % (252 registers, 2 CTAs per SM); 8 = warp-independent k_tournq for every
         // round of a real panel (takes precedence over 1 and 2): +3 %; 16 = four candidate rows per lane at level 0 of the
-        // FP32 nominating rounds of k_tournq (3 sequential eliminations per 256-row group instead of 7): +1.8 %.  Default: 25.
+        // FP32 nominating rounds of k_tournq (3 sequential eliminations per 256-row group instead of 7): +1.8 %; 32 = the
+        // final round takes its pivot ORDER from FP32 eliminations too (4 rows per lane: one elimination for <= 128 nominees)
+        // and inverts the pivot block in FP64 (2 phases instead of 4): +1.1 % (N = 512: +2.9 %).  Default: 57.
         const bool use_w = warp_ok && (fin ? (real_panel && (g_tourn_warp & 2))
                                            : (real_panel ? (g_tourn_warp & 1) != 0 : (f32 && (g_tourn_warp & 4))));
         if (warp_ok && real_panel && (g_tourn_warp & 8)) {    // warp-independent kernel: one warp per 256-row group / matrix
@@ -1396,6 +1401,9 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
                 else
                     k_tournq<TTR<double>, true, 2, 4, 2><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
                                                                                        cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
+            } else if (f32 && (g_tourn_warp & 32)) {        // final round: FP32 pivot order (4 rows per lane), FP64 inverse
+                k_tournq<TTR<float>, false, 2, 6, 4><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                     cout, cand_stride, 1, LU, moves, perm, perm_stride, info, mixr);
             } else {
                 k_tournq<TTR<double>, true, 2, 4, 2><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
                                                                                    cout, cand_stride, 1, LU, moves, perm, perm_stride, info, mixr);
