@@ -23,12 +23,14 @@ int gnb_cuda_fail(gnb_ctx* c, cudaError_t e, const char* where) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static int g_engine_rec = 1;      // 1: recursive multi-level engine (gnb_rec.cu), 0: two-level engine (gnb_elim.cu)
+static int g_gless_mixed = 1;     // GrLessInt: mixed layout too (back-substitution with a real-stored operand)
 static int g_mixed_layout = 1;    // transmission: store the real columns as doubles (mixed layout, gnb_rec.cu)
 static int g_contacts_last = 1;   // transmission: reorder the contact orbitals to the end (short back-substitution)
 static int g_chain_joint = 1;     // chain contacts with equal block size / iteration parameters share one fixed-point batch
 static int g_small = 1;           // N <= gnb_small_max_n(): one CTA per energy, matrix on chip (gnb_small.cu)
 int gnb_small_enabled() { return g_small; }
 static int g_rec_streams = 2;     // independent sub-batches (streams) per chunk in the recursive engine
+static int g_rec_stream_min_m = 64;   // a sub-batch stream gets at least this many matrices
 static int g_rec_stagger_us = 0;  // sub-batch s starts s * this many microseconds late (phase offset between the streams)
 __global__ void k_stagger(long ns) {
     unsigned long long t0, t;
@@ -152,6 +154,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "engine_rec")) g_engine_rec = value;
     else if (!strcmp(name, "rec_streams")) g_rec_streams = value;
     else if (!strcmp(name, "rec_stagger_us")) g_rec_stagger_us = value;
+    else if (!strcmp(name, "rec_stream_min_m") && value > 0) g_rec_stream_min_m = value;
     else if (!strcmp(name, "small_fused")) g_small = value;
     else if (!strcmp(name, "chain_joint")) g_chain_joint = value;
     else if (!strcmp(name, "chain_compact")) gnb_chain_set_compact(value);
@@ -161,6 +164,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "small_wide")) gnb_small_set_wide(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;
+    else if (!strcmp(name, "gless_mixed")) g_gless_mixed = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
     else if (!strcmp(name, "tourn_warp")) gnb_set_tourn_warp(value);
     else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
@@ -468,6 +472,22 @@ static int result_to_host(gnb_ctx* c, void* dst, const void* src, size_t bytes) 
     return GNB_OK;
 }
 
+// pinned landing buffer -> caller's (pageable) array; a few host threads for the N x N results of large systems
+// (one thread copies ~10 GB/s: 7 ms for the 67 MB of N = 2048)
+static void host_copy(void* dst, const void* src, size_t bytes) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int T = (int)std::min<size_t>(std::min(4u, hw), std::max<size_t>(1, bytes >> 22));
+    if (T <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    auto work = [&](int t) {
+        const size_t lo = bytes / T * t, hi = t == T - 1 ? bytes : bytes / T * (t + 1);
+        memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+    };
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
 static int end_call(gnb_ctx* c) {
     int info = 0;
     void* pend_dst = c->pend_dst; const size_t pend_bytes = c->pend_bytes;
@@ -475,7 +495,7 @@ static int end_call(gnb_ctx* c) {
     GNB_CK(cudaMemcpyAsync(&info, c->info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     GNB_CK(cudaStreamSynchronize(c->stream));
     GNB_CK(cudaGetLastError());
-    if (pend_dst) memcpy(pend_dst, c->h_pin, pend_bytes);
+    if (pend_dst) host_copy(pend_dst, c->h_pin, pend_bytes);
     if (c->timing) c->gemm_timer.resolve();
     if (info) return gnb_fail(c, GNB_ERR_SINGULAR, "Singular matrix");
     return GNB_OK;
@@ -596,7 +616,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
         // Independent sub-batches on separate streams: the latency-bound panel kernels of one sub-batch
         // overlap the tensor-pipe-bound rank-K updates of the others.
         int S = std::max(1, std::min(g_rec_streams, GNB_MAX_SUBSTREAMS));
-        S = std::min(S, std::max(1, M / 64));
+        S = std::min(S, std::max(1, M / g_rec_stream_min_m));
         if (c->timing) S = 1;                   // per-launch event timing of the rank-K kernel needs it alone on the GPU
         if (S <= 1) {
             c->launches += gnb_eliminate_rec(c->stream, M, L.Np, L.naugp, A, strideA, L.ld, jordan, w);
@@ -1245,7 +1265,7 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
     }
     const int naug = (int)cols.size();
     Lay L = make_layout(N, naug);
-    const int ld = L.ld, Np = L.Np;
+    const int Np = L.Np;
     if ((rc = put(c, c->cols, cols.data(), cols.size() * sizeof(int), GNB_HOST))) return rc;
     // All-contacts-last ordering (as in gnb_transmission): with real F, S and real energies every column left of
     // the contact orbitals stays real through the elimination.  The result is formed in the permuted order and
@@ -1267,8 +1287,12 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
             if ((rc = put(c, c->in_stage, pinv.data(), (size_t)N * sizeof(int), GNB_HOST))) return rc;
             d_pi = c->rows.as<int>(); d_pinv = c->in_stage.as<int>();
             L.nreal = N - ncall;
+            // real columns stored as doubles (as in gnb_transmission); the back-substitution reads the real-stored part
+            // of the normalised rows through k_gemm's real-operand path
+            if (g_mixed_layout && g_gless_mixed && L.nreal >= 64) L.use_mixed_layout();
         }
     }
+    const int ld = L.ld;
     cplx* d_out = nullptr;
     if ((rc = get_out(c, out, loc, &d_out))) return rc;
     cplx* d_acc = d_out;                         // accumulation target (permuted order when d_pi is set)
@@ -1282,11 +1306,11 @@ extern "C" int gnb_gless_int(gnb_ctx* c, int M, const double* E, const double* w
         if ((rc = put_chunk_scalars(c, E, w, k0, m))) return rc;
         const cplx* dE = c->dE.as<cplx>();
         GNB_CK(c->A.ensure((size_t)m * Np * ld * sizeof(cplx)));
-        cplx* A = c->A.as<cplx>();
+        cplx* A = L.logical(c->A.p);
         const long strideA = (long)Np * ld;
         if ((rc = prepare_sigma(c, m, dE, 1))) return rc;
         if ((rc = pad_chunk(c, m, L, A))) return rc;
-        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr, d_pi, d_pinv))) return rc;
+        if ((rc = assemble_chunk(c, m, dE, A, strideA, ld, true, nullptr, nullptr, d_pi, d_pinv, L.mixr))) return rc;
         gnb_launch_set_aug(c->stream, m, A, strideA, ld, N, L.xoff, c->cols.as<int>(), naug, d_pinv);
         c->launches++;
         if ((rc = run_eliminate(c, m, L, A, 0))) return rc;

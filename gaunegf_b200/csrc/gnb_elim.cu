@@ -1031,7 +1031,14 @@ __global__ void __launch_bounds__(BM * 4, BM == 64 ? 2 : 4) k_gemm(GnbGemmArgs g
                 const int idx = tid + q * NT;
                 const int r = idx / GM_KC, k = idx - r * GM_KC;
                 cplx v = cmake(0.0, 0.0);
-                if (i0 + r < g.ihi && k0 + k < g.kdim) v = cmul(sc, Pb[(long)(i0 + r) * g.ldp + k0 + k]);
+                if (i0 + r < g.ihi && k0 + k < g.kdim) {
+                    if (g.Pr) {                                  // real-stored operand (mixed layout)
+                        const double pr = g.Pr[(long)b * g.stridePr + (long)(i0 + r) * g.ldpr + k0 + k];
+                        v = cmake(sc.x * pr, sc.y * pr);
+                    } else {
+                        v = cmul(sc, Pb[(long)(i0 + r) * g.ldp + k0 + k]);
+                    }
+                }
                 Ps[r * GM_PS + k] = v;
             }
             if (WT) {
@@ -1338,7 +1345,7 @@ void gnb_launch_pad_diag(cudaStream_t st, int M, cplx* A, long strideA, int ld, 
 void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt, bool batchk) {
     const int ni = g.ihi - g.ilo, nj = g.jhi - g.jlo;
     if (ni <= 0 || nj <= 0 || g.kdim <= 0 || nbatch <= 0) return;
-    if (g_gemm_pipe && !wt && !batchk && g.kdim <= 4 * GM_KC && !g.wscale) {
+    if (g_gemm_pipe && !wt && !batchk && g.kdim <= 4 * GM_KC && !g.wscale && !g.Pr) {
         const int nti = cdiv_i(ni, GP_BM), ntj = cdiv_i(nj, GP_BN);
         const long total = (long)nbatch * nti * ntj;
         if (total < (1L << 31)) {

@@ -18,6 +18,8 @@ struct GnbGemmArgs {
     int zero_init, plus;         // C = 0 before accumulation; C += (plus) or C -= (minus)
     int nbatch_k;                // BATCHK: number of batches folded into K
     const cplx* wscale;          // optional per-batch complex scale applied to P
+    const double* Pr;            // optional: P given as REAL doubles (mixed layout of gnb_rec.cu), replaces P; k_gemm only
+    long stridePr; int ldpr;     // batch stride / row stride of Pr in doubles
 };
 
 // Optional per-launch CUDA-event timing of the rank-K update kernel (bench.py's roofline leg).

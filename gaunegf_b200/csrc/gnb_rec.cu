@@ -1411,18 +1411,28 @@ struct Rec {
         backsub(c0 + h, w - h, row_lo);
         const int ilo = std::max(c0, row_lo);
         if (ilo >= c0 + h) return;
-        GnbGemmArgs g{};
-        g.C = A + N; g.strideC = strideA; g.ldc = ld;
-        g.P = A + c0 + h; g.strideP = strideA; g.ldp = ld;
-        g.W = A + (long)(c0 + h) * ld + N; g.strideW = strideA; g.ldw = ld;
-        g.ilo = ilo; g.ihi = c0 + h; g.jlo = 0; g.jhi = naug; g.kdim = w - h;
-        g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
-        {
+        // K = columns [c0 + h, c0 + w): the part left of mixr is stored as real doubles (mixed layout), the rest complex
+        const int ksplit = mixr > 0 ? std::min(std::max(c0 + h, mixr), c0 + w) : c0 + h;
+        for (int part = 0; part < 2; part++) {
+            const int klo_ = part == 0 ? c0 + h : ksplit, khi_ = part == 0 ? ksplit : c0 + w;
+            if (khi_ <= klo_) continue;
+            GnbGemmArgs g{};
+            g.C = A + N; g.strideC = strideA; g.ldc = ld;
+            g.P = A + klo_; g.strideP = strideA; g.ldp = ld;
+            if (part == 0 && mixr > 0) {
+                g.Pr = reinterpret_cast<const double*>(reinterpret_cast<const char*>(A) + (size_t)mixr * 8) + klo_;
+                g.stridePr = 2 * strideA; g.ldpr = 2 * ld;
+            }
+            g.W = A + (long)klo_ * ld + N; g.strideW = strideA; g.ldw = ld;
+            g.ilo = ilo; g.ihi = c0 + h; g.jlo = 0; g.jhi = naug; g.kdim = khi_ - klo_;
+            g.skip_lo = g.skip_hi = -1; g.zero_init = 0; g.plus = 0; g.wscale = nullptr;
             TraceScope ts("backsub", st, M);
             if (ws.timer) ws.timer->begin(st);
             gnb_launch_gemm(st, g, M, false, false);
-            if (ws.timer) ws.timer->end(st, 8.0 * (double)(c0 + h - ilo) * (double)naug * g.kdim * M);
-            if (ws.flops_acc) *ws.flops_acc += 8.0 * (double)(c0 + h - ilo) * (double)naug * g.kdim * M;
+            // real P x complex W: 4 flops per (row, column, k)
+            const double fl = (g.Pr ? 4.0 : 8.0) * (double)(c0 + h - ilo) * (double)naug * g.kdim * M;
+            if (ws.timer) ws.timer->end(st, fl);
+            if (ws.flops_acc) *ws.flops_acc += fl;
             launches++;
         }
         backsub(c0, h, row_lo);
