@@ -11,6 +11,7 @@
 // has no f64 kind).  All energies of a chunk advance in lock-step so that every launch fills the
 // 148 SMs.  Matrices are row-major interleaved complex128.
 #include <algorithm>
+#include <type_traits>
 #include "gnb_common.cuh"
 #include "gnb_kernels.h"
 
@@ -676,6 +677,78 @@ __device__ __forceinline__ void tw_finish_real(const cplx* __restrict__ Ab, int 
     }
 }
 
+// Net row moves + permutation bookkeeping of a finished tournament (one warp; lanes 0..31 = pivot order)
+__device__ __forceinline__ void tw_bookkeeping(int c0, const int* s_win, int* __restrict__ mvb, int* pb, int lane) {
+    constexpr int w = GNB_NB;
+    const bool act = lane < w;
+    const int ch = act ? s_win[lane] : -1;                 // chosen global row, pivot order
+    const bool in_blk = act && ch < c0 + w;                // ch >= c0 always
+    const unsigned chosen_pos = __reduce_or_sync(0xffffffffu, in_blk ? (1u << (ch - c0)) : 0u);
+    const unsigned vacmask = __ballot_sync(0xffffffffu, act && !in_blk);
+    const unsigned dismask = 0xffffffffu & ~chosen_pos;    // block rows that were not chosen
+    int d2 = -1, s2 = -1;
+    if (act) { mvb[1 + 2 * lane] = c0 + lane; mvb[2 + 2 * lane] = ch; }
+    if (act && !in_blk) {
+        const int rank = __popc(vacmask & ((1u << lane) - 1u));
+        const int p = __fns(dismask, 0, rank + 1);
+        d2 = ch; s2 = c0 + p;                              // displaced block row fills the vacated slot
+        mvb[1 + 2 * (w + rank)] = d2;
+        mvb[2 + 2 * (w + rank)] = s2;
+    }
+    if (lane == 0) mvb[0] = w + __popc(vacmask);
+    if (pb) {
+        const int o1 = act ? pb[ch] : 0;
+        const int o2 = (s2 >= 0) ? pb[s2] : 0;
+        __syncwarp();
+        if (act) pb[c0 + lane] = o1;
+        __syncwarp();
+        if (d2 >= 0) pb[d2] = o2;
+    }
+}
+
+// Final round of a COMPLEX panel, one warp: as tw_finish_real, complex arithmetic (lane r holds row r of the pivot block as
+// 32 complex doubles; s_gj: 32 complex).  The pivot order comes from the single-precision eliminations.
+__device__ __forceinline__ void tw_finish_cplx(const cplx* __restrict__ Ab, int ld, int c0, const int* s_win, int nfin, cplx* s_gj,
+                                               cplx* __restrict__ LUb, int* __restrict__ mvb, int* pb, int lane, int* info) {
+    {
+        cplx m[32];
+        const int row = lane < nfin ? s_win[lane] : -1;
+        if (row >= 0) {
+            const cplx* src = Ab + (long)row * ld + c0;
+#pragma unroll
+            for (int k = 0; k < 32; k++) m[k] = src[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) m[k] = cmake((k == lane) ? 1.0 : 0.0, 0.0);
+        }
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) {
+            if (lane == k) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) s_gj[q] = m[q];
+            }
+            __syncwarp();
+            const bool isp = lane == k;
+            const cplx f = m[0];
+            const cplx p0 = s_gj[0];
+            const bool nz = p0.x != 0.0 || p0.y != 0.0;
+            if (info && !nz && lane == 0) *info = 1;                       // exactly singular pivot
+            const cplx rk = nz ? crcp_fast(p0) : cmake(0.0, 0.0);
+#pragma unroll
+            for (int q = 1; q < 32; q++) {
+                const cplx pq = cmul(s_gj[q], rk);                         // scaled pivot row
+                m[q - 1] = isp ? pq : cfnma(m[q], f, pq);
+            }
+            m[31] = isp ? rk : cneg(cmul(f, rk));
+            __syncwarp();
+        }
+        cplx* inv = LUb + (long)lane * GNB_NB;
+#pragma unroll
+        for (int k = 0; k < 32; k++) inv[k] = m[k];
+    }
+    tw_bookkeeping(c0, s_win, mvb, pb, lane);
+}
+
 template <typename T, bool F64, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_tournw(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n_in, const int* __restrict__ cand_in,
@@ -768,13 +841,14 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
     // NR0 = candidate rows per lane at level 0 (lists of 32 NR0 rows): 4 halves the number of sequential eliminations
     // of a 256-row group (2 + 1 instead of 4 + 2 + 1) at 1.5 x the work per pivot step; the merges always hold 2 rows per lane
     typedef typename T::C C;
-    static_assert(sizeof(C) <= 8, "real panels only");
+    constexpr bool CPLX = !std::is_floating_point<C>::value;          // float2 / double2 rows
+    static_assert(!CPLX || (NR0 == 2 && !F64), "complex panels: two rows per lane, single-precision rounds");
     static_assert(NR0 == 2 || NR0 == 4, "rows per lane at level 0");
     constexpr int w = GNB_NB, L0 = 32 * NR0;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     __shared__ __align__(16) C s_prow_all[NW][32];
     __shared__ int s_list_all[NW][2][4][32];
-    __shared__ __align__(16) double s_gj_all[NW][32];
+    __shared__ __align__(16) double s_gj_all[NW][CPLX ? 64 : 32];
     const int gid = blockIdx.x * NW + warp;
     if (gid >= total_groups) return;                         // warp-uniform; no CTA barrier below
     const int b = gid / grp, g = gid - b * grp;
@@ -857,8 +931,12 @@ k_tournq(const cplx* __restrict__ A, long strideA, int ld, int c0, int r0, int n
     // final round: the pivot block is inverted in FP64 on the original entries.  With T = float the pivot ORDER comes from
     // single-precision eliminations (a near-tie may resolve differently than in FP64: a threshold-pivoting order with
     // threshold 1 - 1e-7, as stable as partial pivoting); exact singularity is then detected by the FP64 Gauss-Jordan
-    tw_finish_real(Ab, ld, c0, mixr, s_win, nfin, s_gj_all[warp], LU + (long)b * GNB_NB * GNB_NB,
-                   moves + (long)b * GNB_MOVES_STRIDE, perm ? perm + (long)b * perm_stride : nullptr, lane, F64 ? nullptr : info);
+    if constexpr (CPLX)
+        tw_finish_cplx(Ab, ld, c0, s_win, nfin, reinterpret_cast<cplx*>(s_gj_all[warp]), LU + (long)b * GNB_NB * GNB_NB,
+                       moves + (long)b * GNB_MOVES_STRIDE, perm ? perm + (long)b * perm_stride : nullptr, lane, info);
+    else
+        tw_finish_real(Ab, ld, c0, mixr, s_win, nfin, s_gj_all[warp], LU + (long)b * GNB_NB * GNB_NB,
+                       moves + (long)b * GNB_MOVES_STRIDE, perm ? perm + (long)b * perm_stride : nullptr, lane, F64 ? nullptr : info);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1369,7 +1447,8 @@ void gnb_launch_gemm(cudaStream_t st, const GnbGemmArgs& g, int nbatch, bool wt,
 static int g_tourn_fp32 = 1;      // nominating (non-final) tournament rounds in single precision
 void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 // Tournament pivoting of the 32-wide panel at column c0 (candidate rows [c0, N)); used by the recursive engine.
-static int g_tourn_warp = 57;     // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
+static int g_tournq_cplx_min_m = 400;
+static int g_tourn_warp = 249;     // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
 void gnb_set_tourn_warp(int on) { g_tourn_warp = on; }
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
@@ -1392,9 +1471,33 @@ long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long st
         // round of a real panel (takes precedence over 1 and 2): +3 %; 16 = four candidate rows per lane at level 0 of the
         // FP32 nominating rounds of k_tournq (3 sequential eliminations per 256-row group instead of 7): +1.8 %; 32 = the
         // final round takes its pivot ORDER from FP32 eliminations too (4 rows per lane: one elimination for <= 128 nominees)
-        // and inverts the pivot block in FP64 (2 phases instead of 4): +1.1 % (N = 512: +2.9 %).  Default: 57.
+        // and inverts the pivot block in FP64 (2 phases instead of 4): +1.1 % (N = 512: +2.9 %); 64 / 128 = nominating / final
+        // rounds of COMPLEX panels on k_tournq (float2 rows, FP32 order + FP64 complex inverse) for batches >= 400.  Default: 249.
         const bool use_w = warp_ok && (fin ? (real_panel && (g_tourn_warp & 2))
                                            : (real_panel ? (g_tourn_warp & 1) != 0 : (f32 && (g_tourn_warp & 4))));
+        // complex panels on the warp-independent kernel: measured +0.9 % on the complex-F T(E) step (625 matrices per stream),
+        // -2.5 % on GrInt (148 per stream: one warp per 256-row group leaves the SMs with 4 warps each), hence the batch limit
+        if (warp_ok && !real_panel && f32 && (g_tourn_warp & 64) && M >= g_tournq_cplx_min_m) {
+            const int grp = cdiv_i(n, 256);
+            const int total = M * grp;
+            if (grp > 1 || !(g_tourn_warp & 128)) {
+                if (grp > 1) {
+                    k_tournq<TT<float>, false, 2, 5, 2><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                        cout, cand_stride, 0, LU, moves, perm, perm_stride, info, mixr);
+                    launches++;
+                    n = (grp - 1) * w + min(w, n - (grp - 1) * 256);
+                    cin = cout;
+                    cout = (cout == cand0) ? cand1 : cand0;
+                    continue;
+                }
+                // fall through: FP64 final round on k_tourn (<= 256 rows are reduced by it in two launches)
+            } else {
+                k_tournq<TT<float>, false, 2, 5, 2><<<cdiv_i(total, 2), 64, 0, st>>>(A, strideA, ld, c0, c0, n, grp, total, cin, cand_stride,
+                                                                                    cout, cand_stride, 1, LU, moves, perm, perm_stride, info, mixr);
+                launches++;
+                break;
+            }
+        }
         if (warp_ok && real_panel && (g_tourn_warp & 8)) {    // warp-independent kernel: one warp per 256-row group / matrix
             const int grp = cdiv_i(n, 256);
             const int total = M * grp;
