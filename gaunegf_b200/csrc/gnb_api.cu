@@ -161,6 +161,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "small_reg")) gnb_small_set_reg(value);
     else if (!strcmp(name, "small_cluster")) gnb_small_set_cluster(value);
     else if (!strcmp(name, "small_cluster_maxm")) gnb_small_set_cluster_max_m(value);
+    else if (!strcmp(name, "small_cl_relaxed")) gnb_small_set_cl_relaxed(value);
     else if (!strcmp(name, "small_wide")) gnb_small_set_wide(value);
     else if (!strcmp(name, "contacts_last")) g_contacts_last = value;
     else if (!strcmp(name, "mixed_layout")) g_mixed_layout = value;

@@ -118,6 +118,7 @@ struct GnbSmallArgs {
     double* dos_tot; double* dos_site;     // DOS (dos_site may be null)
     int ca, cb; double* T;                 // T
     int* info;
+    int cl_relaxed;                        // cluster kernels: non-owner warps arrive at the column barrier without release semantics (set by the launcher)
 };
 cudaError_t gnb_small_init();
 void gnb_small_set_reg(int on);        // developer switch "small_reg": register-resident (1) or shared-memory (0) kernel
@@ -127,6 +128,7 @@ int gnb_small_cluster_max_m(int n);    // largest batch for which the cluster ke
 void gnb_small_set_wide(int on);       // developer switch "small_wide"
 void gnb_small_set_cluster(int on);    // developer switch "small_cluster"
 void gnb_small_set_cluster_max_m(int m);   // developer switch "small_cluster_maxm"
+void gnb_small_set_cl_relaxed(int on);     // developer switch "small_cl_relaxed"
 int gnb_small_enabled();               // developer switch "small_fused" (gnb_api.cu)
 void gnb_launch_small(cudaStream_t st, const GnbSmallArgs& a);
 

@@ -106,7 +106,8 @@ static int chain_invert(gnb_ctx* c, int M, int nc, cplx* Min, cplx* Gout) {
     // one CTA per matrix, on chip (gnb_small.cu).  The thread-block-cluster kernels (97..192) serve the TAIL of the fixed
     // point only: with few live problems the iteration is bound by the block engine's launch chain (~25 dependent launches
     // per inverse), which one cluster launch replaces; at the 512-problem batches of BASELINE cfg 4 the block engine is faster
-    if (gnb_small_enabled() && (nc <= gnb_small_max_n() || (nc <= gnb_small_inverse_max_n() && M <= gnb_small_cluster_max_m(nc)))) {
+    if (gnb_small_enabled() && (nc <= gnb_small_max_n() || (nc <= gnb_small_inverse_max_n() && M <= std::min(128, gnb_small_cluster_max_m(nc))))) {   // (here the matrices are given: no
+        // assembly to fuse, so the cluster kernels pay off later than on the energy-grid calls: 2.76 s at 256, 2.0-2.3 s at 128)
         GnbSmallArgs sa{};
         sa.N = nc; sa.M = M; sa.mode = GNB_SMALL_GREEN; sa.Araw = Min; sa.info = c->info.as<int>();
         sa.G = Gout; sa.strideG = (long)nc * nc; sa.ldg = nc;

@@ -480,6 +480,10 @@ __device__ __forceinline__ unsigned cluster_rank() {
     return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrive without release semantics: for warps that published nothing since the last barrier (their reads of the step are
+// complete by data dependence); the release variant makes every arriving warp drain its memory operations (ncu: membar =
+// 32 % of the stall samples when all 32 warps of the cluster arrived with .release at every column)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned remote_addr(const void* p, unsigned rank) {
     unsigned l = (unsigned)__cvta_generic_to_shared(p), r;
@@ -602,7 +606,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(32 * NW, 1) k_reg_g
     for (int k = 0; k < N; k++) {
         const int par = k & 1;
         if (k > 0) {
-            if (gw != k % GW) cluster_arrive();                      // the owner of column k arrived when it published
+            if (gw != k % GW) { if (a.cl_relaxed) cluster_arrive_relaxed(); else cluster_arrive(); }   // the owner of column k arrived (release) when it published
             cluster_wait();
         }
         const int p = piv[k];
@@ -655,8 +659,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(32 * NW, 1) k_reg_g
     }
 }
 
+static int g_cl_relaxed = 0;            // developer switch "small_cl_relaxed" (measured: within noise, off)
 template <int RA, int CB, int NW, int CL>
-void launch_reg_cl(cudaStream_t st, const GnbSmallArgs& a) {
+void launch_reg_cl(cudaStream_t st, const GnbSmallArgs& a_) {
+    GnbSmallArgs a = a_;
+    a.cl_relaxed = g_cl_relaxed;
     const size_t smem = (size_t)(2 * 32 * RA + 2 + 32 * (a.N | 1)) * sizeof(cplx) + (size_t)2 * 32 * RA * sizeof(int);
     k_reg_gj_cl<RA, CB, NW, CL><<<a.M * CL, 32 * NW, smem, st>>>(a);
 }
@@ -668,6 +675,7 @@ size_t small_smem(int N, int nt) {
 
 }  // namespace
 
+void gnb_small_set_cl_relaxed(int on) { g_cl_relaxed = on; }
 static int g_reg_resident = 1;          // developer switch "small_reg"
 static int g_reg_wide = 0;              // developer switch "small_wide": N <= 64 on 16 warps x (2 x 4) tiles
 void gnb_small_set_wide(int on) { g_reg_wide = on; }
