@@ -34,6 +34,7 @@ SIGNATURES = {
     "gnb_gemm_stats": (C.c_int, [_vp, _dp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "gnb_set_system": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
     "gnb_set_system_cached": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "gnb_system_differs": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "gnb_sigma_clear": (C.c_int, [_vp]),
     "gnb_sigma_set_dense0": (C.c_int, [_vp, _vp, C.c_int]),
     "gnb_sigma_add_const_block": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -191,17 +192,29 @@ class Context:
         Fa, Sa = np.asarray(F), np.asarray(S)
         assert Fa.shape == Sa.shape, "F and S must have the same shape"
         assert Fa.ndim == 2 and Fa.shape[0] == Fa.shape[1], "F and S must be square matrices"
-        def as_input(a):        # real float64 arrays go to the library as they are (no complex copy per call)
-            if a.dtype == np.float64 and a.flags.c_contiguous:
-                return a, 1
-            return c128(a), 0
-        (Fc, fr), (Sc, sr) = as_input(Fa), as_input(Sa)
+        (Fc, fr), (Sc, sr) = self._as_input(Fa), self._as_input(Sa)
         self.N = Fc.shape[0]
         up = C.c_int(0)
         self.check(self.lib.gnb_set_system_cached(self.h, self.N, ptr(Fc), ptr(Sc), fr | (sr << 1), C.byref(up)))
         self.last_system_upload = up.value                 # bit 0: F was sent, bit 1: S was sent
         if up.value == 0:
             self.system_uploads_skipped += 1
+
+    @staticmethod
+    def _as_input(a):           # real float64 arrays go to the library as they are (no complex copy per call)
+        if a.dtype == np.float64 and a.flags.c_contiguous:
+            return a, 1
+        return c128(a), 0
+
+    def system_differs(self, F, S, full=True):
+        """read-only: do (F, S) differ from the resident pair?  full=False: size + strided sample (parallel.set_system)"""
+        Fa, Sa = np.asarray(F), np.asarray(S)
+        if Fa.shape != Sa.shape or Fa.ndim != 2 or Fa.shape[0] != Fa.shape[1]:
+            return True
+        (Fc, fr), (Sc, sr) = self._as_input(Fa), self._as_input(Sa)
+        d = C.c_int(1)
+        self.check(self.lib.gnb_system_differs(self.h, Fc.shape[0], ptr(Fc), ptr(Sc), fr | (sr << 1), int(bool(full)), C.byref(d)))
+        return bool(d.value)
 
     def set_system_device(self, N, F_ptr, S_ptr):
         self.N = int(N)

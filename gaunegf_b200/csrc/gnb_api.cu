@@ -258,6 +258,44 @@ static void shadow_pass(const double* src, bool src_real, double* shadow, size_t
     for (int t = 0; t < T; t++) { *changed |= ch[t] != 0; *real &= real_slice[t] != 0; }
 }
 
+// Does (F, S) differ from what gnb_set_system_cached made resident?  full = 1: every element (threaded, read-only);
+// full = 0: size + a strided sample (a cheap local sanity check for ranks that follow rank 0's full comparison,
+// gaunegf_b200/parallel.py).  differs: 0 / 1.
+extern "C" int gnb_system_differs(gnb_ctx* c, int N, const double* F, const double* S, int real_input, int full, int* differs) {
+    if (!c || N <= 0 || !F || !S || !differs) return gnb_fail(c, GNB_ERR_ARG, "system_differs: bad arguments");
+    *differs = 1;
+    if (c->shadow_N != N || c->N != N || !c->hF || !c->hS) return GNB_OK;
+    if (c->shadow_ev) GNB_CK(cudaEventSynchronize(c->shadow_ev));
+    const size_t n = (size_t)N * N;
+    const double* mats[2] = {F, S};
+    const double* shad[2] = {static_cast<const double*>(c->hF), static_cast<const double*>(c->hS)};
+    const bool re[2] = {(real_input & 1) != 0, (real_input & 2) != 0};
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int T = full ? (int)std::min<size_t>(std::min(8u, hw), std::max<size_t>(1, n >> 15)) : 1;
+    const size_t step = full ? 1 : 1021;                     // sample: every 1021st element (prime: walks rows and columns)
+    std::vector<char> diff(T, 0);
+    auto work = [&](int t) {
+        bool d = false;
+        for (int m = 0; m < 2 && !d; m++) {
+            const size_t lo = n * t / T, hi = n * (t + 1) / T;
+            if (full && !re[m]) { d = memcmp(mats[m] + 2 * lo, shad[m] + 2 * lo, (hi - lo) * 16) != 0; continue; }
+            for (size_t i = lo; i < hi; i += step) {
+                if (re[m]) d |= (shad[m][2 * i] != mats[m][i]) | (shad[m][2 * i + 1] != 0.0);
+                else d |= (shad[m][2 * i] != mats[m][2 * i]) | (shad[m][2 * i + 1] != mats[m][2 * i + 1]);
+            }
+        }
+        diff[t] = d;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    int any = 0;
+    for (int t = 0; t < T; t++) any |= diff[t];
+    *differs = any;
+    return GNB_OK;
+}
+
 // set_system for host arrays that usually repeat: F and S are compared with pinned shadow copies kept by the context and only
 // what changed goes over PCIe (the reference re-sends F and S on every integrator call, integrate.py:92-95; an SCF step
 // changes F but not S).  real_input: bit 0 = F holds N^2 real doubles, bit 1 = S does (else complex128).

@@ -66,7 +66,7 @@ def GrInt(F, S, g, Elist, weights):
     Elist, weights = _check(F, S, Elist, weights)
     N = np.shape(F)[0]
     ctx = default_context()
-    ctx.set_system(F, S)
+    parallel.set_system(ctx, F, S)
     plan = ObjectPlan(g, N)
     plan.install(ctx)
     parallel_logger.info("Calculating G^R with GInt on B200: %dx%d, %d energies", N, N, Elist.size)
@@ -83,7 +83,7 @@ def GrIntLevels(F, S, g, levels):
     levels = [_check(F, S, E, w) for E, w in levels]
     N = np.shape(F)[0]
     ctx = default_context()
-    ctx.set_system(F, S)
+    parallel.set_system(ctx, F, S)
     plan = ObjectPlan(g, N)
     plan.install(ctx)
     if plan.kind not in (DESC, DENSE_CONST):            # host-evaluated Sigma objects: level by level
@@ -109,7 +109,7 @@ def GrLessInt(F, S, g, Elist, weights, ind=None):
     Elist, weights = _check(F, S, Elist, weights)
     N = np.shape(F)[0]
     ctx = default_context()
-    ctx.set_system(F, S)
+    parallel.set_system(ctx, F, S)
     plan = ObjectPlan(g, N)
     plan.install(ctx)
     nct = plan.ncontacts()

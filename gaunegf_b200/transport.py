@@ -112,7 +112,7 @@ def _transmission_batch(F, S, calc, energies, spin):
     n = np.shape(F)[0]
     energies = np.asarray(energies, dtype=float)
     if spin == 'r':
-        ctx.set_system(F, S)
+        parallel.set_system(ctx, F, S)
         plan = calc._plan(n)
         plan.install(ctx)
         if plan.kind == DESC:
@@ -144,7 +144,7 @@ def _transmission_batch(F, S, calc, energies, spin):
         perm = np.concatenate([np.arange(0, 2 * half, 2), np.arange(1, 2 * half, 2)])
         ix = np.ix_(perm, perm)
         Fm, Sm = Fm[ix], Sm[ix]
-    ctx.set_system(Fm, Sm)
+    parallel.set_system(ctx, Fm, Sm)
     ctx.sigma_clear()
     if calc.energy_dependent:
         plan = calc._plan(n)
@@ -189,7 +189,7 @@ def _dos_batch(F, S, calc, energies, spin):
     energies = np.asarray(energies, dtype=float)
     if spin not in _SPINS:
         raise ValueError(f"Unknown spin configuration '{spin}'. Use 'r', 'u', 'ro', or 'g'")
-    ctx.set_system(F, S)
+    parallel.set_system(ctx, F, S)
 
     def _host_sigma_dos(E):        # Sigma(E) from the provider on the host, inverse and reduction on the GPU
         st = _batched_sigma(calc, E, spin, n, 'tot')

@@ -70,6 +70,11 @@ int gnb_set_system(gnb_ctx* ctx, int N, const double* F, const double* S, int lo
  * are fully consumed when the call returns.  real_input: bit 0 = F holds N*N real doubles, bit 1 = S does (restricted-spin
  * Gaussian output; otherwise complex128).  uploaded (may be NULL): bit 0 = F was sent, bit 1 = S was sent. */
 int gnb_set_system_cached(gnb_ctx* ctx, int N, const double* F, const double* S, int real_input, int* uploaded);
+/* Read-only test whether (F, S) differ from the resident pair of gnb_set_system_cached.  full = 1: every element; full = 0:
+ * size and a strided sample only.  With one process per GPU every rank receives the same F and S: rank 0 runs the full
+ * comparison, the others the sample, and one flag is agreed on (gaunegf_b200/parallel.py) instead of N full passes over host
+ * memory that all ranks of a box share.  differs: 0 / 1. */
+int gnb_system_differs(gnb_ctx* ctx, int N, const double* F, const double* S, int real_input, int full, int* differs);
 
 /* ---- self-energy description ------------------------------------------------------------------
  * Sigma_tot(E) = Sigma0 + sum_c scatter(inds_c, blk_c(E)).  Contacts are numbered 0..nc-1; the
