@@ -156,6 +156,23 @@ assert np.allclose(D, np.outer(E.real, np.arange(3.0)))
 # fewer energies than ranks: one rank gets an empty slice
 one = parallel.sharded_matrix_sum(N, E[:1], w[:1], partial)
 assert np.max(np.abs(one - w[0] * f(E[0]))) < 1e-12
+# parallel.set_system: rank 0's full comparison (or any rank's sanity sample) decides for every rank
+class FakeCtx:
+    device = 0
+    def __init__(self, full_says, sample_says):
+        self.full_says, self.sample_says, self.uploads, self.asked = full_says, sample_says, 0, []
+        self.last_system_upload, self.system_uploads_skipped = 3, 0
+    def system_differs(self, F, S, full=True):
+        self.asked.append(full)
+        return self.full_says if full else self.sample_says
+    def set_system(self, F, S):
+        self.uploads += 1
+for full_says, sample_says, expect in ((False, False, 0), (True, False, 1), (False, True, 1)):
+    c = FakeCtx(full_says, sample_says)
+    parallel.set_system(c, None, None)
+    assert c.asked == [rank == 0], "rank 0 compares in full, the others sample"
+    assert c.uploads == expect, (rank, full_says, sample_says, c.uploads)
+    assert c.system_uploads_skipped == 1 - expect
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
