@@ -72,6 +72,7 @@ __device__ __forceinline__ void bulk_g2s_keep(void* dst, const void* src, int by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 // C is read once and written once per launch and nothing re-reads it before it has left the L2 (the working set of a
 // chunk is ~100 x the L2): streaming (evict-first) accesses keep it from displacing the packed operands, which every
 // row / column tile of a matrix re-reads (ncu: DRAM reads of the mid-K launches were 1.6 x their algorithmic bytes)
@@ -178,6 +179,13 @@ __global__ void __launch_bounds__(288, 1) k_rk_gemm(RkGemmArgs g, int nti, int n
         if (g.kskip && i0 >= g.klo && i0 + TM <= g.khi) ch0 = (i0 + 32 - g.klo) / KC;
         const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);     // warp tile inside the range
         const int mode = !g.preal ? 3 : (j0 + TN <= g.nreal ? 1 : 2);              // 1: real x real, 2: real x complex
+        if ((g.cs & 4) && active && ch0 < nch_all && j0 >= g.mixr) {               // C tile on its way to L2 while the K loop runs
+            const cplx* Cp = g.C + (long)b * g.sC + (long)(i0 + wm * 16 + gid) * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) prefetch_l2(Cp + (long)(mi * 8) * g.ldc + ni * 8);
+        }
         for (int ch = ch0; ch < nch_all; ch++, q++) {
             const int s = q % RK_ST;
             mbar_wait(&full[s], (q / RK_ST) & 1);
@@ -409,6 +417,21 @@ __global__ void __launch_bounds__(288, 2) k_rk_gemm_rp(RkGemmRpArgs g, int nti, 
         const int i0 = g.ilo + ti * TM, j0 = g.jlo + tj * TN;
         const bool active = (wm * 16 < g.ihi - i0) && (wn * 32 < g.jhi - j0);
         const bool wre = !WR && (j0 + wn * 32 >= g.jre);      // warp-uniform: this warp's 32 columns are real-valued
+        if ((g.cs & 4) && active) {                            // C tile on its way to L2 while the K loop runs
+            if (WR) {
+                const double* Cr = rk_real_view(g.C + (long)b * g.sC, g.mixr) + (long)(i0 + wm * 16 + gid) * 2 * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) prefetch_l2(Cr + (long)(mi * 8) * 2 * g.ldc + ni * 8);
+            } else {
+                const cplx* Cp = g.C + (long)b * g.sC + (long)(i0 + wm * 16 + gid) * g.ldc + j0 + wn * 32 + tig * 2;
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) prefetch_l2(Cp + (long)(mi * 8) * g.ldc + ni * 8);
+            }
+        }
         for (int ch = 0; ch < nch_all; ch++, q++) {
             const int s = q % RK_ST;
             mbar_wait(&full[s], (q / RK_ST) & 1);
@@ -1059,7 +1082,7 @@ static int g_rk_real = 1;        // skip the imaginary DMMAs where the operands 
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
 static int g_rk_wskip = 1;       // forward-W: skip the dead write of W into A (FORWARD mode, rows above back_row_lo)
-static int g_rk_cs = 0;          // bit 0: streaming (evict-first) read-modify-write of C in the rank-K kernels, bit 1: L2 evict-last operand
+static int g_rk_cs = 4;          // bit 2: L2 prefetch of the C tile at the start of its K loop; bit 0: streaming (evict-first) read-modify-write of C in the rank-K kernels, bit 1: L2 evict-last operand
                                  // copies.  Measured: no effect on the step (59.23 / 59.28 / 59.22 / 59.31 ms for 0 / 1 / 2 / 3), so off
 static int g_rk_augreal = 1;     // FORWARD: real arithmetic on the augmented columns while the pivot blocks are real
 static int g_rk_tcap_k = 0;      // > 0: a rank-K CTA works on at most max(1, tcap_k / K) tiles (short-lived CTAs), 0: persistent
