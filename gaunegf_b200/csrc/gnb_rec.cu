@@ -901,6 +901,13 @@ __global__ void __launch_bounds__(256, sizeof(AT) == sizeof(double) ? 3 : 2) k_r
             const int i = idx >> 5, cc = idx & 31;
             sB[i * WM_BS + cc] = rstore ? cmake(Abr[(long)(c0 + i) * 2 * ld + cs + cc], 0.0) : Ab[(long)(c0 + i) * ld + cs + cc];
         }
+        if (tt + 1 < tiles_per_cta && cs + WM_TC < jhi) {     // the next tile of this CTA on its way to L2
+            const int csn = cs + WM_TC, i = t >> 2, part = t & 3;
+            if (i < nrows) {
+                if (csn < mixr) prefetch_l2(Abr + (long)(c0 + i) * 2 * ld + csn + part * 8);
+                else { prefetch_l2(Ab + (long)(c0 + i) * ld + csn + part * 8); prefetch_l2(Ab + (long)(c0 + i) * ld + csn + part * 8 + 4); }
+            }
+        }
         __syncthreads();
         double cre[2][2], cim[2][2];
         // pivot blocks left of nreal are real; so are the columns left of nreal (see RkGemmArgs::nreal)
@@ -1019,6 +1026,13 @@ __global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, l
         for (int idx = t; idx < nrows * WM_TC; idx += 256) {
             const int i = idx >> 5, cc = idx & 31;
             sB[i * WR_BS + cc] = rstore ? Abr[(long)(c0 + i) * 2 * ld + cs + cc] : Ab[(long)(c0 + i) * ld + cs + cc].x;
+        }
+        if (tt + 1 < tiles_per_cta && cs + WM_TC < jhi) {     // the next tile of this CTA on its way to L2 (one 32-byte sector per thread)
+            const int csn = cs + WM_TC, i = t >> 2, part = t & 3;
+            if (i < nrows) {
+                if (csn < mixr) prefetch_l2(Abr + (long)(c0 + i) * 2 * ld + csn + part * 8);
+                else { prefetch_l2(Ab + (long)(c0 + i) * ld + csn + part * 8); prefetch_l2(Ab + (long)(c0 + i) * ld + csn + part * 8 + 4); }
+            }
         }
         __syncthreads();
         const int col = cs + wn * 8 + tig * 2;                // this thread's two adjacent output columns
