@@ -564,15 +564,38 @@ __global__ void __launch_bounds__(256) k_rk_panel_save(const cplx* __restrict__ 
     const bool realp = c0 < mixr;                            // real-stored panel -> real-packed copy
     const double* Arv = rk_real_view(Ab, mixr);
     double* PRb = PpkR + (long)b * stridePkR;
-#pragma unroll 4
-    for (int q = wrp; q < PS_ROWS; q += 8) {
-        const int r = r0 + q;
-        if (r >= N) break;
-        const int src = s_map[q];
-        const bool piv = (r >= c0 && r < c0 + GNB_NB);
-        const long off = ((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk;
-        if (realp) PRb[off] = piv ? 0.0 : Arv[(long)src * 2 * ld + c0 + lane];
-        else Pb[off] = piv ? cmake(0.0, 0.0) : Ab[(long)src * ld + c0 + lane];
+    // all 16 rows of this warp are loaded before the first store (16 independent loads in flight per lane: ncu showed the
+    // 4-deep version at 83 % long_scoreboard and 3.6 TB/s)
+    constexpr int RPW = PS_ROWS / 8;
+    if (realp) {
+        double v[RPW];
+#pragma unroll
+        for (int j = 0; j < RPW; j++) {
+            const int q = wrp + 8 * j, r = r0 + q;
+            const bool piv = (r >= c0 && r < c0 + GNB_NB);
+            v[j] = (r < N && !piv) ? Arv[(long)s_map[q] * 2 * ld + c0 + lane] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < RPW; j++) {
+            const int r = r0 + wrp + 8 * j;
+            if (r < N) PRb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk] = v[j];
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {                      // two passes of 8 rows: the same register footprint as the real case
+            cplx v[RPW / 2];
+#pragma unroll
+            for (int j = 0; j < RPW / 2; j++) {
+                const int q = wrp + 8 * (j + h * (RPW / 2)), r = r0 + q;
+                const bool piv = (r >= c0 && r < c0 + GNB_NB);
+                v[j] = (r < N && !piv) ? Ab[(long)s_map[q] * ld + c0 + lane] : cmake(0.0, 0.0);
+            }
+#pragma unroll
+            for (int j = 0; j < RPW / 2; j++) {
+                const int r = r0 + wrp + 8 * (j + h * (RPW / 2));
+                if (r < N) Pb[((long)kc * nrb + (r >> 5)) * RK_PBLK + (r & 31) * RK_PPS + kk] = v[j];
+            }
+        }
     }
 }
 
