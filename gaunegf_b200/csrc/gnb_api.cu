@@ -116,6 +116,9 @@ extern "C" int gnb_destroy(gnb_ctx* c) {
     for (int i = 0; i < GNB_MAX_SUBSTREAMS; i++) {
         if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
         if (c->sub_ev[i]) cudaEventDestroy(c->sub_ev[i]);
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->la_fork[i]) cudaEventDestroy(c->la_fork[i]);
+        if (c->la_join[i]) cudaEventDestroy(c->la_join[i]);
     }
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -642,6 +645,19 @@ static int pad_chunk(gnb_ctx* c, int M, const Lay& L, cplx* A) {
     return GNB_OK;
 }
 
+// look-ahead stream + events of sub-batch s (created on first use)
+static int attach_side(gnb_ctx* c, int s, GnbRecWork& w) {
+    if (!c->side[s]) {
+        int prio_lo = 0, prio_hi = 0;
+        GNB_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        GNB_CK(cudaStreamCreateWithPriority(&c->side[s], cudaStreamNonBlocking, prio_hi));
+        GNB_CK(cudaEventCreateWithFlags(&c->la_fork[s], cudaEventDisableTiming));
+        GNB_CK(cudaEventCreateWithFlags(&c->la_join[s], cudaEventDisableTiming));
+    }
+    w.side = c->side[s]; w.la_fork = c->la_fork[s]; w.la_join = c->la_join[s];
+    return GNB_OK;
+}
+
 static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
     int rc;
     const long strideA = (long)L.Np * L.ld;
@@ -658,6 +674,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
         S = std::min(S, std::max(1, M / g_rec_stream_min_m));
         if (c->timing) S = 1;                   // per-launch event timing of the rank-K kernel needs it alone on the GPU
         if (S <= 1) {
+            if (!jordan && !c->timing && (rc = attach_side(c, 0, w))) return rc;
             c->launches += gnb_eliminate_rec(c->stream, M, L.Np, L.naugp, A, strideA, L.ld, jordan, w);
         } else {
             for (int s = 0; s < S; s++)
@@ -681,6 +698,7 @@ static int run_eliminate(gnb_ctx* c, int M, const Lay& L, cplx* A, int jordan) {
                 ws.Wpk = w.Wpk + (long)m0 * w.strideWk;
                 ws.PpkR = w.PpkR ? w.PpkR + (long)m0 * w.stridePkR : nullptr;
                 ws.WpkR = w.WpkR ? w.WpkR + (long)m0 * w.strideWkR : nullptr;
+                if (!jordan && (rc = attach_side(c, s, ws))) return rc;
                 GNB_CK(cudaStreamWaitEvent(c->sub[s], c->fork_ev, 0));
                 if (g_rec_stagger_us > 0 && s > 0) k_stagger<<<1, 1, 0, c->sub[s]>>>((long)s * g_rec_stagger_us * 1000L);
                 c->launches += gnb_eliminate_rec(c->sub[s], m1 - m0, L.Np, L.naugp, A + (long)m0 * strideA, strideA, L.ld,

@@ -75,6 +75,8 @@ struct gnb_ctx {
     EventTimer gemm_timer;
     cudaStream_t sub[GNB_MAX_SUBSTREAMS] = {};
     cudaEvent_t sub_ev[GNB_MAX_SUBSTREAMS] = {};
+    cudaStream_t side[GNB_MAX_SUBSTREAMS] = {};      // look-ahead streams of the sub-batches (gnb_rec.cu)
+    cudaEvent_t la_fork[GNB_MAX_SUBSTREAMS] = {}, la_join[GNB_MAX_SUBSTREAMS] = {};
     cudaEvent_t fork_ev = nullptr;
     int device = 0;
     cudaStream_t stream = 0;

@@ -88,6 +88,8 @@ struct GnbRecWork {
     int mixr;                          // mixed layout: columns [0, mixr) stored as real doubles (0 or == nreal)
     double* flops_acc;                 // host accumulator: executed real FP64 flops of the rank-K / forward-W /
                                        // back-substitution launches (4-multiplication equivalents; may be null)
+    cudaStream_t side;                 // look-ahead: second stream of this (sub-)batch, null = none
+    cudaEvent_t la_fork, la_join;      // look-ahead fork / join events
 };
 size_t gnb_rec_pk_elems(int N);               // cplx elements per matrix of Ppk / Lpk (incl. slack)
 size_t gnb_rec_wk_elems(int N, int ld);       // cplx elements per matrix of Wpk (incl. slack)

@@ -1022,9 +1022,10 @@ __global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, l
                                                          const cplx* __restrict__ inv_b, const cplx* __restrict__ Lsrc,
                                                          long stridePk, int nrb, cplx* __restrict__ Wpk, long strideWk, int ncb,
                                                          int mixr, const double* __restrict__ PpkR, long stridePkR,
-                                                         double* __restrict__ WpkR, long strideWkR, int a_lo) {
+                                                         double* __restrict__ WpkR, long strideWkR, int a_lo, int fused) {
+    static_assert(WM_AS == WR_BS, "the staged A operands double as B operands of the prologue products");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sA = reinterpret_cast<double*>(smem_raw);        // [3][32][WM_AS]: inv_a, L_ba, inv_b
+    double* sA = reinterpret_cast<double*>(smem_raw);        // [3][32][WM_AS]: inv_a, L_ba (fused: -inv_b L_ba inv_a), inv_b
     double* sB = sA + 3 * GNB_NB * WM_AS;                    // [64][WR_BS]: R_a / W_a rows, then R_b rows
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int gid = lane >> 2, tig = lane & 3, wm = warp >> 2, wn = warp & 3;
@@ -1041,6 +1042,32 @@ __global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, l
         }
     }
     const int nrows = nb * GNB_NB;
+    // Fused leaf pair: with Y = -inv_b L_ba inv_a (two 32^3 products, once per CTA) the pair is ONE block product
+    //     [W_a; W_b] = [[inv_a, 0], [Y, inv_b]] [R_a; R_b]
+    // whose three 32 x 32 x columns products do not depend on each other: no barrier between them, where the
+    // three-step form (W_a, R_b -= L W_a, W_b) needs four per tile.  Same flops.
+    fused = fused && nb == 2;
+    if (fused) {
+        double c[2][2];
+        __syncthreads();
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) c[mi][0] = c[mi][1] = 0.0;
+        ws_rr_product(c, sA + GNB_NB * WM_AS, sA, wm, wn, gid, tig, false);          // X = L_ba inv_a  -> sB rows 0..31
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int r = wm * 16 + mi * 8 + gid, cc = wn * 8 + tig * 2;
+            sB[r * WR_BS + cc] = c[mi][0]; sB[r * WR_BS + cc + 1] = c[mi][1];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) c[mi][0] = c[mi][1] = 0.0;
+        ws_rr_product(c, sA + 2 * GNB_NB * WM_AS, sB, wm, wn, gid, tig, true);       // Y = -inv_b X    -> the L_ba slot
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int r = wm * 16 + mi * 8 + gid, cc = wn * 8 + tig * 2;
+            sA[(GNB_NB + r) * WM_AS + cc] = c[mi][0]; sA[(GNB_NB + r) * WM_AS + cc + 1] = c[mi][1];
+        }
+    }
     for (int tt = 0; tt < tiles_per_cta; tt++) {
         const int cs = jlo + (blockIdx.x * tiles_per_cta + tt) * WM_TC;
         if (cs >= jhi) break;                                 // block-uniform
@@ -1078,7 +1105,14 @@ __global__ void __launch_bounds__(256, 4) k_rk_wsolve_rr(cplx* __restrict__ A, l
         ws_rr_product(c, sA, sB, wm, wn, gid, tig, false);
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) emit(c0 + wm * 16 + mi * 8 + gid, c[mi][0], c[mi][1]);
-        if (nb == 2) {
+        if (fused) {
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) c[mi][0] = c[mi][1] = 0.0;
+            ws_rr_product(c, sA + GNB_NB * WM_AS, sB, wm, wn, gid, tig, false);                       // Y R_a
+            ws_rr_product(c, sA + 2 * GNB_NB * WM_AS, sB + GNB_NB * WR_BS, wm, wn, gid, tig, false);   // + inv_b R_b
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) emit(c0 + GNB_NB + wm * 16 + mi * 8 + gid, c[mi][0], c[mi][1]);
+        } else if (nb == 2) {
             __syncthreads();                                  // every warp is done reading R_a
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
@@ -1118,6 +1152,10 @@ static int g_rk_kskip = 1;
 static int g_rk_real = 1;        // skip the imaginary DMMAs where the operands are known to be real
 static int g_rk_strip = 1;       // 128 x 32 CTA tiles for 32-column strips
 static int g_rk_sms = 148;
+static int g_rk_wsolve_fused = 1;   // leaf pair of the fully real forward-W kernel as one block product (no barriers between its products)
+static int g_rk_lookahead = 0;   // FORWARD: wide part of a far update on a second stream beside the next leaf pair's panel work
+static int g_rk_la_mink = 64;    // ... for far updates with K >= this
+static int g_rk_la_ctas = 1;     // ... with this many rank-K CTAs per SM
 static int g_rk_wskip = 1;       // forward-W: skip the dead write of W into A (FORWARD mode, rows above back_row_lo)
 static int g_rk_cs = 4;          // bit 2: L2 prefetch of the C tile at the start of its K loop; bit 0: streaming (evict-first) read-modify-write of C in the rank-K kernels, bit 1: L2 evict-last operand
                                  // copies.  Measured: no effect on the step (59.23 / 59.28 / 59.22 / 59.31 ms for 0 / 1 / 2 / 3), so off
@@ -1167,6 +1205,10 @@ void gnb_rec_set_option(const char* name, int value) {
     else if (!strcmp(name, "rk_fin_mma")) g_rk_fin_mma = value;
     else if (!strcmp(name, "rk_tcap_k")) g_rk_tcap_k = value;
     else if (!strcmp(name, "rk_wskip")) g_rk_wskip = value;
+    else if (!strcmp(name, "rk_lookahead")) g_rk_lookahead = value;
+    else if (!strcmp(name, "rk_la_mink")) g_rk_la_mink = value;
+    else if (!strcmp(name, "rk_la_ctas")) g_rk_la_ctas = value;
+    else if (!strcmp(name, "rk_wsolve_fused")) g_rk_wsolve_fused = value;
     else if (!strcmp(name, "rk_augreal")) g_rk_augreal = value;
     else if (!strcmp(name, "rk_cs")) g_rk_cs = value;
     else if (!strcmp(name, "rk_lowprio")) g_rk_lowprio = value;
@@ -1239,6 +1281,14 @@ struct Rec {
     const GnbRecWork& ws; long launches;
     int nrb, ncb;
     int mixr;                                                // real-stored leading columns (mixed layout), 0 = none
+    // Look-ahead (FORWARD mode): after a far update has reached the 64 columns of the next leaf pair, the rest of it
+    // (the WIDE part: forward-W + rank-K update of all other columns) runs on a second stream with one rank-K CTA per
+    // SM, while the main stream already factors that pair - its tournaments, panel saves and leaf forward-W are
+    // latency-bound kernels that fit beside the rank-K CTAs.  The row moves of the saved panels (k_rk_moves_P), which
+    // the wide update is still reading, are deferred to the join.
+    bool la_pending = false, la_defer = false;
+    int la_jn = 0, la_ctas = 0;
+    std::vector<std::pair<int, int>> la_deferred;            // (c0, live_lo) of postponed k_rk_moves_P calls
 
     cplx* inv(int c0) const { return ws.inv + (long)(c0 / GNB_NB) * ws.inv_blk_stride; }
     int* mv(int c0) const { return ws.moves + (long)(c0 / GNB_NB) * ws.moves_blk_stride; }
@@ -1269,7 +1319,7 @@ struct Rec {
             const int tm = strip ? 128 : 64, tn = strip ? 32 : 64;
             const int nti = cdiv_i(ihi - ilo, tm), ntj = cdiv_i(jhi - jlo, tn);
             const long total = (long)M * nti * ntj;
-            int resident = g_rk_sms * ((wr || g_rk_rp2) ? 2 : 1);
+            int resident = g_rk_sms * (la_ctas > 0 ? la_ctas : ((wr || g_rk_rp2) ? 2 : 1));
             const int K = khi - klo;
             // exactly half of the column tiles are the cheap real-valued ones: interleave them, odd CTA stride
             r.jint = (!wr && !strip && r.jre > jlo && r.jre < jhi && (ntj % 2 == 0) && (r.jre - jlo) == (ntj / 2) * tn) ? 1 : 0;
@@ -1329,14 +1379,8 @@ struct Rec {
         launches++;
     }
 
-    void base_step(int c0, int live_lo) {
-        {
-            TraceScope ts("tourn", st, M);
-            launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
-                                              inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info,
-                                              (g_rk_real && c0 + GNB_NB <= ws.nreal) ? 1 : 0, mixr);
-        }
-        TraceScope ts2("panel", st, M);
+    // row moves of block c0 on the saved panels [live_lo, c0)
+    void moves_P(int c0, int live_lo) {
         const int rp = mixr > 0 ? 1 : 0;                   // panels left of mixr live real-packed in PpkR
         if (live_lo < c0) {
             const int split = rp ? std::min(c0, mixr) : live_lo;       // [live_lo, split): real-packed chunks
@@ -1353,6 +1397,26 @@ struct Rec {
                 launches++;
             }
         }
+    }
+    // end of a look-ahead window: the main stream waits for the wide update, then applies the postponed panel moves
+    void la_join() {
+        if (!la_pending) return;
+        cudaStreamWaitEvent(st, ws.la_join, 0);
+        la_pending = false; la_defer = false;
+        for (auto& d : la_deferred) moves_P(d.first, d.second);
+        la_deferred.clear();
+    }
+
+    void base_step(int c0, int live_lo) {
+        {
+            TraceScope ts("tourn", st, M);
+            launches += gnb_launch_tournament(st, M, N, A, strideA, ld, c0, GNB_NB, ws.cand0, ws.cand1, ws.cand_stride,
+                                              inv(c0), mv(c0), jordan ? ws.perm : nullptr, ws.perm_stride, ws.info,
+                                              (g_rk_real && c0 + GNB_NB <= ws.nreal) ? 1 : 0, mixr);
+        }
+        TraceScope ts2("panel", st, M);
+        if (la_defer) la_deferred.emplace_back(c0, live_lo);     // the wide update of the look-ahead still reads these panels
+        else moves_P(c0, live_lo);
         const int rlo = jordan ? 0 : c0 + GNB_NB;
         if (rlo < N) {
             dim3 grid(cdiv_i(N - rlo, PS_ROWS), M);
@@ -1400,7 +1464,7 @@ struct Rec {
                     dim3 grid(cdiv_i(ntile, per), M);
                     k_rk_wsolve_rr<<<grid, 256, kWrSmem, st>>>(A, strideA, ld, c0, nb, jlo, jreal, per, inv(c0),
                                                                nb == 2 ? inv(c0 + GNB_NB) : nullptr, Lsrc, ws.stridePk, nrb, ws.Wpk,
-                                                               ws.strideWk, ncb, mixr, ws.PpkR, ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo);
+                                                               ws.strideWk, ncb, mixr, ws.PpkR, ws.stridePkR, ws.WpkR, ws.strideWkR, a_lo, g_rk_wsolve_fused);
                     launches++;
                 }
                 if (jhi > jreal) {
@@ -1441,6 +1505,7 @@ struct Rec {
 
     void apply_far(int c0, int w, int jlo, int jhi) {
         if (jhi <= jlo) return;
+        if (la_pending && jhi > la_jn) la_join();            // leaves the columns of the look-ahead window
         dim3 grid(cdiv_i(jhi - jlo, 32), M);
         TraceScope ts("movesA", st, M);
         k_rk_moves_A<<<grid, 256, 0, st>>>(A, strideA, ld, jlo, jhi, ws.moves, ws.moves_blk_stride, c0 / GNB_NB,
@@ -1458,7 +1523,21 @@ struct Rec {
         const int h = (w / GNB_NB + 1) / 2 * GNB_NB;
         factor(c0, h, true, live ? live_lo : c0);
         const int hi = (!jordan && c0 + w == N) ? N + naug : c0 + w;     // augmented columns ride along
-        apply_far(c0, h, c0 + h, hi);
+        if (!jordan && ws.side && g_rk_lookahead && !ws.timer && h >= g_rk_la_mink && w - h >= 2 * GNB_NB &&
+            hi - (c0 + h) > 2 * GNB_NB) {
+            const int jn = c0 + h + 2 * GNB_NB;                          // the next leaf pair's columns: narrow part
+            apply_far(c0, h, c0 + h, jn);                                // (joins a previous window first)
+            cudaEventRecord(ws.la_fork, st);
+            cudaStreamWaitEvent(ws.side, ws.la_fork, 0);
+            cudaStream_t main_st = st;
+            st = ws.side; la_ctas = g_rk_la_ctas;
+            apply_far(c0, h, jn, hi);                                    // wide part on the second stream
+            cudaEventRecord(ws.la_join, st);
+            st = main_st; la_ctas = 0;
+            la_pending = true; la_defer = true; la_jn = jn;
+        } else {
+            apply_far(c0, h, c0 + h, hi);
+        }
         factor(c0 + h, w - h, jordan ? true : live, live ? live_lo : c0 + h);
         if (jordan) apply_far(c0 + h, w - h, c0, c0 + h);
     }
@@ -1506,6 +1585,7 @@ long gnb_eliminate_rec(cudaStream_t st, int M, int N, int naug, cplx* A, long st
     Rec e{st, M, N, naug, A, strideA, ld, jordan, ws, 0, N / 32, (N + naug) / 32, (!jordan && g_rk_real) ? ws.mixr : 0};
     if (jordan) { gnb_launch_init_perm(st, M, ws.perm, ws.perm_stride, N); e.launches++; }
     e.factor(0, N, false, 0);
+    e.la_join();
     if (!jordan && naug > 0) {
         e.apply_far(N - GNB_NB, GNB_NB, N, N + naug);      // the last block is nobody's left sibling
         e.backsub(0, N, std::max(0, ws.back_row_lo) / GNB_NB * GNB_NB);
