@@ -694,7 +694,7 @@ __device__ __forceinline__ void rk_moves_tile(ET* __restrict__ Xb, long ldx, int
         }
     }
 }
-__global__ void __launch_bounds__(256) k_rk_moves_A(cplx* __restrict__ A, long strideA, int ld, int jlo, int jhi,
+__global__ void __launch_bounds__(256, 5) k_rk_moves_A(cplx* __restrict__ A, long strideA, int ld, int jlo, int jhi,
                                                     const int* __restrict__ moves, long moves_blk_stride, int blk_lo,
                                                     int blk_hi, int mixr) {
     __shared__ int s_dst[2 * GNB_NB], s_src[2 * GNB_NB];
