@@ -327,12 +327,12 @@ extern "C" int gnb_set_system_cached(gnb_ctx* c, int N, const double* F, const d
     }
     const bool have = c->shadow_N == N;
     bool chF, chS, reF, reS;
+    int rc;
     shadow_pass(F, (real_input & 1) != 0, static_cast<double*>(c->hF), 2 * (size_t)N * N, have, c->realF_slice, &chF, &reF);
+    if (chF && (rc = put(c, c->dF, c->hF, bytes, GNB_HOST))) return rc;       // F is on its way while S is compared
     shadow_pass(S, (real_input & 2) != 0, static_cast<double*>(c->hS), 2 * (size_t)N * N, have, c->realS_slice, &chS, &reS);
     c->shadow_N = N;
     c->real_FS = reF && reS;
-    int rc;
-    if (chF && (rc = put(c, c->dF, c->hF, bytes, GNB_HOST))) return rc;
     if (chS && (rc = put(c, c->dS, c->hS, bytes, GNB_HOST))) return rc;
     if (chF || chS) GNB_CK(cudaEventRecord(c->shadow_ev, c->stream));
     if (uploaded) *uploaded = (chF ? 1 : 0) | (chS ? 2 : 0);
