@@ -149,6 +149,7 @@ extern "C" int gnb_gemm_stats(gnb_ctx* c, double* ms, double* flops, int64_t* la
     if (reset) c->gemm_timer.reset();
     return GNB_OK;
 }
+void gnb_set_tournq_cplx_min_m(int m);
 extern "C" int gnb_dev_set_option(const char* name, int value) {     // developer A/B switches
     if (!name) return GNB_ERR_ARG;
     if (!strcmp(name, "two_level")) gnb_set_two_level(value);
@@ -171,6 +172,7 @@ extern "C" int gnb_dev_set_option(const char* name, int value) {     // develope
     else if (!strcmp(name, "gless_mixed")) g_gless_mixed = value;
     else if (!strcmp(name, "tourn_fp32")) gnb_set_tourn_group(value);
     else if (!strcmp(name, "tourn_warp")) gnb_set_tourn_warp(value);
+    else if (!strcmp(name, "tournq_cplx_min_m")) gnb_set_tournq_cplx_min_m(value);
     else if (!strncmp(name, "rk_", 3)) gnb_rec_set_option(name, value);
     else return GNB_ERR_ARG;
     return GNB_OK;

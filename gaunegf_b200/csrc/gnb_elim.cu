@@ -1450,6 +1450,7 @@ void gnb_set_tourn_group(int g) { g_tourn_fp32 = g != 0; }
 static int g_tournq_cplx_min_m = 400;
 static int g_tourn_warp = 249;     // bit mask: warp-synchronous tournament kernels (k_tournw / k_tournq) where they apply, see below
 void gnb_set_tourn_warp(int on) { g_tourn_warp = on; }
+void gnb_set_tournq_cplx_min_m(int m) { g_tournq_cplx_min_m = m; }
 long gnb_launch_tournament(cudaStream_t st, int M, int N, const cplx* A, long strideA, int ld, int c0, int w,
                            int* cand0, int* cand1, int cand_stride, cplx* LU, int* moves, int* perm, int perm_stride,
                            int* info, int real_panel, int mixr) {

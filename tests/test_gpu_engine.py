@@ -263,7 +263,13 @@ def _set(ctx, **opts):
 
 
 DEFAULTS = dict(engine_rec=1, rk_m3=1, rk_m3_mink=64, rk_kskip=1, contacts_last=1, tourn_fp32=1, rec_streams=2,
-                rk_real=1, mixed_layout=1, rk_strip=1, rk_wsolve_mma=1, rk_fin_mma=1)
+                rk_real=1, mixed_layout=1, rk_strip=1, rk_wsolve_mma=1, rk_fin_mma=1, rk_augreal=1, rk_wskip=1,
+                rk_wsolve_fused=1, rk_lookahead=0, rk_la_ctas=1, rk_cs=4, tourn_warp=249, gless_mixed=1, rk_tcap_k=0,
+                rk_lowprio=0, tournq_cplx_min_m=400)
+# round-2 switches: (option, value A, value B)
+ROUND2_SWITCHES = [("rk_augreal", 1, 0), ("rk_wskip", 1, 0), ("rk_wsolve_fused", 1, 0), ("rk_lookahead", 0, 1),
+                   ("rk_cs", 4, 3), ("tourn_warp", 249, 1), ("tourn_warp", 249, 9), ("tourn_warp", 249, 25),
+                   ("gless_mixed", 1, 0), ("rk_tcap_k", 0, 256), ("tournq_cplx_min_m", 400, 1)]
 
 
 @pytest.mark.parametrize("N,nc", [(96, 8), (100, 7), (256, 16), (416, 33), (600, 40)])
@@ -311,6 +317,37 @@ def test_recursive_engine_switches_do_not_change_results(ctx, opt):
     a, b = list(res.values())
     for x, y in zip(a, b):
         assert relerr(x, y) < TOL
+
+
+@pytest.mark.parametrize("opt,va,vb", ROUND2_SWITCHES)
+def test_round2_switches_do_not_change_results(ctx, opt, va, vb):
+    """real arithmetic on the augmented columns, the skipped W write, the fused leaf pair, the look-ahead, cache hints, the
+    tournament kernels (k_tournw / k_tournq with 2 or 4 rows per lane, FP64 or FP32-order final round), the mixed layout
+    of GrLessInt and short-lived rank-K CTAs are performance switches: T(E), the GrLessInt integral and a complex-F
+    T(E) (complex panels) must stay within the parity tolerance, and match the oracle"""
+    N, nc = 416, 33
+    F, S, inds, sig = const_system(ctx, N, nc, seed=13)
+    Er = np.linspace(-0.9, 0.9, 130)
+    wr = np.linspace(0.1, 0.3, 130)
+    res = {}
+    try:
+        for v in (va, vb):
+            _set(ctx, **{opt: v})
+            ctx.set_system(F, S)
+            out = [ctx.transmission(Er, 0, -1), ctx.gless_int(Er, wr, -1), ctx.gless_int(Er, wr, 0)]
+            Fc, _ = sy.hermitian_pair(N, seed=13, complex_F=True)
+            ctx.set_system(Fc, S)
+            out.append(ctx.transmission(Er[:40], 0, -1))
+            res[v] = out
+    finally:
+        _set(ctx, **DEFAULTS)
+    for x, y in zip(res[va], res[vb]):
+        assert relerr(x, y) < TOL
+    st = sig[0] + sig[1]
+    g1 = 1j * (sig[0] - sig[0].conj().T)
+    g2 = 1j * (sig[1] - sig[1].conj().T)
+    Tref = np.array([O.transmission_restricted(e, F, S, st, g1, g2) for e in Er[::13]])
+    assert relerr(res[vb][0][::13], Tref) < TOL
 
 
 def test_full_size_properties_n1024(ctx):
