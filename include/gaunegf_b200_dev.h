@@ -13,8 +13,12 @@
 extern "C" {
 #endif
 
-/* name = value; names: engine_rec, rec_streams, small_fused, small_reg, small_cluster, small_wide, chain_joint,
- * chain_compact, chain_fused, contacts_last, mixed_layout, tourn_fp32, two_level, gemm_pipe, gemm_bm, rk_* (gnb_rec.cu) */
+/* name = value; names: engine_rec, rec_streams, rec_stream_min_m, rec_stagger_us, small_fused, small_reg, small_cluster,
+ * small_cluster_maxm, small_cl_relaxed, small_wide, chain_joint, chain_compact, contacts_last, mixed_layout, gless_mixed,
+ * tourn_fp32, tourn_warp (bit mask of the tournament kernels, gnb_elim.cu), tournq_cplx_min_m, two_level, gemm_pipe, gemm_bm,
+ * rk_* (gnb_rec.cu: rk_m3, rk_m3_mink, rk_kskip, rk_strip, rk_real, rk_wsolve_mma, rk_wsolve_areal, rk_wsolve_fused, rk_rp2,
+ * rk_fin_mma, rk_sms, rk_wskip, rk_augreal, rk_cs, rk_tcap_k, rk_lowprio, rk_lookahead, rk_la_mink, rk_la_ctas).  Defaults are
+ * the measured best; DESIGN.md section 5 lists what each one measured. */
 int gnb_dev_set_option(const char* name, int value);
 /* CUDA-event trace of every launch of the recursive engine (tools/trace_elim.py) */
 int gnb_dev_trace_start(void);
