@@ -35,6 +35,7 @@ SIGNATURES = {
     "gnb_set_system": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
     "gnb_set_system_cached": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp]),
     "gnb_system_differs": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "gnb_set_system_known": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "gnb_sigma_clear": (C.c_int, [_vp]),
     "gnb_sigma_set_dense0": (C.c_int, [_vp, _vp, C.c_int]),
     "gnb_sigma_add_const_block": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -207,14 +208,27 @@ class Context:
         return c128(a), 0
 
     def system_differs(self, F, S, full=True):
-        """read-only: do (F, S) differ from the resident pair?  full=False: size + strided sample (parallel.set_system)"""
+        """read-only: which of (F, S) differ from the resident pair?  bit 0 = F, bit 1 = S (3: nothing comparable resident).
+        full=False: size + strided sample (parallel.set_system)"""
         Fa, Sa = np.asarray(F), np.asarray(S)
         if Fa.shape != Sa.shape or Fa.ndim != 2 or Fa.shape[0] != Fa.shape[1]:
-            return True
+            return 3
         (Fc, fr), (Sc, sr) = self._as_input(Fa), self._as_input(Sa)
-        d = C.c_int(1)
+        d = C.c_int(3)
         self.check(self.lib.gnb_system_differs(self.h, Fc.shape[0], ptr(Fc), ptr(Sc), fr | (sr << 1), int(bool(full)), C.byref(d)))
-        return bool(d.value)
+        return int(d.value)
+
+    def set_system_known(self, F, S, changed):
+        """set_system without the comparison: `changed` (bit 0 = F, bit 1 = S) names what to copy and upload"""
+        Fa, Sa = np.asarray(F), np.asarray(S)
+        assert Fa.shape == Sa.shape and Fa.ndim == 2 and Fa.shape[0] == Fa.shape[1], "F and S must be square matrices of one size"
+        (Fc, fr), (Sc, sr) = self._as_input(Fa), self._as_input(Sa)
+        self.N = Fc.shape[0]
+        up = C.c_int(0)
+        self.check(self.lib.gnb_set_system_known(self.h, self.N, ptr(Fc), ptr(Sc), fr | (sr << 1), int(changed) & 3, C.byref(up)))
+        self.last_system_upload = up.value
+        if up.value == 0:
+            self.system_uploads_skipped += 1
 
     def set_system_device(self, N, F_ptr, S_ptr):
         self.N = int(N)

@@ -268,7 +268,7 @@ static void shadow_pass(const double* src, bool src_real, double* shadow, size_t
 // gaunegf_b200/parallel.py).  differs: 0 / 1.
 extern "C" int gnb_system_differs(gnb_ctx* c, int N, const double* F, const double* S, int real_input, int full, int* differs) {
     if (!c || N <= 0 || !F || !S || !differs) return gnb_fail(c, GNB_ERR_ARG, "system_differs: bad arguments");
-    *differs = 1;
+    *differs = 3;
     if (c->shadow_N != N || c->N != N || !c->hF || !c->hS) return GNB_OK;
     if (c->shadow_ev) GNB_CK(cudaEventSynchronize(c->shadow_ev));
     const size_t n = (size_t)N * N;
@@ -280,16 +280,19 @@ extern "C" int gnb_system_differs(gnb_ctx* c, int N, const double* F, const doub
     const size_t step = full ? 1 : 1021;                     // sample: every 1021st element (prime: walks rows and columns)
     std::vector<char> diff(T, 0);
     auto work = [&](int t) {
-        bool d = false;
-        for (int m = 0; m < 2 && !d; m++) {
+        int bits = 0;
+        for (int m = 0; m < 2; m++) {
             const size_t lo = n * t / T, hi = n * (t + 1) / T;
-            if (full && !re[m]) { d = memcmp(mats[m] + 2 * lo, shad[m] + 2 * lo, (hi - lo) * 16) != 0; continue; }
-            for (size_t i = lo; i < hi; i += step) {
-                if (re[m]) d |= (shad[m][2 * i] != mats[m][i]) | (shad[m][2 * i + 1] != 0.0);
-                else d |= (shad[m][2 * i] != mats[m][2 * i]) | (shad[m][2 * i + 1] != mats[m][2 * i + 1]);
-            }
+            bool d = false;
+            if (full && !re[m]) d = memcmp(mats[m] + 2 * lo, shad[m] + 2 * lo, (hi - lo) * 16) != 0;
+            else
+                for (size_t i = lo; i < hi; i += step) {
+                    if (re[m]) d |= (shad[m][2 * i] != mats[m][i]) | (shad[m][2 * i + 1] != 0.0);
+                    else d |= (shad[m][2 * i] != mats[m][2 * i]) | (shad[m][2 * i + 1] != mats[m][2 * i + 1]);
+                }
+            bits |= (d ? 1 : 0) << m;
         }
-        diff[t] = d;
+        diff[t] = (char)bits;
     };
     std::vector<std::thread> th;
     for (int t = 1; t < T; t++) th.emplace_back(work, t);
@@ -297,7 +300,35 @@ extern "C" int gnb_system_differs(gnb_ctx* c, int N, const double* F, const doub
     for (auto& x : th) x.join();
     int any = 0;
     for (int t = 0; t < T; t++) any |= diff[t];
-    *differs = any;
+    *differs = any;                                          // bit 0: F differs, bit 1: S differs
+    return GNB_OK;
+}
+
+// set_system when the caller already knows which of the two matrices changed (gnb_system_differs, agreed between the ranks):
+// changed bit 0 = F, bit 1 = S.  The named matrices are copied into the shadows and uploaded without a comparison, the others
+// are not touched.  Falls back to the comparing call when there is no valid shadow of this size.
+static void shadow_pass(const double* src, bool src_real, double* shadow, size_t ndoubles, bool have_shadow,
+                        std::vector<char>& real_slice, bool* changed, bool* real);
+extern "C" int gnb_set_system_cached(gnb_ctx* c, int N, const double* F, const double* S, int real_input, int* uploaded);
+extern "C" int gnb_set_system_known(gnb_ctx* c, int N, const double* F, const double* S, int real_input, int changed, int* uploaded) {
+    if (!c || N <= 0 || !F || !S) return gnb_fail(c, GNB_ERR_ARG, "set_system: bad arguments");
+    if (c->shadow_N != N || c->N != N || !c->hF || !c->hS) return gnb_set_system_cached(c, N, F, S, real_input, uploaded);
+    cudaSetDevice(c->device);
+    if (c->shadow_ev) GNB_CK(cudaEventSynchronize(c->shadow_ev));
+    const size_t bytes = (size_t)N * N * sizeof(cplx);
+    bool ch, reF = true, reS = true;
+    int rc;
+    if (changed & 1) {
+        shadow_pass(F, (real_input & 1) != 0, static_cast<double*>(c->hF), 2 * (size_t)N * N, false, c->realF_slice, &ch, &reF);
+        if ((rc = put(c, c->dF, c->hF, bytes, GNB_HOST))) return rc;
+    } else for (char r : c->realF_slice) reF &= r != 0;
+    if (changed & 2) {
+        shadow_pass(S, (real_input & 2) != 0, static_cast<double*>(c->hS), 2 * (size_t)N * N, false, c->realS_slice, &ch, &reS);
+        if ((rc = put(c, c->dS, c->hS, bytes, GNB_HOST))) return rc;
+    } else for (char r : c->realS_slice) reS &= r != 0;
+    c->real_FS = reF && reS;
+    if (changed & 3) GNB_CK(cudaEventRecord(c->shadow_ev, c->stream));
+    if (uploaded) *uploaded = changed & 3;
     return GNB_OK;
 }
 

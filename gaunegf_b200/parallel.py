@@ -59,14 +59,13 @@ def set_system(ctx, F, S):
         return ctx.set_system(F, S)
     import torch
     import torch.distributed as dist
-    differs = ctx.system_differs(F, S, full=(rank == 0))
+    bits = ctx.system_differs(F, S, full=(rank == 0))      # bit 0: F differs, bit 1: S differs
     dev = ("cuda:%d" % ctx.device) if dist.get_backend() == "nccl" else "cpu"
-    flag = torch.tensor([1 if differs else 0], dtype=torch.int32, device=dev)
+    flag = torch.tensor([bits & 1, (bits >> 1) & 1], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-    if int(flag.item()):
-        return ctx.set_system(F, S)
-    ctx.last_system_upload = 0
-    ctx.system_uploads_skipped += 1
+    f, s = (int(v) for v in flag.tolist())
+    # what changed is copied and uploaded without another comparison; an unchanged matrix is not read at all
+    return ctx.set_system_known(F, S, f | (s << 1))
 
 
 def _device_buffers(N, device):

@@ -73,8 +73,11 @@ int gnb_set_system_cached(gnb_ctx* ctx, int N, const double* F, const double* S,
 /* Read-only test whether (F, S) differ from the resident pair of gnb_set_system_cached.  full = 1: every element; full = 0:
  * size and a strided sample only.  With one process per GPU every rank receives the same F and S: rank 0 runs the full
  * comparison, the others the sample, and one flag is agreed on (gaunegf_b200/parallel.py) instead of N full passes over host
- * memory that all ranks of a box share.  differs: 0 / 1. */
+ * memory that all ranks of a box share.  differs: bit 0 = F differs, bit 1 = S differs (3 when there is nothing resident). */
 int gnb_system_differs(gnb_ctx* ctx, int N, const double* F, const double* S, int real_input, int full, int* differs);
+/* gnb_set_system_cached without the comparison, for a caller that knows which matrices changed (changed: bit 0 = F,
+ * bit 1 = S, e.g. the flags the ranks agreed on): those are copied into the shadows and uploaded, the others stay. */
+int gnb_set_system_known(gnb_ctx* ctx, int N, const double* F, const double* S, int real_input, int changed, int* uploaded);
 
 /* ---- self-energy description ------------------------------------------------------------------
  * Sigma_tot(E) = Sigma0 + sum_c scatter(inds_c, blk_c(E)).  Contacts are numbered 0..nc-1; the

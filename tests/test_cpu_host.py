@@ -165,14 +165,14 @@ class FakeCtx:
     def system_differs(self, F, S, full=True):
         self.asked.append(full)
         return self.full_says if full else self.sample_says
-    def set_system(self, F, S):
-        self.uploads += 1
-for full_says, sample_says, expect in ((False, False, 0), (True, False, 1), (False, True, 1)):
+    def set_system_known(self, F, S, changed):
+        self.uploads.append(changed)
+for full_says, sample_says, expect in ((0, 0, 0), (1, 0, 1), (0, 2, 2), (2, 1, 3), (3, 3, 3)):
     c = FakeCtx(full_says, sample_says)
+    c.uploads = []
     parallel.set_system(c, None, None)
     assert c.asked == [rank == 0], "rank 0 compares in full, the others sample"
-    assert c.uploads == expect, (rank, full_says, sample_says, c.uploads)
-    assert c.system_uploads_skipped == 1 - expect
+    assert c.uploads == [expect], (rank, full_says, sample_says, c.uploads)     # every rank acts on the agreed bits
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """

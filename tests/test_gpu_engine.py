@@ -156,8 +156,20 @@ def test_set_system_cached_uploads_only_what_changed(ctx):
     assert relerr(ctx.transmission(Er, 0, -1), np.array([O.transmission_restricted(e, Fc, S2, st, g1, g2) for e in Er])) < TOL
     ctx.set_system(F2, S2)                                 # back to real input: the real-structure shortcut applies again
     assert relerr(ctx.transmission(Er, 0, -1), np.array([O.transmission_restricted(e, F2, S2, st, g1, g2) for e in Er])) < TOL
+    # read-only comparison (what rank 0 runs for all ranks) and the comparison-free update that follows the agreed flags
+    assert ctx.system_differs(F2, S2) == 0 and ctx.system_differs(F2, S2, full=False) == 0
+    F3 = F2.copy(); F3[N - 1, N - 2] += 1e-9
+    S3 = S2.copy(); S3[0, 0] *= 1.0005
+    assert ctx.system_differs(F3, S2) == 1 and ctx.system_differs(F2, S3) == 2 and ctx.system_differs(F3, S3) == 3
+    assert ctx.system_differs(F2, S3, full=False) == 2                       # element 0 is in the sample
+    ctx.set_system_known(F3, S3, 2)                                           # only S is taken over ...
+    assert ctx.last_system_upload == 2 and ctx.system_differs(F3, S3) == 1    # ... F is still the old one
+    ctx.set_system_known(F3, S3, 1)
+    assert ctx.system_differs(F3, S3) == 0
+    assert relerr(ctx.green(E), np.array([O.gr_matrix(st, e, F3, S3) for e in E])) < TOL
     Fs, Ss = sy.hermitian_pair(40, seed=2)
-    ctx.set_system(Fs, Ss)
+    assert ctx.system_differs(Fs, Ss) == 3                                    # another size: nothing comparable
+    ctx.set_system_known(Fs, Ss, 0)                                           # falls back to the comparing call
     assert ctx.last_system_upload == 3 and ctx.N == 40
 
 
