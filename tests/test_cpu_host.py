@@ -156,6 +156,21 @@ assert np.allclose(D, np.outer(E.real, np.arange(3.0)))
 # fewer energies than ranks: one rank gets an empty slice
 one = parallel.sharded_matrix_sum(N, E[:1], w[:1], partial)
 assert np.max(np.abs(one - w[0] * f(E[0]))) < 1e-12
+# several weighted sums in one batch (the nested levels of the adaptive quadrature): every segment is sharded on its own,
+# ragged and empty segments included, one all-reduce for all of them
+ends = [3, 3, 4, 11]
+def partial_seg(El, wl, local_ends, out):
+    res, lo = [], 0
+    for hi in local_ends:
+        res.append(sum((wk * f(ek) for ek, wk in zip(El[lo:hi], wl[lo:hi])), np.zeros((N, N), complex)))
+        lo = int(hi)
+    return np.array(res)
+sums = parallel.sharded_matrix_sums(N, E, w, ends, partial_seg)
+lo = 0
+for s_, hi in enumerate(ends):
+    ref_s = sum((wk * f(ek) for ek, wk in zip(E[lo:hi], w[lo:hi])), np.zeros((N, N), complex))
+    assert np.max(np.abs(sums[s_] - ref_s)) < 1e-12 * max(1.0, np.max(np.abs(ref_s))), ("segment", s_)
+    lo = hi
 # parallel.set_system: rank 0's full comparison (or any rank's sanity sample) decides for every rank
 class FakeCtx:
     device = 0
