@@ -405,11 +405,15 @@ def run_ours(args):
 
     if rank == 0:
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_alg = None, None, None
         for name in ("r02_rk_gemm_ncu.json", "r01c_rk_gemm_ncu.json"):
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", name))).get("dram_bytes_per_launch")
-                traffic_src = f"profiles/{name} (ncu --set full capture of this kernel; static, not re-measured in this run)"
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                traffic = prof.get("dram_bytes_per_launch")
+                traffic_alg = prof.get("algorithmic_bytes_per_launch")
+                traffic_src = (f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum of the LARGEST launch of the family "
+                               "(top-level far update, K = 512, 625 matrices) from an ncu --set full capture; static, not "
+                               "re-measured in this run; traffic_algorithmic = C tile read + written once + the packed operands once")
                 break
             except Exception:
                 pass
@@ -435,7 +439,7 @@ def run_ours(args):
                                    "the contact orbitals ordered last keep every column left of the contacts exactly real); "
                                    "complex tiles with K >= 64 use 3M arithmetic (3 DMMAs for an 8-flop MAC)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "traffic_source": traffic_src,
+                         "traffic": traffic, "traffic_algorithmic": traffic_alg, "traffic_source": traffic_src,
                          "peak_source": "measured in this run: gnb_dev_fp64_peak (register-resident DMMA.8x8x4 issue loop on every "
                                         "SM, best of ~0.3 s of launches), clocks as in `clocks`",
                          "launches_timed": int(gemm_n),
