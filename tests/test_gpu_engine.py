@@ -126,6 +126,30 @@ def test_segmented_gr_int_equals_separate_calls(ctx, N, nc):
         ctx.gr_int_seg(z, w, [4, 2, 18])
 
 
+@pytest.mark.parametrize("N", [130, 256])
+def test_block_engine_singular_raises(ctx, N):
+    """exactly singular A (zero rows off the contacts) on the block engine: numpy.linalg.LinAlgError like the reference's
+    solve(), on the real-structure T(E) path (FP32 pivot order + FP64 pivot-block inverse detects the zero pivot), the
+    complex Gauss-Jordan path and GrLessInt"""
+    nc = 16
+    Z = np.zeros((N, N))
+    ctx.set_system(Z, Z)
+    ctx.sigma_clear()
+    ctx.sigma_add_const_block(np.arange(nc), -0.1j * np.eye(nc))
+    ctx.sigma_add_const_block(np.arange(N - nc, N), -0.1j * np.eye(nc))
+    E = np.linspace(-0.3, 0.3, 5)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.transmission(E, 0, -1)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.green(E + 0.1j)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.gless_int(E, np.ones(5), -1)
+    # and the context is usable afterwards
+    F, S, inds, sig = const_system(ctx, N, nc, seed=3)
+    st = sig[0] + sig[1]
+    assert relerr(ctx.green(E[:1] + 0.1j)[0], O.gr_matrix(st, E[0] + 0.1j, F, S)) < TOL
+
+
 def test_set_system_cached_uploads_only_what_changed(ctx):
     """gnb_set_system_cached: F and S are compared with the context's pinned shadows; an in-place change of either is
     seen, only the changed matrix is re-sent, and the results follow the new values"""
