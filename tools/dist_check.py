@@ -43,6 +43,17 @@ errs = {
 with contextlib.redirect_stdout(io.StringIO()):
     P = de.densityComplexN(F, S, g, -8.0, 0.0, 36, 0.0, False)
 errs["densityComplexN"] = rel(P, O.densityComplexN(F, S, og, -8.0, 0.0, 36, 0.0))
+# adaptive contour integration: several nested levels per batch, every level sharded on its own (sharded_matrix_sums)
+with contextlib.redirect_stdout(io.StringIO()):
+    Pa = de.densityComplex(F, S, g, -8.0, 0.0, 1e-6, 0.0)
+    Pa_ref = O.densityComplex(F, S, og, -8.0, 0.0, 1e-6, 0.0)
+errs["densityComplex_adaptive"] = rel(Pa, Pa_ref)
+lv = it.GrIntLevels(F, S, g, [(z[:2], w[:2]), (z[2:6], w[2:6]), (z[6:6], w[6:6]), (z[6:], w[6:])])
+errs["GrIntLevels"] = max(rel(lv[0], O.GrInt(F, S, og, z[:2], w[:2])), rel(lv[1], O.GrInt(F, S, og, z[2:6], w[2:6])),
+                          float(np.max(np.abs(lv[2]))), rel(lv[3], O.GrInt(F, S, og, z[6:], w[6:])))
+# the same F, S again: the ranks agree that nothing changed; a changed F is taken over by every rank
+F2 = F.copy(); F2[3, 3] += 0.01
+errs["GrInt_changed_F"] = rel(it.GrInt(F2, S, g, z, w), O.GrInt(F2, S, og, z, w))
 worst = torch.tensor([max(errs.values())], device="cuda", dtype=torch.float64)
 dist.all_reduce(worst, op=dist.ReduceOp.MAX)
 if rank == 0:
